@@ -1,0 +1,180 @@
+/*
+ * pfb.h -- C ABI of libpfb.so, the B200 (sm_100a) particle-filter hot path.
+ *
+ * The reference (pyRecEst v0.9.1, /root/reference) is 100 % Python and has no FFI; the
+ * seam this library plugs into is the set of Python methods listed beside each entry point
+ * (file:line relative to /root/reference).  pyrecest_b200/ binds these symbols with ctypes
+ * (see INTEGRATION.md for the stub a pyRecEst maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named *_dev / x / w / cdf / u / noise ... is DEVICE memory owned by the
+ *     caller (torch); small parameter blocks (pfb_*_params) are HOST structs copied by value.
+ *   - particle records are row-major (n, dim) -- the reference's own `.d` layout --
+ *     element type `dtype` (PFB_F64 default, PFB_F32 storage option); log-weights, weights,
+ *     CDFs, uniforms and all reduction outputs are always float64.
+ *   - the library never allocates, frees or synchronises: scratch comes from `ws`
+ *     (pfb_workspace_bytes), every call is asynchronous on `stream` (a cudaStream_t).
+ *   - return value: 0 = PFB_OK, otherwise a pfb_status; pfb_last_error() gives text
+ *     (thread-local).  Device-detected conditions (all-zero weights, NaN, negative
+ *     likelihood) are reported through the `stats` words the caller reads back.
+ */
+#ifndef PFB_H
+#define PFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
+#define PFB_ABI_VERSION 1
+
+typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
+
+typedef enum {
+  PFB_OK = 0,
+  PFB_ERR_INVALID = 1,      /* bad argument (dim, kind, null pointer, alignment) */
+  PFB_ERR_WORKSPACE = 2,    /* workspace too small */
+  PFB_ERR_CUDA = 3,         /* a CUDA runtime call failed; see pfb_last_error() */
+  PFB_ERR_UNSUPPORTED = 4
+} pfb_status;
+
+/* manifolds / predict modes -------------------------------------------------------------- */
+typedef enum {
+  PFB_PRED_EUCLID = 0,       /* x' = f(x) + n                 euclidean_particle_filter.py:59-69 */
+  PFB_PRED_TORUS_SHIFT = 1,  /* x' = mod(mod(n + mod(f(x))))  hypertoroidal_particle_filter.py:43-56,
+                                abstract_particle_filter.py:49-50, hypertoroidal_wrapped_normal_distribution.py:51-63,109-115 */
+  PFB_PRED_TORUS_ADD = 2,    /* x' = mod(f(x) + mod(n + mu))  abstract_particle_filter.py:44-47 */
+  PFB_PRED_SPHERE_VMF = 3,   /* S^2: VMF(mode = f(x), kappa) draw from (u, z1, z2); pattern of
+                                hyperhemisphere_cart_prod_particle_filter.py:90-95 + scipy _rvs_3d/_rotate_samples */
+  PFB_PRED_SPHERE_ADD = 4    /* x' = (f(x) + n)/|f(x) + n| */
+} pfb_predict_mode;
+
+typedef struct {
+  int32_t mode;              /* pfb_predict_mode */
+  int32_t dim;               /* stored components D */
+  int32_t has_F;             /* 0: identity transition; 1: x -> F x + b (registry LinearTransition) */
+  int32_t has_b;
+  int32_t noise_cols;        /* columns of the noise array E (0 = no noise; 3 for SPHERE_VMF) */
+  int32_t has_A;             /* 1: noise rows are standard normals, n = z A + mu_noise (A is E x D, the
+                                numpy-legacy factor sqrt(s)[:,None] * Vt of svd(C)); 0: rows used as given */
+  int32_t has_mu_noise;
+  int32_t renormalize;       /* SPHERE_VMF: renormalise the rotated draw */
+  double F[PFB_MAXD * PFB_MAXD];   /* row-major */
+  double b[PFB_MAXD];
+  double A[PFB_MAXD * PFB_MAXD];   /* row-major E x D */
+  double mu_noise[PFB_MAXD];
+  double kappa;              /* SPHERE_VMF */
+  double exp_m2k;            /* SPHERE_VMF: exp(-2 kappa), computed by the host like scipy does */
+} pfb_predict_params;
+
+/* likelihood registry ---------------------------------------------------------------------- */
+typedef enum {
+  PFB_LIK_NONE = -1,
+  PFB_LIK_GAUSS = 0,     /* gaussian_distribution.py:43-50 (scipy mvn.pdf)                      */
+  PFB_LIK_WN_MULTI = 1,  /* hypertoroidal_wrapped_normal_distribution.py:65-93, image table      */
+  PFB_LIK_WN_1D = 2,     /* circle/wrapped_normal_distribution.py:59-127 (series until converged) */
+  PFB_LIK_VM = 3,        /* circle/von_mises_distribution.py:42-50                                */
+  PFB_LIK_VMF = 4        /* hypersphere_subset/von_mises_fisher_distribution.py:51-54             */
+} pfb_lik_kind;
+
+typedef struct {
+  int32_t kind;
+  int32_t dim;               /* stored components D */
+  int32_t n_images;          /* WN_MULTI: rows of images_dev */
+  int32_t reserved;
+  double mu[PFB_MAXD];
+  double W[PFB_MAXD * PFB_MAXD]; /* GAUSS / WN_MULTI: whitening matrix (row-major D x D), y = (x - mu) W */
+  double logc;               /* log normalising constant added to every log-likelihood */
+  double kappa;              /* VM / VMF */
+  double sigma;              /* WN_1D */
+  const double* images_dev;  /* WN_MULTI: DEVICE table (n_images, 2D + 1): g_k = P o_k (D), h_k = o_k^T P o_k, o_k (D) */
+} pfb_lik_params;
+
+/* stats words written by the weighting / normalise kernels (device doubles) */
+enum {
+  PFB_STAT_MAX = 0,      /* max_i logw_i                                   */
+  PFB_STAT_SUMEXP = 1,   /* sum_i exp(logw_i - max)                        */
+  PFB_STAT_SUMSQ = 2,    /* sum_i exp(logw_i - max)^2  (ESS = S1^2/S2)     */
+  PFB_STAT_FLAGS = 3,    /* bit0: NaN seen, bit1: all weights zero/-inf    */
+  PFB_STAT_TOTAL = 4,    /* last raw CDF entry c_{N-1}                      */
+  PFB_STAT_COUNT = 8
+};
+
+typedef enum { PFB_SCAN_FAST = 0, PFB_SCAN_SEQEXACT = 1 } pfb_scan_mode;
+typedef enum { PFB_EST_NONE = 0, PFB_EST_SUM = 1, PFB_EST_TRIG = 2 } pfb_est_kind;
+typedef enum { PFB_MOM_MEAN = 0, PFB_MOM_TRIG = 1, PFB_MOM_SCATTER = 2, PFB_MOM_CENTRAL = 3 } pfb_moment_kind;
+
+int pfb_abi_version(void);
+const char* pfb_last_error(void);
+
+/* scratch needed by any entry point for up to n particles (flags, tile states, partials).
+ * The first pfb_workspace_bytes(0) bytes must be zeroed once (pfb_workspace_init). */
+int64_t pfb_workspace_bytes(int64_t n);
+int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream);
+
+/* K(1) predict.  Replaces AbstractParticleFilter.predict_nonlinear
+ * (pyrecest/filters/abstract_particle_filter.py:21-54) and its Euclidean / hypertoroidal
+ * overrides.  x_in may equal x_out (in place). */
+int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t n,
+                const void* x_in, void* x_out, const void* noise, void* stream);
+
+/* K(2) log-likelihood weighting: logw_i = loglik(x_i) + log(w_prev_i) (w_prev NULL = uniform 1/n
+ * is NOT added: a constant shift cancels in the normalisation).  Also reduces max_i into stats[0].
+ * Replaces the likelihood evaluation inside AbstractDiracDistribution.reweigh
+ * (pyrecest/distributions/abstract_dirac_distribution.py:69-80). */
+int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void* x,
+               const double* w_prev, double* logw, double* stats, void* ws, int64_t ws_bytes,
+               void* stream);
+
+/* K(1)+K(2) fused: predict, write x_out, weight the predicted particle. */
+int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
+                       int64_t n, const void* x_in, void* x_out, const void* noise,
+                       double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream);
+
+/* K(3) max / log-sum-exp normalisation: stats <- (max, sum exp, sum exp^2, flags); if w_out
+ * != NULL, w_out_i = exp(logw_i - max) / sumexp  (the posterior weights reweigh() returns). */
+int pfb_normalize(int64_t n, const double* logw, double* w_out, double* stats, void* ws,
+                  int64_t ws_bytes, void* stream);
+
+/* K(4a) inclusive prefix sum of non-negative weights -> raw CDF c (not divided by c_{n-1}).
+ * Input is either w (logw == NULL) or exp(logw_i - stats[PFB_STAT_MAX]) (w == NULL).
+ * PFB_SCAN_SEQEXACT reproduces numpy.cumsum's sequential fp64 rounding bit for bit
+ * (numpy Generator.choice: cdf = p.cumsum(), reached from
+ * pyrecest/_backend/_shared_numpy/random.py:28-29); PFB_SCAN_FAST is a plain blocked scan.
+ * stats[PFB_STAT_TOTAL] <- c_{n-1}. */
+int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const double* logw, double* cdf,
+                 double* stats, void* ws, int64_t ws_bytes, void* stream);
+
+/* K(4b) resampling: idx_j = #{i : fl(c_i / c_{n-1}) <= u_j} (searchsorted side='right', the
+ * division done per comparison so it is the reference's `cdf /= cdf[-1]` bit for bit), then
+ * x_out[j] = x_in[idx_j].  systematic != 0: u_j = (j + u[0]) / n_out computed in-kernel, idx
+ * clamped to n-1.  idx_out (int64) optional.  est_kind: also reduce the resampled particles
+ * (uniform weights 1/n_out) into est_out: PFB_EST_SUM -> mean (D doubles), PFB_EST_TRIG ->
+ * (sum cos, sum sin)/n_out per dim (2D doubles).
+ * Replaces AbstractDiracDistribution.sample (abstract_dirac_distribution.py:82-84) and the
+ * resampling step of update_nonlinear_using_likelihood (abstract_particle_filter.py:122-125). */
+int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                 const double* u, int32_t systematic, const void* x_in, void* x_out,
+                 int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes,
+                 void* stream);
+
+/* K(5) weighted moments (w == NULL: uniform 1/n).  out (doubles):
+ *   PFB_MOM_MEAN    sum w x              (D)      linear_dirac_distribution.py:19-21, hyperspherical_dirac_distribution.py:43-44
+ *   PFB_MOM_TRIG    sum w cos(order x), sum w sin(order x)   (2D)  hypertoroidal_dirac_distribution.py:72-80
+ *   PFB_MOM_SCATTER sum w x x^T          (D*D)    abstract_hypersphere_subset_dirac_distribution.py:18-26
+ *   PFB_MOM_CENTRAL sum w (x-c)(x-c)^T / sum w, c = center (D DEVICE doubles, e.g. a PFB_MOM_MEAN output)  linear_dirac_distribution.py:73-82
+ * plus out[last] = sum w. */
+int pfb_moments(int32_t kind, pfb_dtype dtype, int32_t dim, int64_t n, const void* x,
+                const double* w, int32_t order, const double* center, double* out, void* ws,
+                int64_t ws_bytes, void* stream);
+
+/* element-wise numpy.mod(x, 2 pi) on n*dim values (HypertoroidalDiracDistribution.__init__,
+ * hypertoroidal_dirac_distribution.py:41) */
+int pfb_wrap_2pi(pfb_dtype dtype, int64_t count, const void* x_in, void* x_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB_H */

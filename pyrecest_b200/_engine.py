@@ -1,0 +1,128 @@
+"""Thin typed wrapper: torch CUDA tensors -> raw pointers -> libpfb.so (include/pfb.h).
+
+torch is plumbing here (device memory, streams); every computation of the hot path happens in
+the hand-written kernels behind the C ABI.  One Engine per device; scratch (workspace, stats)
+is owned here and grown on demand, so the C library never allocates."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float64: L.PFB_F64, torch.float32: L.PFB_F32}
+_ENGINES: dict = {}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    def __init__(self, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "pyrecest_b200 needs a CUDA device: the particle-filter path runs only in the sm_100a kernels "
+                "of libpfb.so (there is no CPU fallback)."
+            )
+        self.device = torch.device(device)
+        self.lib = L.lib()
+        self.launches = 0  # kernels of libpfb launched through this engine
+        self._ws = None
+        self._ws_n = -1
+        self.stats = torch.zeros(L.STAT_COUNT, dtype=torch.float64, device=self.device)
+        self._ensure_ws(0)
+
+    # -- scratch --------------------------------------------------------------------------------
+    def _ensure_ws(self, n):
+        if n > self._ws_n:
+            nbytes = int(self.lib.pfb_workspace_bytes(n))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            assert self._ws.data_ptr() % 256 == 0
+            self._ws_n = n
+            L.check(self.lib.pfb_workspace_init(_ptr(self._ws), nbytes, _stream(self.device)))
+        return _ptr(self._ws), self._ws.numel()
+
+    def scan_error_flags(self):
+        """debug word of the sequential-exact scan (0 = all invariants held)."""
+        return int(self._ws[8:12].view(torch.int32).item())
+
+    # -- kernels -----------------------------------------------------------------------------------
+    def predict(self, params, x_in, x_out, noise):
+        n = x_in.shape[0]
+        L.check(self.lib.pfb_predict(C.byref(params), _DT[x_in.dtype], n, _ptr(x_in), _ptr(x_out), _ptr(noise),
+                                     _stream(self.device)))
+        self.launches += 1
+
+    def loglik(self, lik, x, logw, w_prev=None, stats=None):
+        n = x.shape[0]
+        ws, wsb = self._ensure_ws(0)
+        st = self.stats if stats is None else stats
+        L.check(self.lib.pfb_loglik(C.byref(lik), _DT[x.dtype], n, _ptr(x), _ptr(w_prev), _ptr(logw), _ptr(st), ws,
+                                    wsb, _stream(self.device)))
+        self.launches += 1
+
+    def predict_loglik(self, params, lik, x_in, x_out, noise, logw, stats=None):
+        n = x_in.shape[0]
+        ws, wsb = self._ensure_ws(0)
+        st = self.stats if stats is None else stats
+        L.check(self.lib.pfb_predict_loglik(C.byref(params), C.byref(lik), _DT[x_in.dtype], n, _ptr(x_in),
+                                            _ptr(x_out), _ptr(noise), _ptr(logw), _ptr(st), ws, wsb,
+                                            _stream(self.device)))
+        self.launches += 1
+
+    def normalize(self, logw, w_out=None, stats=None):
+        n = logw.shape[0]
+        ws, wsb = self._ensure_ws(0)
+        st = self.stats if stats is None else stats
+        L.check(self.lib.pfb_normalize(n, _ptr(logw), _ptr(w_out), _ptr(st), ws, wsb, _stream(self.device)))
+        self.launches += 1 if w_out is None else 2
+
+    def scan(self, cdf, w=None, logw=None, exact=True, stats=None):
+        n = cdf.shape[0]
+        ws, wsb = self._ensure_ws(n)
+        st = self.stats if stats is None else stats
+        L.check(self.lib.pfb_scan_cdf(L.SCAN_SEQEXACT if exact else L.SCAN_FAST, n, _ptr(w), _ptr(logw), _ptr(cdf),
+                                      _ptr(st), ws, wsb, _stream(self.device)))
+        self.launches += 1
+
+    def resample(self, cdf, u, x_in, x_out, n_out, dim, systematic=False, idx_out=None, est_kind=L.EST_NONE,
+                 est_out=None):
+        n = cdf.shape[0]
+        ws, wsb = self._ensure_ws(0)
+        dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        L.check(self.lib.pfb_resample(dt, dim, n, n_out, _ptr(cdf), _ptr(u), 1 if systematic else 0, _ptr(x_in),
+                                      _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
+                                      _stream(self.device)))
+        self.launches += 1
+
+    def moments(self, kind, x, dim, w=None, order=1, center=None, out=None):
+        n = x.shape[0]
+        ws, wsb = self._ensure_ws(0)
+        if out is None:
+            out = torch.empty(dim * dim + 2 * dim + 2, dtype=torch.float64, device=self.device)
+        L.check(self.lib.pfb_moments(kind, _DT[x.dtype], dim, n, _ptr(x), _ptr(w), order, _ptr(center), _ptr(out),
+                                     ws, wsb, _stream(self.device)))
+        self.launches += 1
+        return out
+
+    def wrap_2pi(self, x_in, x_out):
+        L.check(self.lib.pfb_wrap_2pi(_DT[x_in.dtype], x_in.numel(), _ptr(x_in), _ptr(x_out), _stream(self.device)))
+        self.launches += 1
+
+
+def engine(device=None) -> Engine:
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    key = str(device)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device)
+    return _ENGINES[key]

@@ -1,0 +1,113 @@
+"""ctypes binding of libpfb.so (include/pfb.h).  No torch types cross this boundary: only raw
+device pointers, sizes and the CUDA stream handle.
+
+The library is REQUIRED: there is no CPU or pure-PyTorch fallback.  If libpfb.so is missing or
+a symbol is absent, importing this module's `lib()` raises immediately."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
+CSRC = os.path.join(HERE, "csrc")
+
+PFB_MAXD = 6
+PFB_F64, PFB_F32 = 0, 1
+# predict modes
+PRED_EUCLID, PRED_TORUS_SHIFT, PRED_TORUS_ADD, PRED_SPHERE_VMF, PRED_SPHERE_ADD = range(5)
+# likelihood kinds
+LIK_GAUSS, LIK_WN_MULTI, LIK_WN_1D, LIK_VM, LIK_VMF = range(5)
+# stats words
+STAT_MAX, STAT_SUMEXP, STAT_SUMSQ, STAT_FLAGS, STAT_TOTAL, STAT_COUNT = 0, 1, 2, 3, 4, 8
+SCAN_FAST, SCAN_SEQEXACT = 0, 1
+EST_NONE, EST_SUM, EST_TRIG = 0, 1, 2
+MOM_MEAN, MOM_TRIG, MOM_SCATTER, MOM_CENTRAL = 0, 1, 2, 3
+
+
+class PredictParams(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("dim", C.c_int32), ("has_F", C.c_int32), ("has_b", C.c_int32),
+        ("noise_cols", C.c_int32), ("has_A", C.c_int32), ("has_mu_noise", C.c_int32),
+        ("renormalize", C.c_int32),
+        ("F", C.c_double * (PFB_MAXD * PFB_MAXD)), ("b", C.c_double * PFB_MAXD),
+        ("A", C.c_double * (PFB_MAXD * PFB_MAXD)), ("mu_noise", C.c_double * PFB_MAXD),
+        ("kappa", C.c_double), ("exp_m2k", C.c_double),
+    ]
+
+
+class LikParams(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("dim", C.c_int32), ("n_images", C.c_int32), ("reserved", C.c_int32),
+        ("mu", C.c_double * PFB_MAXD), ("W", C.c_double * (PFB_MAXD * PFB_MAXD)),
+        ("logc", C.c_double), ("kappa", C.c_double), ("sigma", C.c_double),
+        ("images_dev", C.c_void_p),
+    ]
+
+
+_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
+# name -> (restype, argtypes); every symbol include/pfb.h declares
+SIGNATURES = {
+    "pfb_abi_version": (C.c_int, []),
+    "pfb_last_error": (C.c_char_p, []),
+    "pfb_workspace_bytes": (_i64, [_i64]),
+    "pfb_workspace_init": (C.c_int, [_vp, _i64, _vp]),
+    "pfb_predict": (C.c_int, [C.POINTER(PredictParams), C.c_int, _i64, _vp, _vp, _vp, _vp]),
+    "pfb_loglik": (C.c_int, [C.POINTER(LikParams), C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_predict_loglik": (C.c_int, [C.POINTER(PredictParams), C.POINTER(LikParams), C.c_int, _i64, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_normalize": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_scan_cdf": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_resample": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+class PfbError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libpfb.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise PfbError("building libpfb.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library with typed entry points.  Raises if the CUDA library is not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PfbError(
+                f"{LIB_PATH} not found: the CUDA library is required (no fallback). "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C pyrecest_b200/csrc`."
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        if handle.pfb_abi_version() != 1:
+            raise PfbError("libpfb ABI version mismatch")
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().pfb_last_error().decode("utf-8", "replace")
+        if rc == 4:
+            raise NotImplementedError(msg)
+        if rc == 1:
+            raise ValueError(msg)
+        raise PfbError(f"libpfb error {rc}: {msg}")

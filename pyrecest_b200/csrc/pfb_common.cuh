@@ -1,0 +1,236 @@
+// Shared device/host helpers for libpfb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pfb.h"
+
+namespace pfb {
+
+constexpr int kThreads = 256;            // CTA size of the streaming kernels
+constexpr int kMaxPartialBlocks = 4096;  // upper bound on reduction partials per launch
+constexpr double kTwoPi = 6.283185307179586476925286766559;  // == 2.0 * math.pi in fp64
+
+// ---- error text (thread-local) ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define PFB_CUDA_OK(expr)                                   \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return pfb::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define PFB_LAUNCH_OK(name)                                   \
+  do {                                                        \
+    cudaError_t _e = cudaGetLastError();                      \
+    if (_e != cudaSuccess) return pfb::cuda_fail(_e, name);   \
+  } while (0)
+
+int sm_count();
+
+// ---- workspace layout --------------------------------------------------------------------
+// [0, 256)            : unsigned int counters (zeroed once by pfb_workspace_init, self-cleaning)
+// [256, +partials)    : kMaxPartialBlocks * 64 doubles of reduction partials
+// [.., +tiles)        : scan tile state (flags re-zeroed by every scan call)
+constexpr int64_t kWsCounters = 256;
+constexpr int64_t kPartialDoubles = 64;  // doubles per block partial (>= D*D + D + 1 ...)
+constexpr int64_t kWsPartials = (int64_t)kMaxPartialBlocks * kPartialDoubles * 8;
+constexpr int kScanTile = 2048;          // elements per scan tile
+// per tile: flagA, sumA_agg, sumA_incl, flagB, agg_even, agg_odd, incl  (7 x 8 bytes) -> pad to 64
+constexpr int64_t kTileStateBytes = 64;
+constexpr int kGuideShift = 3;           // guide table: one bucket per 2^3 = 8 cdf entries (rounded to pow2)
+
+inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
+inline int64_t ws_header() { return kWsCounters + kWsPartials; }
+
+struct Workspace {
+  unsigned int* counters;
+  double* partials;
+  unsigned char* tiles;
+  int64_t tile_bytes;
+};
+int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out);
+
+// ---- numpy.mod(x, 2*pi) ----------------------------------------------------------------------
+// numpy/_core/src/npymath: mod = fmod(a, b); if (mod) { if ((b < 0) != (mod < 0)) mod += b; }
+// else mod = copysign(0, b).   fmod is exact, the add is one IEEE rounding (can return 2*pi).
+__device__ __forceinline__ double np_mod_2pi(double a) {
+  double m = fmod(a, kTwoPi);
+  if (m != 0.0) {
+    if (m < 0.0) m += kTwoPi;
+  } else {
+    m = 0.0;  // +0.0 also for -0.0 / negative multiples
+  }
+  return m;
+}
+
+// ---- record I/O ---------------------------------------------------------------------------
+// Particle records are row-major (n, D).  v1: straight per-thread loads; consecutive lanes read
+// consecutive records so a warp touches one contiguous 32*D*sizeof(T) byte span.
+template <typename T, int D>
+__device__ __forceinline__ void load_rec(const T* __restrict__ base, int64_t i, double (&r)[D]) {
+  const T* p = base + i * D;
+  if constexpr (sizeof(T) == 8 && D % 2 == 0) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) {
+      double2 v = __ldg(q + c);
+      r[2 * c] = v.x;
+      r[2 * c + 1] = v.y;
+    }
+  } else if constexpr (sizeof(T) == 4 && D % 4 == 0) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      float4 v = __ldg(q + c);
+      r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+  } else if constexpr (sizeof(T) == 4 && D % 2 == 0) {
+    const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) {
+      float2 v = __ldg(q + c);
+      r[2 * c] = v.x; r[2 * c + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) r[c] = (double)__ldg(p + c);
+  }
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void store_rec(T* __restrict__ base, int64_t i, const double (&r)[D]) {
+  T* p = base + i * D;
+  if constexpr (sizeof(T) == 8 && D % 2 == 0) {
+    double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) q[c] = make_double2(r[2 * c], r[2 * c + 1]);
+  } else if constexpr (sizeof(T) == 4 && D % 4 == 0) {
+    float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c)
+      q[c] = make_float4((float)r[4 * c], (float)r[4 * c + 1], (float)r[4 * c + 2], (float)r[4 * c + 3]);
+  } else if constexpr (sizeof(T) == 4 && D % 2 == 0) {
+    float2* q = reinterpret_cast<float2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) q[c] = make_float2((float)r[2 * c], (float)r[2 * c + 1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) p[c] = (T)r[c];
+  }
+}
+
+// ---- warp / block reductions ------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum K values per thread across the CTA; result valid in thread 0 (array `v` is overwritten).
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* smem /* >= K * 32 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) smem[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = (lane < nwarp) ? smem[k * 32 + lane] : 0.0;
+      v[k] = warp_sum(x);
+    }
+  }
+}
+
+__device__ __forceinline__ double block_max(double v, double* smem /* >= 32 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double x = (lane < nwarp) ? smem[lane] : -INFINITY;
+  return warp_max(x);  // valid in warp 0; broadcast by caller if needed
+}
+
+// True (for every thread of the CTA) in the last CTA of the grid to arrive.  Call after the
+// CTA's partial results were written to global memory by any of its threads.
+__device__ __forceinline__ bool block_is_last(unsigned int* counter) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *counter = 0u;  // self-cleaning for the next launch on this stream
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+// grid sizing for streaming kernels: enough CTAs for ~8 resident per SM, capped for the partials
+inline int stream_grid(int64_t n, int per_thread = 1) {
+  int64_t want = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// ---- acquire / release helpers for the look-back scans ------------------------------------------
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_s64(long long* p, long long v) {
+  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_relaxed_s64(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+}  // namespace pfb
+
+// dispatch helpers -------------------------------------------------------------------------------
+#define PFB_DISPATCH_DIM(dim, ...)                                  \
+  switch (dim) {                                                    \
+    case 1: { constexpr int D = 1; __VA_ARGS__; } break;            \
+    case 2: { constexpr int D = 2; __VA_ARGS__; } break;            \
+    case 3: { constexpr int D = 3; __VA_ARGS__; } break;            \
+    case 4: { constexpr int D = 4; __VA_ARGS__; } break;            \
+    case 5: { constexpr int D = 5; __VA_ARGS__; } break;            \
+    case 6: { constexpr int D = 6; __VA_ARGS__; } break;            \
+    default: pfb::set_error("dim %d outside 1..%d", (int)(dim), PFB_MAXD); return PFB_ERR_INVALID; \
+  }
+
+#define PFB_DISPATCH_DTYPE(dtype, ...)                              \
+  if ((dtype) == PFB_F64) { using T = double; __VA_ARGS__; }        \
+  else if ((dtype) == PFB_F32) { using T = float; __VA_ARGS__; }    \
+  else { pfb::set_error("bad dtype %d", (int)(dtype)); return PFB_ERR_INVALID; }

@@ -1,0 +1,521 @@
+// K(1) predict, K(2) log-likelihood weighting, and their fusion.
+//
+// One thread per particle record (row-major (n, D)), grid-stride.  Arithmetic is float64
+// whatever the storage type.  Operation order follows oracle/pf_oracle.py so that the pure
+// add / numpy.mod paths are bit-exact (the library is compiled with -fmad=false; the fused
+// multiply-adds that are wanted are written explicitly).
+#include "pfb_common.cuh"
+
+namespace pfb {
+
+// ---------------------------------------------------------------------------------------------
+// predict
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void apply_transition(const pfb_predict_params& p, const double (&x)[D],
+                                                 double (&y)[D]) {
+  if (p.has_F) {
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double acc = p.F[r * D] * x[0];
+#pragma unroll
+      for (int c = 1; c < D; ++c) acc = fma(p.F[r * D + c], x[c], acc);
+      y[r] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < D; ++r) y[r] = x[r];
+  }
+  if (p.has_b) {
+#pragma unroll
+    for (int r = 0; r < D; ++r) y[r] += p.b[r];
+  }
+}
+
+// noise row in state space: rows as given, or z A (+ mu) for standard-normal input
+template <typename T, int D>
+__device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T* __restrict__ noise,
+                                           int64_t i, double (&n)[D]) {
+  double z[D];
+  load_rec<T, D>(noise, i, z);
+  if (p.has_A) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      double acc = z[0] * p.A[c];
+#pragma unroll
+      for (int k = 1; k < D; ++k) acc = fma(z[k], p.A[k * D + c], acc);
+      n[c] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) n[c] = z[c];
+  }
+  if (p.has_mu_noise) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) n[c] += p.mu_noise[c];
+  }
+}
+
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T* __restrict__ x_in,
+                                            const T* __restrict__ noise, int64_t i, double (&out)[D]) {
+  double x[D], y[D];
+  load_rec<T, D>(x_in, i, x);
+  apply_transition<D>(p, x, y);
+  const bool has_noise = (noise != nullptr) && p.noise_cols > 0;
+  if constexpr (MODE == PFB_PRED_EUCLID) {
+    if (has_noise) {
+      double n[D];
+      load_noise<T, D>(p, noise, i, n);
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = y[c] + n[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = y[c];
+    }
+  } else if constexpr (MODE == PFB_PRED_TORUS_SHIFT) {
+    if (has_noise) {
+      double n[D];
+      load_noise<T, D>(p, noise, i, n);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
+        double s = np_mod_2pi(n[c] + mean);      // sample(): draw + mean, wrapped
+        out[c] = np_mod_2pi(s);                  // filter wraps again
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = np_mod_2pi(y[c]);
+    }
+  } else if constexpr (MODE == PFB_PRED_TORUS_ADD) {
+    if (has_noise) {
+      double n[D];
+      load_noise<T, D>(p, noise, i, n);          // includes the (host-wrapped) noise mean
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double s = np_mod_2pi(n[c]);
+        out[c] = np_mod_2pi(y[c] + s);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = np_mod_2pi(y[c]);
+    }
+  } else if constexpr (MODE == PFB_PRED_SPHERE_VMF) {
+    static_assert(D == 3 || MODE != PFB_PRED_SPHERE_VMF, "VMF noise is implemented on S^2");
+    if (has_noise) {
+      double t[D];
+      load_rec<T, D>(noise, i, t);               // (u, z1, z2)
+      // scipy _rvs_3d: canonical draw around e1
+      double xc = 1.0 + log(t[0] + (1.0 - t[0]) * p.exp_m2k) / p.kappa;
+      double temp = sqrt(1.0 - xc * xc);
+      double nrm = sqrt(t[1] * t[1] + t[2] * t[2]);
+      double s[3] = {xc, temp * (t[1] / nrm), temp * (t[2] / nrm)};
+      // scipy _rotate_samples: +-Householder reflector taking e1 to the mode y
+      double alpha = y[0];
+      double xn2 = y[1] * y[1] + y[2] * y[2];
+      double r[3];
+      bool positive;
+      if (xn2 == 0.0) {
+        r[0] = s[0]; r[1] = s[1]; r[2] = s[2];
+        positive = alpha > 0.0;
+      } else {
+        double beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        double tau = (beta - alpha) / beta;
+        double den = alpha - beta;
+        double v1 = y[1] / den, v2 = y[2] / den;
+        double vs = (s[0] + v1 * s[1]) + v2 * s[2];
+        double tv = tau * vs;
+        r[0] = s[0] - tv;
+        r[1] = s[1] - tv * v1;
+        r[2] = s[2] - tv * v2;
+        positive = beta > 0.0;
+      }
+      if (!positive) { r[0] = -r[0]; r[1] = -r[1]; r[2] = -r[2]; }
+      if (p.renormalize) {
+        double nn = sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+        r[0] /= nn; r[1] /= nn; r[2] /= nn;
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = r[c < 3 ? c : 0];
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = y[c];
+    }
+  } else {  // PFB_PRED_SPHERE_ADD
+    double n[D];
+    if (has_noise) {
+      load_noise<T, D>(p, noise, i, n);
+#pragma unroll
+      for (int c = 0; c < D; ++c) y[c] += n[c];
+    }
+    double ss = y[0] * y[0];
+#pragma unroll
+    for (int c = 1; c < D; ++c) ss += y[c] * y[c];
+    double nn = sqrt(ss);
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = y[c] / nn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// log-likelihoods
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ double whitened_sq(const pfb_lik_params& L, const double (&dev)[D]) {
+  double maha = 0.0;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    double acc = dev[0] * L.W[c];
+#pragma unroll
+    for (int r = 1; r < D; ++r) acc = fma(dev[r], L.W[r * D + c], acc);
+    maha = fma(acc, acc, maha);
+  }
+  return maha;
+}
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kImageCut = 90.0;  // drop images whose maha exceeds the best one by this much (e^-45)
+
+template <int D, int KIND>
+__device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const double (&x)[D],
+                                             const double* __restrict__ images /* smem or null */) {
+  if constexpr (KIND == PFB_LIK_GAUSS) {
+    double dev[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dev[c] = x[c] - L.mu[c];
+    return L.logc - 0.5 * whitened_sq<D>(L, dev);
+  } else if constexpr (KIND == PFB_LIK_WN_MULTI) {
+    // xs = (xs + pi) % (2 pi) - pi; sum over the image table of mvn.pdf(xs + 2 pi k)
+    double dev[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kPi) - kPi) - L.mu[c];
+    const double q0 = whitened_sq<D>(L, dev);
+    const int K = L.n_images;
+    constexpr int ROW = 2 * D + 1;
+    // pass 1: cheap maha_k = q0 + 2 g_k.dev + h_k, find the minimum
+    double mmin = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const double* row = images + k * ROW;
+      double lin = row[0] * dev[0];
+#pragma unroll
+      for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
+      double m = fma(2.0, lin, q0) + row[D];
+      mmin = fmin(mmin, m);
+    }
+    // pass 2: accurate maha for the images that matter, summed relative to the cheap minimum
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double* row = images + k * ROW;
+      double lin = row[0] * dev[0];
+#pragma unroll
+      for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
+      double m = fma(2.0, lin, q0) + row[D];
+      if (m - mmin <= kImageCut) {
+        double sh[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) sh[c] = dev[c] + row[D + 1 + c];
+        sum += exp(-0.5 * (whitened_sq<D>(L, sh) - mmin));
+      }
+    }
+    return L.logc - 0.5 * mmin + log(sum);
+  } else if constexpr (KIND == PFB_LIK_WN_1D) {
+    if (L.sigma > 10.0) return -log(kTwoPi);
+    double xx = np_mod_2pi(x[0]);
+    xx -= L.mu[0];
+    const double tmp = -1.0 / (2.0 * (L.sigma * L.sigma));
+    double result = exp(xx * xx * tmp);
+    for (int k = 1; k <= 1000; ++k) {
+      double xp = xx + kTwoPi * k;
+      double xm = xx - kTwoPi * k;
+      double old = result;
+      result += exp(xp * xp * tmp) + exp(xm * xm * tmp);
+      if (result == old) break;
+    }
+    return log(result) + L.logc;  // logc = log(1/sqrt(2 pi)/sigma)
+  } else if constexpr (KIND == PFB_LIK_VM) {
+    return fma(L.kappa, cos(x[0] - L.mu[0]), L.logc);  // logc = -log(2 pi I0(kappa))
+  } else {  // PFB_LIK_VMF
+    double dot = L.mu[0] * x[0];
+#pragma unroll
+    for (int c = 1; c < D; ++c) dot = fma(L.mu[c], x[c], dot);
+    return fma(L.kappa, dot, L.logc);  // logc = log C(kappa)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T, int D, int MODE>
+__global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p, int64_t n,
+                                                           const T* __restrict__ x_in, T* x_out,
+                                                           const T* __restrict__ noise) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double out[D];
+    predict_one<T, D, MODE>(p, x_in, noise, i, out);
+    store_rec<T, D>(x_out, i, out);
+  }
+}
+
+// finish the max reduction: partial (max, nan) per CTA -> stats by the last CTA
+__device__ __forceinline__ void finish_max(double tmax, double tnan, double* stats, Workspace ws,
+                                           double* smem) {
+  double bm = block_max(tmax, smem);
+  double bn = block_max(tnan, smem);
+  if (threadIdx.x == 0) {
+    ws.partials[2 * blockIdx.x] = bm;
+    ws.partials[2 * blockIdx.x + 1] = bn;
+  }
+  if (block_is_last(ws.counters)) {
+    double m = -INFINITY, nn = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      m = fmax(m, ws.partials[2 * b]);
+      nn = fmax(nn, ws.partials[2 * b + 1]);
+    }
+    m = block_max(m, smem);
+    nn = block_max(nn, smem);
+    if (threadIdx.x == 0) {
+      stats[PFB_STAT_MAX] = m;
+      double flags = 0.0;
+      if (nn > 0.0) flags += 1.0;
+      if (m == -INFINITY) flags += 2.0;
+      stats[PFB_STAT_FLAGS] = flags;
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, double* smem_img) {
+  if (L.kind != PFB_LIK_WN_MULTI) return nullptr;
+  const int count = L.n_images * (2 * D + 1);
+  for (int k = threadIdx.x; k < count; k += blockDim.x) smem_img[k] = L.images_dev[k];
+  __syncthreads();
+  return smem_img;
+}
+
+template <typename T, int D, int KIND>
+__global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int64_t n,
+                                                          const T* __restrict__ x,
+                                                          const double* __restrict__ w_prev,
+                                                          double* __restrict__ logw, double* stats,
+                                                          Workspace ws) {
+  extern __shared__ double smem_dyn[];
+  __shared__ double red[32];
+  const double* images = stage_images<D>(L, smem_dyn);
+  double tmax = -INFINITY, tnan = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double r[D];
+    load_rec<T, D>(x, i, r);
+    double l = loglik_one<D, KIND>(L, r, images);
+    if (w_prev != nullptr) l += log(w_prev[i]);
+    logw[i] = l;
+    if (l != l) tnan = 1.0;
+    tmax = fmax(tmax, l);
+  }
+  finish_max(tmax, tnan, stats, ws, red);
+}
+
+template <typename T, int D, int MODE, int KIND>
+__global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_params p,
+                                                                  pfb_lik_params L, int64_t n,
+                                                                  const T* __restrict__ x_in, T* x_out,
+                                                                  const T* __restrict__ noise,
+                                                                  double* __restrict__ logw,
+                                                                  double* stats, Workspace ws) {
+  extern __shared__ double smem_dyn[];
+  __shared__ double red[32];
+  const double* images = stage_images<D>(L, smem_dyn);
+  double tmax = -INFINITY, tnan = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double out[D];
+    predict_one<T, D, MODE>(p, x_in, noise, i, out);
+    store_rec<T, D>(x_out, i, out);
+    if constexpr (sizeof(T) == 4) {
+      // weight what was stored (the fp32 particle), as a separate pfb_loglik call would
+#pragma unroll
+      for (int c = 0; c < D; ++c) out[c] = (double)(float)out[c];
+    }
+    double l = loglik_one<D, KIND>(L, out, images);
+    logw[i] = l;
+    if (l != l) tnan = 1.0;
+    tmax = fmax(tmax, l);
+  }
+  finish_max(tmax, tnan, stats, ws, red);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) wrap_kernel(int64_t count, const T* __restrict__ x_in,
+                                                        T* x_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    x_out[i] = (T)np_mod_2pi((double)x_in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side validation + dispatch
+// ---------------------------------------------------------------------------------------------
+static int check_predict(const pfb_predict_params* p) {
+  if (!p) { set_error("predict params NULL"); return PFB_ERR_INVALID; }
+  if (p->dim < 1 || p->dim > PFB_MAXD) { set_error("dim %d outside 1..%d", p->dim, PFB_MAXD); return PFB_ERR_INVALID; }
+  if (p->mode < PFB_PRED_EUCLID || p->mode > PFB_PRED_SPHERE_ADD) { set_error("bad predict mode %d", p->mode); return PFB_ERR_INVALID; }
+  if (p->mode == PFB_PRED_SPHERE_VMF && p->dim != 3) { set_error("VMF noise needs dim 3 (S^2), got %d", p->dim); return PFB_ERR_UNSUPPORTED; }
+  if (p->noise_cols != 0 && p->noise_cols != p->dim) { set_error("noise_cols %d must equal dim %d", p->noise_cols, p->dim); return PFB_ERR_INVALID; }
+  if (p->mode == PFB_PRED_SPHERE_VMF && p->noise_cols && !(p->kappa > 0.0)) { set_error("kappa must be > 0"); return PFB_ERR_INVALID; }
+  return PFB_OK;
+}
+
+static int check_lik(const pfb_lik_params* L, int dim) {
+  if (!L) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
+  if (L->dim != dim) { set_error("likelihood dim %d != particle dim %d", L->dim, dim); return PFB_ERR_INVALID; }
+  if (L->kind < PFB_LIK_GAUSS || L->kind > PFB_LIK_VMF) { set_error("unknown likelihood kind %d (arbitrary callables are not supported)", L->kind); return PFB_ERR_UNSUPPORTED; }
+  if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
+  if (L->kind == PFB_LIK_WN_MULTI) {
+    if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
+    if ((int64_t)L->n_images * (2 * dim + 1) * 8 > 48 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+  }
+  return PFB_OK;
+}
+
+static size_t lik_smem(const pfb_lik_params* L) {
+  return L->kind == PFB_LIK_WN_MULTI ? (size_t)L->n_images * (2 * L->dim + 1) * 8 : 0;
+}
+
+#define PFB_DISPATCH_MODE(mode, ...)                                                       \
+  switch (mode) {                                                                          \
+    case PFB_PRED_EUCLID: { constexpr int MODE = PFB_PRED_EUCLID; __VA_ARGS__; } break;     \
+    case PFB_PRED_TORUS_SHIFT: { constexpr int MODE = PFB_PRED_TORUS_SHIFT; __VA_ARGS__; } break; \
+    case PFB_PRED_TORUS_ADD: { constexpr int MODE = PFB_PRED_TORUS_ADD; __VA_ARGS__; } break; \
+    case PFB_PRED_SPHERE_ADD: { constexpr int MODE = PFB_PRED_SPHERE_ADD; __VA_ARGS__; } break; \
+    default: set_error("bad mode"); return PFB_ERR_INVALID;                                 \
+  }
+
+#define PFB_DISPATCH_KIND(kind, ...)                                                       \
+  switch (kind) {                                                                          \
+    case PFB_LIK_GAUSS: { constexpr int KIND = PFB_LIK_GAUSS; __VA_ARGS__; } break;         \
+    case PFB_LIK_WN_MULTI: { constexpr int KIND = PFB_LIK_WN_MULTI; __VA_ARGS__; } break;   \
+    case PFB_LIK_VMF: { constexpr int KIND = PFB_LIK_VMF; __VA_ARGS__; } break;             \
+    default: set_error("bad kind"); return PFB_ERR_INVALID;                                 \
+  }
+
+}  // namespace pfb
+
+using namespace pfb;
+
+extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t n, const void* x_in,
+                           void* x_out, const void* noise, void* stream) {
+  int rc = check_predict(p);
+  if (rc) return rc;
+  if (n <= 0) return PFB_OK;
+  if (!x_in || !x_out) { set_error("NULL particle pointer"); return PFB_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(n);
+  PFB_DISPATCH_DTYPE(dtype, {
+    if (p->mode == PFB_PRED_SPHERE_VMF) {
+      predict_kernel<T, 3, PFB_PRED_SPHERE_VMF><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
+    } else {
+      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
+    }
+  });
+  PFB_LAUNCH_OK("predict_kernel");
+  return PFB_OK;
+}
+
+extern "C" int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void* x,
+                          const double* w_prev, double* logw, double* stats, void* ws, int64_t ws_bytes,
+                          void* stream) {
+  if (!lik) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
+  int rc = check_lik(lik, lik->dim);
+  if (rc) return rc;
+  if (n <= 0) return PFB_OK;
+  if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  Workspace W;
+  rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(n);
+  const size_t sm = lik_smem(lik);
+  PFB_DISPATCH_DTYPE(dtype, {
+    if (lik->kind == PFB_LIK_WN_1D) {
+      loglik_kernel<T, 1, PFB_LIK_WN_1D><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W);
+    } else if (lik->kind == PFB_LIK_VM) {
+      loglik_kernel<T, 1, PFB_LIK_VM><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W);
+    } else {
+      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W))));
+    }
+  });
+  PFB_LAUNCH_OK("loglik_kernel");
+  return PFB_OK;
+}
+
+namespace pfb {
+// Only manifold-consistent (mode, likelihood) pairs are instantiated:
+//   Euclidean <-> gauss;  torus <-> wn_multi (any D), wn_1d / vm (D = 1);  sphere <-> vmf.
+template <typename T, int D, int MODE, int KIND>
+static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* lik, int64_t n, const void* x_in,
+                            void* x_out, const void* noise, double* logw, double* stats, Workspace W,
+                            cudaStream_t st) {
+  predict_loglik_kernel<T, D, MODE, KIND><<<stream_grid(n), kThreads, lik_smem(lik), st>>>(
+      *p, *lik, n, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  return PFB_OK;
+}
+
+template <typename T, int D, int MODE>
+static int launch_fused(const pfb_predict_params* p, const pfb_lik_params* lik, int64_t n, const void* x_in,
+                        void* x_out, const void* noise, double* logw, double* stats, Workspace W,
+                        cudaStream_t st) {
+  constexpr bool torus = (MODE == PFB_PRED_TORUS_SHIFT || MODE == PFB_PRED_TORUS_ADD);
+  constexpr bool sphere = (MODE == PFB_PRED_SPHERE_VMF || MODE == PFB_PRED_SPHERE_ADD);
+  if constexpr (MODE == PFB_PRED_EUCLID) {
+    if (lik->kind == PFB_LIK_GAUSS) return launch_fused_one<T, D, MODE, PFB_LIK_GAUSS>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+  }
+  if constexpr (torus) {
+    if (lik->kind == PFB_LIK_WN_MULTI) return launch_fused_one<T, D, MODE, PFB_LIK_WN_MULTI>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+    if constexpr (D == 1) {
+      if (lik->kind == PFB_LIK_WN_1D) return launch_fused_one<T, 1, MODE, PFB_LIK_WN_1D>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+      if (lik->kind == PFB_LIK_VM) return launch_fused_one<T, 1, MODE, PFB_LIK_VM>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+    }
+  }
+  if constexpr (sphere && D >= 2) {
+    if (lik->kind == PFB_LIK_VMF) return launch_fused_one<T, D, MODE, PFB_LIK_VMF>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+  }
+  set_error("likelihood kind %d is not defined on the manifold of predict mode %d (dim %d)", lik->kind, MODE, D);
+  return PFB_ERR_UNSUPPORTED;
+}
+}  // namespace pfb
+
+extern "C" int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
+                                  int64_t n, const void* x_in, void* x_out, const void* noise, double* logw,
+                                  double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  int rc = check_predict(p);
+  if (rc) return rc;
+  rc = check_lik(lik, p->dim);
+  if (rc) return rc;
+  if (n <= 0) return PFB_OK;
+  if (!x_in || !x_out || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  Workspace W;
+  rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, {
+    if (p->mode == PFB_PRED_SPHERE_VMF) {
+      rc = launch_fused<T, 3, PFB_PRED_SPHERE_VMF>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+    } else {
+      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (rc = launch_fused<T, D, MODE>(p, lik, n, x_in, x_out, noise, logw, stats, W, st))));
+    }
+  });
+  if (rc) return rc;
+  PFB_LAUNCH_OK("predict_loglik_kernel");
+  return PFB_OK;
+}
+
+extern "C" int pfb_wrap_2pi(pfb_dtype dtype, int64_t count, const void* x_in, void* x_out, void* stream) {
+  if (count <= 0) return PFB_OK;
+  if (!x_in || !x_out) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(count);
+  PFB_DISPATCH_DTYPE(dtype, (wrap_kernel<T><<<grid, kThreads, 0, st>>>(count, (const T*)x_in, (T*)x_out)));
+  PFB_LAUNCH_OK("wrap_kernel");
+  return PFB_OK;
+}

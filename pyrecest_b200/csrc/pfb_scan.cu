@@ -1,0 +1,523 @@
+// K(3) max / log-sum-exp normalisation and K(4a) the CDF scan (fast and sequential-exact).
+//
+// Sequential-exact scan: reproduces numpy.cumsum(p) (c_i = fl(c_{i-1} + p_i), fp64, ties to
+// even, p_i >= 0) bit for bit in ONE pass with a chained (decoupled look-back) scan:
+//   * channel A is an ordinary fp64 look-back scan of tile sums; it bounds the running sum at
+//     every tile boundary to a relative 4 n 2^-53, which tells most tiles with certainty which
+//     binade [2^e, 2^(e+1)) the sequential running sum is in while it crosses them ("safe" tiles);
+//   * inside one binade a sequential fp add is an INTEGER add in units of ulp = 2^(e-52):
+//       S_i = S_{i-1} + k_i + [rem_i > half] + [rem_i == half and (S_{i-1} + k_i) odd]
+//     so each element is a map parity(S_{i-1}) -> increment, stored as (inc_even, inc_odd); maps
+//     compose associatively, (g o f)(pi) = f(pi) + g((pi + f(pi)) & 1), which is the operator of
+//     channel B's look-back; a safe tile publishes its composed map before it knows its prefix;
+//   * tiles that may contain a binade crossing (about one per binade) or start at 0 are "hard":
+//     they wait for the exact incoming value and add sequentially with real fp64 adds.
+// SURVEY.md appendix B has the derivation; tests/test_scan_model.py holds a numpy model of the
+// same tile logic and tests/test_gpu_resample.py checks the kernel against np.cumsum.
+#include "pfb_common.cuh"
+
+namespace pfb {
+
+constexpr int kItems = kScanTile / kThreads;  // 8 consecutive elements per thread
+static_assert(kItems * kThreads == kScanTile, "tile shape");
+
+struct TileState {
+  unsigned long long* flagA;  // 0 none, 1 aggregate, 2 inclusive
+  unsigned long long* flagB;  // low 2 bits: 0 none, 1 aggregate map, 2 inclusive; bits 8..: e + 2048
+  double* aggA;
+  double* inclA;
+  long long* aggE;
+  long long* aggO;
+  double* inclB;
+  unsigned int* ticket;
+};
+
+__host__ __device__ inline TileState make_tile_state(unsigned char* base, int64_t ntiles, unsigned int* ticket) {
+  TileState s;
+  s.flagA = reinterpret_cast<unsigned long long*>(base);
+  s.flagB = s.flagA + ntiles;
+  s.aggA = reinterpret_cast<double*>(s.flagB + ntiles);
+  s.inclA = s.aggA + ntiles;
+  s.aggE = reinterpret_cast<long long*>(s.inclA + ntiles);
+  s.aggO = s.aggE + ntiles;
+  s.inclB = reinterpret_cast<double*>(s.aggO + ntiles);
+  s.ticket = ticket;
+  return s;
+}
+
+// ---- parity maps ---------------------------------------------------------------------------------
+struct PMap {
+  long long e, o;  // increment when the incoming integer sum is even / odd
+};
+__device__ __forceinline__ PMap pmap_then(PMap f, PMap g) {  // apply f first, then g
+  PMap h;
+  h.e = f.e + ((f.e & 1LL) ? g.o : g.e);
+  h.o = f.o + (((f.o + 1LL) & 1LL) ? g.o : g.e);
+  return h;
+}
+__device__ __forceinline__ long long pmap_apply(PMap f, long long S) { return S + ((S & 1LL) ? f.o : f.e); }
+
+// map of one addend p >= 0 in the binade whose ulp is 2^ue  (ue = e - 52)
+__device__ __forceinline__ PMap pmap_of(double p, int ue) {
+  const long long bits = __double_as_longlong(p);
+  const int ef = (int)((bits >> 52) & 0x7ff);
+  long long M = bits & 0x000fffffffffffffLL;
+  int q;
+  if (ef == 0) { q = -1074; } else { M |= 0x0010000000000000LL; q = ef - 1075; }
+  PMap r;
+  if (M == 0) { r.e = 0; r.o = 0; return r; }
+  const int sh = ue - q;
+  if (sh <= 0) {
+    long long k = (sh > -11) ? (M << (-sh)) : 0x4000000000000000LL;  // saturate: certainly a crossing
+    r.e = k; r.o = k;
+  } else if (sh >= 63) {
+    r.e = 0; r.o = 0;
+  } else {
+    const long long k = M >> sh;
+    const long long rem = M & ((1LL << sh) - 1LL);
+    const long long half = 1LL << (sh - 1);
+    const long long up = rem > half ? 1LL : 0LL;
+    const bool tie = rem == half;
+    r.e = k + up + ((tie && (k & 1LL)) ? 1LL : 0LL);
+    r.o = k + up + ((tie && !(k & 1LL)) ? 1LL : 0LL);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double ulp_value(int ue) {  // 2^ue, ue >= -1074
+  long long b = (ue >= -1022) ? ((long long)(ue + 1023) << 52) : (1LL << (ue + 1074));
+  return __longlong_as_double(b);
+}
+// integer sum S with c = S * 2^(e-52), for c in [2^e, 2^(e+1)) or subnormal with e == -1022
+__device__ __forceinline__ long long int_of(double c, int e, bool* ok) {
+  const long long bits = __double_as_longlong(c);
+  const int ef = (int)((bits >> 52) & 0x7ff);
+  const long long mant = bits & 0x000fffffffffffffLL;
+  if (ef == 0) { *ok = (e == -1022); return mant; }
+  *ok = (ef - 1023 == e);
+  return mant | 0x0010000000000000LL;
+}
+
+// ---- K(3) normalise ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) lse_reduce_kernel(int64_t n, const double* __restrict__ logw,
+                                                              double* stats, Workspace ws) {
+  __shared__ double red[3 * 32];
+  double m = -INFINITY, s = 0.0, q = 0.0, nanf = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double l = logw[i];
+    if (l != l) { nanf = 1.0; continue; }
+    if (l > m) {
+      double sc = exp(m - l);  // m = -inf -> 0
+      s = s * sc + 1.0;
+      q = q * (sc * sc) + 1.0;
+      m = l;
+    } else if (l > -INFINITY) {
+      double e = exp(l - m);
+      s += e;
+      q += e * e;
+    }
+  }
+  // block combine: common max, rescale, sum
+  double bm = block_max(m, red);
+  double sc = (m == -INFINITY) ? 0.0 : exp(m - bm);
+  double v[3] = {s * sc, q * sc * sc, nanf};
+  block_sum<3>(v, red);
+  if (threadIdx.x == 0) {
+    ws.partials[4 * blockIdx.x + 0] = bm;
+    ws.partials[4 * blockIdx.x + 1] = v[0];
+    ws.partials[4 * blockIdx.x + 2] = v[1];
+    ws.partials[4 * blockIdx.x + 3] = v[2];
+  }
+  if (block_is_last(ws.counters)) {
+    double M = -INFINITY;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) M = fmax(M, ws.partials[4 * b]);
+    M = block_max(M, red);
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      double pm = ws.partials[4 * b];
+      double f = (pm == -INFINITY) ? 0.0 : exp(pm - M);
+      t[0] += ws.partials[4 * b + 1] * f;
+      t[1] += ws.partials[4 * b + 2] * f * f;
+      t[2] += ws.partials[4 * b + 3];
+    }
+    block_sum<3>(t, red);
+    if (threadIdx.x == 0) {
+      stats[PFB_STAT_MAX] = M;
+      stats[PFB_STAT_SUMEXP] = t[0];
+      stats[PFB_STAT_SUMSQ] = t[1];
+      double flags = 0.0;
+      if (t[2] > 0.0) flags += 1.0;
+      if (M == -INFINITY || !(t[0] > 0.0)) flags += 2.0;
+      stats[PFB_STAT_FLAGS] = flags;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) weights_kernel(int64_t n, const double* __restrict__ logw,
+                                                           double* __restrict__ w_out,
+                                                           const double* __restrict__ stats) {
+  const double M = stats[PFB_STAT_MAX], S = stats[PFB_STAT_SUMEXP];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    w_out[i] = exp(logw[i] - M) / S;
+}
+
+// ---- K(4a) scan ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one double per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ double block_excl_scan(double v, double* smem /*33*/, double* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    double w = (lane < (kThreads / 32)) ? smem[lane] : 0.0;
+    double wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < (kThreads / 32)) smem[lane] = wi - w;  // exclusive warp offsets
+    if (lane == (kThreads / 32) - 1) smem[32] = wi;
+  }
+  __syncthreads();
+  *total = smem[32];
+  double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) exc = 0.0;
+  return smem[warp] + exc;
+}
+
+// block-wide exclusive scan of parity maps (ordered composition)
+__device__ __forceinline__ PMap block_excl_scan_pmap(PMap v, long long* smem /* 2*33 */, PMap* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PMap inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    PMap t;
+    t.e = __shfl_up_sync(0xffffffffu, inc.e, o);
+    t.o = __shfl_up_sync(0xffffffffu, inc.o, o);
+    if (lane >= o) inc = pmap_then(t, inc);
+  }
+  // exclusive within warp: inclusive of the previous lane
+  PMap exc;
+  exc.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
+  exc.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
+  if (lane == 0) { exc.e = 0; exc.o = 0; }
+  __syncthreads();
+  if (lane == 31) { smem[2 * warp] = inc.e; smem[2 * warp + 1] = inc.o; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PMap run; run.e = 0; run.o = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      PMap cur; cur.e = smem[2 * w]; cur.o = smem[2 * w + 1];
+      smem[2 * w] = run.e; smem[2 * w + 1] = run.o;  // exclusive warp prefix
+      run = pmap_then(run, cur);
+    }
+    smem[64] = run.e; smem[65] = run.o;
+  }
+  __syncthreads();
+  PMap wp; wp.e = smem[2 * warp]; wp.o = smem[2 * warp + 1];
+  total->e = smem[64]; total->o = smem[65];
+  return pmap_then(wp, exc);
+}
+
+// look-back on channel A (warp 0 only): exclusive fp64 prefix of tile sums
+__device__ __forceinline__ double lookback_A(const TileState& ts, int64_t tile) {
+  const int lane = threadIdx.x & 31;
+  double prefix = 0.0;
+  int64_t j0 = tile - 1;
+  while (true) {
+    const int64_t j = j0 - lane;
+    unsigned long long f = 2;  // tiles before 0 behave like an inclusive 0
+    if (j >= 0) {
+      do { f = ld_acquire_u64(ts.flagA + j); } while (f == 0);
+    }
+    double v = 0.0;
+    if (j >= 0) v = (f == 2) ? ld_relaxed_f64(ts.inclA + j) : ld_relaxed_f64(ts.aggA + j);
+    const unsigned incl_mask = __ballot_sync(0xffffffffu, f == 2);
+    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest tile with an inclusive value
+    // sum lanes 0..first (in tile order: far to near does not matter for a plain sum; keep fixed order)
+    double acc = 0.0;
+    for (int l = (first < 32 ? first : 31); l >= 0; --l) acc += __shfl_sync(0xffffffffu, v, l);
+    prefix = acc + prefix;
+    if (first < 32) break;
+    j0 -= 32;
+  }
+  return prefix;
+}
+
+// look-back on channel B (warp 0 only): exact value c at the start of `tile` (c_in) -- walks back
+// over published parity maps to the nearest exact inclusive value.
+__device__ __forceinline__ double lookback_B(const TileState& ts, int64_t tile, unsigned int* err) {
+  const int lane = threadIdx.x & 31;
+  PMap composed; composed.e = 0; composed.o = 0;  // maps of the tiles after the inclusive one, in order
+  int e_maps = 0;
+  bool have_maps = false;
+  double c_incl = 0.0;
+  int64_t j0 = tile - 1;
+  while (true) {
+    const int64_t j = j0 - lane;
+    unsigned long long f = 2;
+    if (j >= 0) {
+      do { f = ld_acquire_u64(ts.flagB + j); } while ((f & 3ULL) == 0);
+    }
+    const int st = (int)(f & 3ULL);
+    PMap m; m.e = 0; m.o = 0;
+    double ci = 0.0;
+    if (j >= 0) {
+      if (st == 2) ci = ld_relaxed_f64(ts.inclB + j);
+      else { m.e = ld_relaxed_s64(ts.aggE + j); m.o = ld_relaxed_s64(ts.aggO + j); }
+    }
+    const unsigned incl_mask = __ballot_sync(0xffffffffu, st == 2);
+    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+    // compose lanes first-1 .. 0 (tile order), then what we already had
+    PMap win; win.e = 0; win.o = 0;
+    const int top = (first < 32 ? first : 32) - 1;
+    for (int l = top; l >= 0; --l) {
+      PMap t;
+      t.e = __shfl_sync(0xffffffffu, m.e, l);
+      t.o = __shfl_sync(0xffffffffu, m.o, l);
+      win = pmap_then(win, t);
+    }
+    if (top >= 0) {
+      const unsigned long long f0 = __shfl_sync(0xffffffffu, f, 0);
+      const int e_here = (int)(f0 >> 8) - 2048;
+      if (have_maps && e_here != e_maps) atomicOr(err, 4u);
+      e_maps = e_here;
+      have_maps = true;
+    }
+    composed = pmap_then(win, composed);
+    if (first < 32) { c_incl = __shfl_sync(0xffffffffu, ci, first); break; }
+    j0 -= 32;
+  }
+  if (!have_maps) return c_incl;
+  bool ok;
+  long long S = int_of(c_incl, e_maps, &ok);
+  if (!ok) atomicOr(err, 8u);
+  S = pmap_apply(composed, S);
+  return (double)S * ulp_value(e_maps - 52);
+}
+
+template <bool EXACT, bool FROM_LOG>
+__global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double* __restrict__ in,
+                                                        double* __restrict__ cdf, double* stats,
+                                                        TileState ts, int64_t ntiles, double margin,
+                                                        unsigned int* err) {
+  __shared__ double s_dbl[40];
+  __shared__ long long s_ll[72];
+  __shared__ double s_p[EXACT ? kScanTile : 2];
+  __shared__ int64_t s_tile;
+  __shared__ double s_a0, s_cin;
+  __shared__ int s_safe, s_e;
+
+  const double shift = FROM_LOG ? stats[PFB_STAT_MAX] : 0.0;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ts.ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) break;
+    const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
+
+    double p[kItems];
+    if (base + kItems <= n) {
+      const double2* q = reinterpret_cast<const double2*>(in + base);
+#pragma unroll
+      for (int k = 0; k < kItems / 2; ++k) {
+        double2 v = __ldg(q + k);
+        p[2 * k] = v.x; p[2 * k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) p[k] = (base + k < n) ? in[base + k] : (FROM_LOG ? -INFINITY : 0.0);
+    }
+    if (FROM_LOG) {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) p[k] = exp(p[k] - shift);  // exp(-inf) = 0
+    }
+    double tsum = p[0];
+#pragma unroll
+    for (int k = 1; k < kItems; ++k) tsum += p[k];
+    double total;
+    const double toff = block_excl_scan(tsum, s_dbl, &total);
+
+    // ---- channel A: approximate prefix at the tile boundary
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) {
+        if (tile == 0) {
+          st_relaxed_f64(ts.inclA + tile, total);
+          st_release_u64(ts.flagA + tile, 2ULL);
+        } else {
+          st_relaxed_f64(ts.aggA + tile, total);
+          st_release_u64(ts.flagA + tile, 1ULL);
+        }
+      }
+      double a0 = 0.0;
+      if (tile > 0) {
+        a0 = lookback_A(ts, tile);
+        if (threadIdx.x == 0) {
+          st_relaxed_f64(ts.inclA + tile, a0 + total);
+          st_release_u64(ts.flagA + tile, 2ULL);
+        }
+      }
+      if (threadIdx.x == 0) {
+        s_a0 = a0;
+        if (EXACT) {
+          // certain binade?  every running sum inside the tile lies in [lo, hi]
+          const double lo = a0 * (1.0 - margin);
+          const double hi = (a0 + total) * (1.0 + margin);
+          int safe = 0, e = 0;
+          if (tile > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
+            const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
+            const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
+            if (elo == ehi) { safe = 1; e = elo; }
+          }
+          s_safe = safe;
+          s_e = e;
+        }
+      }
+    }
+    __syncthreads();
+
+    double c[kItems];
+    if constexpr (!EXACT) {
+      double run = s_a0 + toff;
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) { run += p[k]; c[k] = run; }
+    } else {
+    if (s_safe) {
+      const int ue = s_e - 52;
+      PMap f = pmap_of(p[0], ue);
+#pragma unroll
+      for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
+      PMap tot;
+      const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+      if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+          st_relaxed_s64(ts.aggE + tile, tot.e);
+          st_relaxed_s64(ts.aggO + tile, tot.o);
+          st_release_u64(ts.flagB + tile, 1ULL | ((unsigned long long)(s_e + 2048) << 8));
+        }
+        const double cin = lookback_B(ts, tile, err);
+        if (threadIdx.x == 0) {
+          bool ok;
+          long long S = int_of(cin, s_e, &ok);
+          if (!ok) atomicOr(err, 1u);
+          const long long Send = pmap_apply(tot, S);
+          if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // safe tile crossed a binade: bound violated
+          st_relaxed_f64(ts.inclB + tile, (double)Send * ulp_value(ue));
+          st_release_u64(ts.flagB + tile, 2ULL | ((unsigned long long)(s_e + 2048) << 8));
+          s_cin = cin;
+        }
+      }
+      __syncthreads();
+      bool ok;
+      long long S = int_of(s_cin, s_e, &ok);
+      S = pmap_apply(g, S);
+      const double u = ulp_value(ue);
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        S = pmap_apply(pmap_of(p[k], ue), S);
+        c[k] = (double)S * u;
+      }
+    } else {
+      // hard tile: exact incoming value, then real sequential fp64 adds
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) s_p[threadIdx.x * kItems + k] = p[k];
+      if (threadIdx.x < 32) {
+        double cin = 0.0;
+        if (tile > 0) cin = lookback_B(ts, tile, err);
+        if (threadIdx.x == 0) s_cin = cin;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double run = s_cin;
+        const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
+        for (int i = 0; i < cnt; ++i) { run = __dadd_rn(run, s_p[i]); s_p[i] = run; }
+        for (int i = cnt; i < kScanTile; ++i) s_p[i] = run;
+        st_relaxed_f64(ts.inclB + tile, run);
+        st_release_u64(ts.flagB + tile, 2ULL);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) c[k] = s_p[threadIdx.x * kItems + k];
+    }
+    }
+
+    if (base + kItems <= n) {
+      double2* q = reinterpret_cast<double2*>(cdf + base);
+#pragma unroll
+      for (int k = 0; k < kItems / 2; ++k) q[k] = make_double2(c[2 * k], c[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k)
+        if (base + k < n) cdf[base + k] = c[k];
+    }
+    if (tile == ntiles - 1) {
+      const int64_t last = n - 1 - tile * kScanTile;
+      if ((int64_t)threadIdx.x == last / kItems) stats[PFB_STAT_TOTAL] = c[last % kItems];
+    }
+  }
+}
+
+}  // namespace pfb
+
+using namespace pfb;
+
+extern "C" int pfb_normalize(int64_t n, const double* logw, double* w_out, double* stats, void* ws,
+                             int64_t ws_bytes, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if (!logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(n, 4);
+  lse_reduce_kernel<<<grid, kThreads, 0, st>>>(n, logw, stats, W);
+  PFB_LAUNCH_OK("lse_reduce_kernel");
+  if (w_out) {
+    weights_kernel<<<stream_grid(n), kThreads, 0, st>>>(n, logw, w_out, stats);
+    PFB_LAUNCH_OK("weights_kernel");
+  }
+  return PFB_OK;
+}
+
+extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const double* logw, double* cdf,
+                            double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if ((w == nullptr) == (logw == nullptr)) { set_error("exactly one of w / logw must be given"); return PFB_ERR_INVALID; }
+  if (!cdf || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
+  const double* in = w ? w : logw;
+  if (((uintptr_t)in & 15) || ((uintptr_t)cdf & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, n, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t ntiles = scan_tiles(n);
+  unsigned int* ticket = W.counters + 1;
+  unsigned int* err = W.counters + 2;
+  TileState ts = make_tile_state(W.tiles, ntiles, ticket);
+  PFB_CUDA_OK(cudaMemsetAsync(W.tiles, 0, (size_t)ntiles * 16, st));   // flagA + flagB
+  PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
+  int64_t g = ntiles < (int64_t)sm_count() * 6 ? ntiles : (int64_t)sm_count() * 6;
+  const int grid = (int)g;
+  const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
+  const bool from_log = (logw != nullptr);
+  if (mode == PFB_SCAN_SEQEXACT) {
+    if (from_log) scan_kernel<true, true><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    else scan_kernel<true, false><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+  } else {
+    if (from_log) scan_kernel<false, true><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    else scan_kernel<false, false><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+  }
+  PFB_LAUNCH_OK("scan_kernel");
+  return PFB_OK;
+}

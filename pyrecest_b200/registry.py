@@ -1,0 +1,273 @@
+"""Host-side reduction of the reference's objects to the POD parameter blocks of include/pfb.h.
+
+Transitions and likelihoods are a REGISTRY: identity / linear transitions, and the built-in
+distribution kinds (Gaussian, hypertoroidal wrapped normal, circular wrapped normal, von Mises,
+von Mises-Fisher).  An arbitrary Python callable is rejected -- it is never run on the CPU
+(BASELINE.json north_star).  Objects are recognised by class name and attributes, so both the
+classes of pyrecest_b200.distributions and the reference's own pyrecest.distributions instances
+(numpy backend) are accepted.
+
+Only tiny (<= 6 x 6) host arrays are touched here; numpy (and scipy.linalg.eigh when present,
+to follow scipy.stats.multivariate_normal's factorisation) do that arithmetic.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+TWO_PI = 2.0 * math.pi
+
+
+def _np(a):
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# transitions
+# --------------------------------------------------------------------------------------------
+class IdentityTransition:
+    """f(x) = x.  What predict_identity dispatches (abstract_particle_filter.py:18-19 passes an
+    identity lambda, which cannot be recognised, so the filters override predict_identity)."""
+
+    def __call__(self, x):
+        return x
+
+
+class LinearTransition:
+    """f(x) = x @ F.T + b, the registry form of a linear system model."""
+
+    def __init__(self, F, b=None):
+        self.F = _np(F)
+        assert self.F.ndim == 2 and self.F.shape[0] == self.F.shape[1], "F must be square"
+        self.b = None if b is None else _np(b).reshape(-1)
+
+    def __call__(self, x):
+        import torch
+
+        F = torch.as_tensor(self.F, dtype=x.dtype, device=x.device)
+        y = x @ F.T
+        if self.b is not None:
+            y = y + torch.as_tensor(self.b, dtype=x.dtype, device=x.device)
+        return y
+
+
+def transition_params(f, dim):
+    """(has_F, F, has_b, b) for a registry transition; raises for anything else."""
+    if f is None or isinstance(f, IdentityTransition):
+        return None, None
+    if isinstance(f, LinearTransition):
+        if f.F.shape[0] != dim:
+            raise ValueError(f"LinearTransition is {f.F.shape[0]}-D, filter state is {dim}-D")
+        return f.F, f.b
+    raise NotImplementedError(
+        "predict_nonlinear only accepts registry transitions (IdentityTransition, LinearTransition(F, b)); "
+        f"got {type(f).__name__}. Arbitrary Python callables are not run on the CPU."
+    )
+
+
+# --------------------------------------------------------------------------------------------
+# distribution kinds
+# --------------------------------------------------------------------------------------------
+_KIND_BY_NAME = {
+    "GaussianDistribution": "gauss",
+    "HypertoroidalWrappedNormalDistribution": "wn_multi",
+    "HypertoroidalWNDistribution": "wn_multi",
+    "ToroidalWrappedNormalDistribution": "wn_multi",
+    "WrappedNormalDistribution": "wn_1d",
+    "WNDistribution": "wn_1d",
+    "VonMisesDistribution": "vm",
+    "VMDistribution": "vm",
+    "VonMisesFisherDistribution": "vmf",
+    "VMFDistribution": "vmf",
+}
+
+
+def kind_of(obj):
+    for cls in type(obj).__mro__:
+        k = _KIND_BY_NAME.get(cls.__name__)
+        if k is not None:
+            return k
+    return None
+
+
+def as_distribution(likelihood):
+    """Accept a registry distribution or its bound .pdf (what update_identity builds,
+    abstract_particle_filter.py:108); reject other callables."""
+    if kind_of(likelihood) is not None:
+        return likelihood
+    owner = getattr(likelihood, "__self__", None)
+    if owner is not None and getattr(likelihood, "__name__", "") == "pdf" and kind_of(owner) is not None:
+        return owner
+    raise NotImplementedError(
+        "likelihood must be one of the built-in distributions (Gaussian, HypertoroidalWrappedNormal, "
+        "WrappedNormal, VonMises, VonMisesFisher) or its bound .pdf; arbitrary Python callables are "
+        f"rejected, not run on the CPU (got {type(likelihood).__name__})."
+    )
+
+
+def gaussian_noise_factor(C):
+    """numpy legacy multivariate_normal factor: draws are z @ A + mean with
+    (u, s, v) = svd(C); A = sqrt(s)[:, None] * v  (gaussian_distribution.py:122-123)."""
+    C = np.atleast_2d(_np(C))
+    (_, s, v) = np.linalg.svd(C)
+    return np.sqrt(s)[:, None] * v
+
+
+def gaussian_whitening(C):
+    """(W, log|C|) the way scipy.stats.multivariate_normal factorises (eigh; W = V / sqrt(lambda))."""
+    C = np.atleast_2d(_np(C))
+    try:
+        import scipy.linalg
+
+        s, u = scipy.linalg.eigh(C, lower=True, check_finite=False)
+    except ImportError:  # pragma: no cover
+        s, u = np.linalg.eigh(C)
+    if np.min(s) <= 0:
+        raise ValueError("covariance must be positive definite")
+    return np.multiply(u, np.sqrt(1.0 / s)), float(np.sum(np.log(s)))
+
+
+def log_i0(kappa):
+    """log I0(kappa), stable for large kappa."""
+    try:
+        from scipy.special import ive
+
+        return float(np.log(ive(0, kappa)) + kappa)
+    except ImportError:  # pragma: no cover
+        import torch
+
+        return float(torch.log(torch.special.i0e(torch.tensor(kappa, dtype=torch.float64))) + kappa)
+
+
+def _log_iv(nu, kappa):
+    from scipy.special import ive
+
+    return float(np.log(ive(nu, kappa)) + kappa)
+
+
+def vmf_log_norm_const(kappa, D):
+    """log C_D(kappa) of VonMisesFisherDistribution.__init__ (von_mises_fisher_distribution.py:41-49)."""
+    dim = D - 1
+    if dim == 2:
+        # kappa / (4 pi sinh kappa), written to survive large kappa
+        return math.log(kappa) - math.log(2.0 * math.pi) - kappa - math.log1p(-math.exp(-2.0 * kappa))
+    half = (dim + 1) / 2.0
+    return (half - 1.0) * math.log(kappa) - half * math.log(TWO_PI) - _log_iv(half - 1.0, kappa)
+
+
+def wn_image_table(mu, P, m=3, cut=None):
+    """Image list of HypertoroidalWrappedNormalDistribution.pdf
+    (hypertoroidal_wrapped_normal_distribution.py:80-91): all offsets 2 pi k, k in {-m..m}^d, pruned to
+    those that can matter.  maha_k(x) - maha_j(x) = 2 (g_k - g_j).dev + (h_k - h_j) is LINEAR in
+    dev = x - mu, so its minimum over the box dev in [-pi - mu, pi - mu) is attained at a corner.
+    Image k is dropped iff some image j beats it by more than `cut` everywhere in the box: then
+    pdf_k <= e^{-cut/2} pdf_j and the (2m+1)^d dropped terms together stay below 2^-53 of the sum.
+    Rows: (g_k = P o_k, h_k = o_k^T P o_k, o_k)."""
+    mu = _np(mu).reshape(-1)
+    d = mu.shape[0]
+    ks = np.array(list(itertools.product(range(-m, m + 1), repeat=d)), dtype=np.float64)
+    offs = ks * TWO_PI
+    g = offs @ P
+    h = np.einsum("kd,kd->k", g, offs)
+    if cut is None:
+        cut = 2.0 * (math.log(len(offs)) + 53.0 * math.log(2.0))
+    lo = -math.pi - mu
+    hi = math.pi - mu
+    dg = g[:, None, :] - g[None, :, :]              # (k, j, d)
+    lin_min = np.sum(np.minimum(2.0 * dg * lo, 2.0 * dg * hi), axis=-1)
+    gap_min = lin_min + (h[:, None] - h[None, :])   # min over the box of maha_k - maha_j
+    keep = ~np.any(gap_min > cut, axis=1)
+    return np.concatenate([g[keep], h[keep, None], offs[keep]], axis=1), int(keep.sum())
+
+
+def predict_noise_spec(noise, dim):
+    """Reduce a noise distribution to (kind, fields).  kinds: None, 'gauss', 'wn', 'vm', 'vmf'."""
+    if noise is None:
+        return None, {}
+    k = kind_of(noise)
+    if k == "gauss":
+        mu = _np(noise.mu).reshape(-1)
+        return "gauss", {"mu": mu, "A": gaussian_noise_factor(noise.C)}
+    if k in ("wn_multi", "wn_1d"):
+        mu = _np(noise.mu).reshape(-1)
+        C = np.atleast_2d(_np(noise.C))
+        return "wn", {"mu": np.mod(mu, TWO_PI), "A": gaussian_noise_factor(C)}
+    if k == "vm":
+        return "vm", {"mu": np.atleast_1d(_np(noise.mu)).reshape(-1), "kappa": np.atleast_1d(_np(noise.kappa)).reshape(-1)}
+    if k == "vmf":
+        return "vmf", {"kappa": float(_np(noise.kappa))}
+    raise NotImplementedError(
+        f"noise distribution {type(noise).__name__} is not in the device registry "
+        "(Gaussian, (Hypertoroidal)WrappedNormal, VonMises, VonMisesFisher)"
+    )
+
+
+def lik_params(dist, dim, images_to_device=None):
+    """Fill a LikParams from a registry distribution; `dim` = stored components of the filter state.
+    Returns (LikParams, keepalive) -- keepalive holds the device image table, if any."""
+    k = kind_of(dist)
+    p = L.LikParams()
+    p.dim = dim
+    keep = None
+    if k == "gauss":
+        mu = _np(dist.mu).reshape(-1)
+        if mu.shape[0] != dim:
+            raise AssertionError("likelihood dimension does not match the filter state")
+        W, logdet = gaussian_whitening(dist.C)
+        p.kind = L.LIK_GAUSS
+        p.mu[:dim] = mu.tolist()
+        p.W[: dim * dim] = W.reshape(-1).tolist()
+        p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)
+    elif k == "wn_multi":
+        mu = _np(dist.mu).reshape(-1)
+        if mu.shape[0] != dim:
+            raise AssertionError("likelihood dimension does not match the filter state")
+        C = np.atleast_2d(_np(dist.C))
+        W, logdet = gaussian_whitening(C)
+        table, n_img = wn_image_table(mu, W @ W.T)
+        p.kind = L.LIK_WN_MULTI
+        p.mu[:dim] = mu.tolist()
+        p.W[: dim * dim] = W.reshape(-1).tolist()
+        p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)
+        p.n_images = n_img
+        if images_to_device is not None:
+            keep = images_to_device(table)
+            p.images_dev = keep.data_ptr()
+        else:
+            keep = table
+    elif k == "wn_1d":
+        if dim != 1:
+            raise AssertionError("WrappedNormalDistribution is circular (dim 1)")
+        sigma = float(np.sqrt(_np(dist.C).reshape(-1)[0])) if hasattr(dist, "C") else float(_np(dist.sigma))
+        if sigma <= 0:
+            raise ValueError(f"sigma must be >0, but received {sigma}.")
+        p.kind = L.LIK_WN_1D
+        p.mu[0] = float(_np(dist.mu).reshape(-1)[0])
+        p.sigma = sigma
+        p.logc = math.log(1.0 / math.sqrt(TWO_PI) / sigma)
+    elif k == "vm":
+        if dim != 1:
+            raise AssertionError("VonMisesDistribution is circular (dim 1)")
+        kappa = float(_np(dist.kappa))
+        p.kind = L.LIK_VM
+        p.mu[0] = float(_np(dist.mu).reshape(-1)[0])
+        p.kappa = kappa
+        p.logc = -(math.log(TWO_PI) + log_i0(kappa))
+    elif k == "vmf":
+        mu = _np(dist.mu).reshape(-1)
+        if mu.shape[0] != dim:
+            raise AssertionError("likelihood dimension does not match the filter state")
+        kappa = float(_np(dist.kappa))
+        p.kind = L.LIK_VMF
+        p.mu[:dim] = mu.tolist()
+        p.kappa = kappa
+        p.logc = vmf_log_norm_const(kappa, dim)
+    else:
+        raise NotImplementedError(f"{type(dist).__name__} is not a registry likelihood")
+    return p, keep

@@ -1,0 +1,421 @@
+"""Parity of the CUDA kernels, called through the C ABI (libpfb.so via pyrecest_b200._engine),
+against the oracle and the golden fixtures made from the real reference.
+Bar: bit-exact for indices, the pure add / numpy.mod predict paths and the sequential-exact CDF;
+rtol 1e-12 (fp64) / 1e-5 (fp32 storage) for everything that goes through exp / log / cos."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-12
+RTOL32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pyrecest_b200._engine import engine
+
+    return engine("cuda:0")
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda:0").contiguous()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def pparams(mode, dim, noise_cols=None, F=None, b=None, A=None, mu=None, kappa=0.0, renorm=0):
+    from pyrecest_b200 import _lib as L
+
+    p = L.PredictParams()
+    p.mode, p.dim = mode, dim
+    p.noise_cols = dim if noise_cols is None else noise_cols
+    if F is not None:
+        p.has_F = 1
+        p.F[: dim * dim] = np.asarray(F, dtype=np.float64).reshape(-1).tolist()
+    if b is not None:
+        p.has_b = 1
+        p.b[:dim] = np.asarray(b, dtype=np.float64).tolist()
+    if A is not None:
+        p.has_A = 1
+        p.A[: dim * dim] = np.asarray(A, dtype=np.float64).reshape(-1).tolist()
+    if mu is not None:
+        p.has_mu_noise = 1
+        p.mu_noise[:dim] = np.asarray(mu, dtype=np.float64).tolist()
+    p.kappa = kappa
+    p.exp_m2k = float(np.exp(-2 * kappa))
+    p.renormalize = renorm
+    return p
+
+
+def test_abi_version():
+    from pyrecest_b200 import _lib as L
+
+    assert L.lib().pfb_abi_version() == 1
+
+
+def test_wrap_bitexact(eng, golden):
+    g = golden("mod_edges")
+    x = dev(g["x"])
+    y = torch.empty_like(x)
+    eng.wrap_2pi(x, y)
+    assert np.array_equal(host(y), g["y"])
+    rng = np.random.default_rng(0)
+    big = np.concatenate([rng.standard_normal(100_003) * 50, rng.random(1000) * 2 * math.pi])
+    x = dev(big)
+    y = torch.empty_like(x)
+    eng.wrap_2pi(x, y)
+    assert np.array_equal(host(y), np.mod(big, 2.0 * np.pi))
+
+
+def test_predict_euclid(eng, golden):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("euclid_cv")
+    d = g["d0"]
+    for t in range(g["Z"].shape[0]):
+        rows = O.gaussian_rows(g["Z"][t], g["Q"], np.zeros(2))
+        x = dev(d)
+        out = torch.empty_like(x)
+        # linear transition on the device + host-made noise rows
+        eng.predict(pparams(L.PRED_EUCLID, 2, F=g["F"]), x, out, dev(rows))
+        np.testing.assert_allclose(host(out), g["d_pred"][t], rtol=1e-14, atol=1e-15)
+        # identity transition: pure adds, bit-exact
+        fd = d @ g["F"].T
+        eng.predict(pparams(L.PRED_EUCLID, 2), dev(fd), out, dev(rows))
+        assert np.array_equal(host(out), O.predict_euclid(fd, rows))
+        # standard normals + A on the device
+        eng.predict(pparams(L.PRED_EUCLID, 2, F=g["F"], A=O.gaussian_noise_factor(g["Q"])), x, out, dev(g["Z"][t]))
+        np.testing.assert_allclose(host(out), g["d_pred"][t], rtol=RTOL64, atol=1e-14)
+        d = g["d_post"][t]
+
+
+def test_predict_torus_shift_bitexact(eng, golden):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("torus_t3")
+    d = g["d0"]
+    for t in range(g["Z"].shape[0]):
+        rows = O.gaussian_rows(g["Z"][t], g["Cn"])
+        x = dev(d)
+        out = torch.empty_like(x)
+        eng.predict(pparams(L.PRED_TORUS_SHIFT, 3), x, out, dev(rows))
+        assert np.array_equal(host(out), g["d_pred"][t])
+        eng.predict(pparams(L.PRED_TORUS_SHIFT, 3, A=O.gaussian_noise_factor(g["Cn"])), x, out, dev(g["Z"][t]))
+        diff = np.abs(host(out) - g["d_pred"][t])
+        diff = np.minimum(diff, 2 * np.pi - diff)
+        assert diff.max() < 1e-12
+        d = g["d_post"][t]
+    # in place, circle
+    g = golden("circle_case")
+    rows = O.gaussian_rows(g["Z"][0][:, None], np.array([[float(g["sig_n"]) ** 2]]))
+    x = dev(g["d0"][:, None])
+    eng.predict(pparams(L.PRED_TORUS_SHIFT, 1), x, x, dev(rows))
+    assert np.array_equal(host(x)[:, 0], g["d_pred"][0])
+
+
+def test_predict_torus_addmode_bitexact(eng, golden):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("torus_addmode")
+    rows = O.gaussian_rows(g["Z"], g["C"])
+    x = dev(np.mod(g["d0"], 2 * np.pi))
+    out = torch.empty_like(x)
+    eng.predict(pparams(L.PRED_TORUS_ADD, 2, mu=np.mod(g["mu_n"], 2 * np.pi)), x, out, dev(rows))
+    assert np.array_equal(host(out), g["d_pred"])
+
+
+def test_predict_sphere_vmf(eng, golden):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("vmf_sampler")
+    x = dev(g["modes"])
+    out = torch.empty_like(x)
+    for kappa in g["kappas"]:
+        eng.predict(pparams(L.PRED_SPHERE_VMF, 3, kappa=float(kappa)), x, out, dev(g["triples"]))
+        np.testing.assert_allclose(host(out), g[f"out_k{kappa}"], rtol=0, atol=2e-14)
+        np.testing.assert_allclose(host(out), O.predict_sphere_vmf(g["modes"], g["triples"], float(kappa)), rtol=0, atol=2e-14)
+    rng = np.random.default_rng(3)
+    n = rng.standard_normal(g["modes"].shape) * 0.1
+    eng.predict(pparams(L.PRED_SPHERE_ADD, 3), x, out, dev(n))
+    np.testing.assert_allclose(host(out), O.predict_sphere_additive(g["modes"], n), rtol=RTOL64)
+
+
+class _D:  # minimal stand-ins recognised by registry.kind_of through their class names
+    pass
+
+
+def _dist(name, **kw):
+    cls = type(name, (), {})
+    o = cls()
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _loglik(eng, dist, x, dim, dtype=torch.float64, w_prev=None):
+    from pyrecest_b200 import registry as R
+
+    lp, keep = R.lik_params(dist, dim, images_to_device=lambda t: dev(t))
+    xd = dev(x.reshape(-1, dim), dtype)
+    logw = torch.empty(xd.shape[0], dtype=torch.float64, device="cuda:0")
+    eng.loglik(lp, xd, logw, w_prev=None if w_prev is None else dev(w_prev))
+    return host(logw), float(host(eng.stats)[0])
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, RTOL64), (torch.float32, RTOL32)])
+def test_loglik_tables(eng, golden, dtype, rtol):
+    g = golden("likelihoods")
+    f32 = dtype == torch.float32
+
+    def cmp(lw, ref, x, fn):
+        if f32:  # compare against the oracle evaluated at the fp32-rounded particle
+            ref = fn(x.astype(np.float32).astype(np.float64))
+        np.testing.assert_allclose(np.exp(lw), ref, rtol=rtol, atol=1e-300)
+
+    for d in (1, 2, 3, 4):
+        x, mu, Cc = g[f"g{d}_x"], g[f"g{d}_mu"], g[f"g{d}_C"]
+        lw, mx = _loglik(eng, _dist("GaussianDistribution", mu=mu, C=Cc), x, d, dtype)
+        cmp(lw, g[f"g{d}_pdf"], x, lambda xx: O.pdf_gauss(xx, mu, Cc))
+        assert mx == lw.max()
+    for tag in ("wn2", "wn3", "wn3b"):
+        x, mu, Cc = g[f"{tag}_x"], g[f"{tag}_mu"], g[f"{tag}_C"]
+        lw, _ = _loglik(eng, _dist("HypertoroidalWrappedNormalDistribution", mu=mu, C=Cc), x, x.shape[1], dtype)
+        cmp(lw, g[f"{tag}_pdf"], x, lambda xx: O.pdf_wn_multi(xx, mu, Cc))
+    x = g["wn1_x"]
+    for i, s in enumerate(g["wn1_sigma"]):
+        lw, _ = _loglik(eng, _dist("WrappedNormalDistribution", mu=g["wn1_mu"], C=np.array(s**2)), x, 1, dtype)
+        cmp(lw, g["wn1_pdf"][i], x, lambda xx: O.pdf_wn_1d(xx, float(g["wn1_mu"]), float(s)))
+    for i, k in enumerate(g["vm_kappa"]):
+        lw, _ = _loglik(eng, _dist("VonMisesDistribution", mu=g["vm_mu"], kappa=k), x, 1, dtype)
+        cmp(lw, g["vm_pdf"][i], x, lambda xx: O.pdf_vm(xx, float(g["vm_mu"]), float(k)))
+    for D in (3, 4):
+        x, mu = g[f"vmf{D}_x"], g[f"vmf{D}_mu"]
+        for i, k in enumerate(g[f"vmf{D}_kappa"]):
+            lw, _ = _loglik(eng, _dist("VonMisesFisherDistribution", mu=mu, kappa=k), x, D, dtype)
+            cmp(lw, g[f"vmf{D}_pdf"][i], x, lambda xx: O.pdf_vmf(xx, mu, float(k)))
+
+
+def test_wn_multi_matches_full_343_sum_on_random_inputs(eng):
+    rng = np.random.default_rng(11)
+    C3 = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+    for scale, mu in ((0.5, [1.0, 2.0, 3.0]), (0.05, [6.2, 0.01, 3.1]), (3.0, [0.0, 5.0, 1.0])):
+        x = rng.random((4000, 3)) * 2 * np.pi
+        x[:8] = [[0, 0, 0], [2 * np.pi] * 3, [np.pi] * 3, [np.pi, 0, 2 * np.pi], mu, [0.0, np.pi, np.pi], [1e-9] * 3, [6.28] * 3]
+        lw, _ = _loglik(eng, _dist("HypertoroidalWrappedNormalDistribution", mu=np.array(mu), C=scale * C3), x, 3)
+        ref = O.pdf_wn_multi(x, np.array(mu), scale * C3)
+        ok = ref > 1e-280
+        np.testing.assert_allclose(np.exp(lw[ok]), ref[ok], rtol=RTOL64)
+
+
+def test_normalize_and_reweigh(eng, golden):
+    g = golden("dirac_moments")
+    w, lik = g["w"], g["lin_lik"]
+    logw = dev(np.log(lik) + np.log(w))
+    wout = torch.empty_like(logw)
+    eng.normalize(logw, wout)
+    np.testing.assert_allclose(host(wout), g["lin_reweighed"], rtol=RTOL64)
+    st = host(eng.stats)
+    p = host(wout)
+    np.testing.assert_allclose(st[1] ** 2 / st[2], 1.0 / np.sum(p * p), rtol=1e-12)
+    assert st[3] == 0.0
+    # -inf and NaN handling
+    bad = np.log(lik)
+    bad[:] = -np.inf
+    eng.normalize(dev(bad), None)
+    assert int(host(eng.stats)[3]) & 2
+    bad = np.log(lik)
+    bad[5] = np.nan
+    eng.normalize(dev(bad), None)
+    assert int(host(eng.stats)[3]) & 1
+
+
+CASES = ["lik", "wide", "ties", "zeros", "uniform", "single"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_scan_seqexact_and_indices_bitexact(eng, golden, name):
+    g = golden("resample_cases")
+    w, u, idx = g[f"{name}_w"], g[f"{name}_u"], g[f"{name}_idx"]
+    wd = dev(w)
+    cdf = torch.empty_like(wd)
+    eng.scan(cdf, w=wd, exact=True)
+    ref = np.cumsum(w)
+    assert np.array_equal(host(cdf), ref), f"max ulp-ish diff {np.max(np.abs(host(cdf) - ref) / ref[-1])}"
+    assert eng.scan_error_flags() == 0
+    assert host(eng.stats)[4] == ref[-1]
+    out_idx = torch.empty(u.shape[0], dtype=torch.int64, device="cuda:0")
+    eng.resample(cdf, dev(u), None, None, u.shape[0], 1, idx_out=out_idx)
+    assert np.array_equal(host(out_idx), idx)
+    # the fast scan is only tolerance-equal, its indices may differ at exact ties
+    eng.scan(cdf, w=wd, exact=False)
+    # (the "ties" case is where a blocked sum is MORE accurate than the sequential one: 1 + 2^-53 + ... )
+    np.testing.assert_allclose(host(cdf), ref, rtol=1e-13 if name != "ties" else 1e-11)
+
+
+@pytest.mark.parametrize("n", [1, 2, 2047, 2048, 2049, 300_001, 3_000_000])
+def test_scan_seqexact_sizes(eng, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) * 2.5
+    w = np.exp(-0.5 * (x - 0.7) ** 2) * (rng.random(n) < 0.97)
+    wd = dev(w)
+    cdf = torch.empty_like(wd)
+    eng.scan(cdf, w=wd, exact=True)
+    assert np.array_equal(host(cdf), np.cumsum(w))
+    assert eng.scan_error_flags() == 0
+    # from log-weights: p = exp(l - max) is formed on the device; the scan of those p is exact
+    lw = -0.5 * (x - 0.7) ** 2
+    lwd = dev(lw)
+    eng.normalize(lwd, None)
+    eng.scan(cdf, logw=lwd, exact=True)
+    c = host(cdf)
+    p = np.diff(np.concatenate([[0.0], c]))
+    np.testing.assert_allclose(p, np.exp(lw - lw.max()), rtol=1e-9, atol=1e-12)
+    u = rng.random(min(n, 100_000))
+    idx = torch.empty(u.shape[0], dtype=torch.int64, device="cuda:0")
+    eng.resample(cdf, dev(u), None, None, u.shape[0], 1, idx_out=idx)
+    cn = c / c[-1]
+    assert np.array_equal(host(idx), np.minimum(np.searchsorted(cn, u, side="right"), n - 1))
+
+
+def test_scan_adversarial_dynamic_range(eng):
+    rng = np.random.default_rng(5)
+    n = 200_000
+    # every binade from 2^-1060 (subnormal) up to 2^40, zeros in between, huge jumps
+    e = np.sort(rng.integers(-1060, 40, size=n))
+    w = np.ldexp(1.0 + rng.random(n), e) * (rng.random(n) < 0.9)
+    w[0] = 0.0
+    w[1] = 5e-324
+    wd = dev(w)
+    cdf = torch.empty_like(wd)
+    eng.scan(cdf, w=wd, exact=True)
+    assert np.array_equal(host(cdf), np.cumsum(w))
+    w2 = np.concatenate([np.full(70_000, 2.0 ** -53), [1.0], np.full(70_000, 2.0 ** -53), [2.0 ** -52] * 5000])
+    wd = dev(w2)
+    cdf = torch.empty_like(wd)
+    eng.scan(cdf, w=wd, exact=True)
+    assert np.array_equal(host(cdf), np.cumsum(w2))
+    assert eng.scan_error_flags() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_resample_gather_and_estimates(eng, golden, dtype):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("torus_t3")
+    N = g["d0"].shape[0]
+    for t in range(2):
+        wpost = O.reweigh(O.uniform_w(N), g["lik"][t])
+        cdf = torch.empty(N, dtype=torch.float64, device="cuda:0")
+        eng.scan(cdf, w=dev(wpost), exact=True)
+        x = dev(g["d_pred"][t], dtype)
+        out = torch.empty_like(x)
+        idx = torch.empty(N, dtype=torch.int64, device="cuda:0")
+        est = torch.empty(6, dtype=torch.float64, device="cuda:0")
+        eng.resample(cdf, dev(g["U"][t]), x, out, N, 3, idx_out=idx, est_kind=L.EST_TRIG, est_out=est)
+        assert np.array_equal(host(idx), g["idx"][t])
+        assert np.array_equal(host(out), host(x)[g["idx"][t]])
+        if dtype == torch.float64:
+            assert np.array_equal(host(out), g["d_post"][t])
+        e = host(est).reshape(3, 2)
+        md = np.mod(np.arctan2(e[:, 1], e[:, 0]), 2 * np.pi)
+        np.testing.assert_allclose(md, g["est"][t], rtol=RTOL64 if dtype == torch.float64 else RTOL32)
+    g = golden("euclid_cv")
+    N = g["d0"].shape[0]
+    lik = O.pdf_gauss(g["d_pred"][0], g["zs"][0], g["R"])
+    cdf = torch.empty(N, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(O.reweigh(O.uniform_w(N), lik)), exact=True)
+    x = dev(g["d_pred"][0], dtype)
+    out = torch.empty_like(x)
+    est = torch.empty(2, dtype=torch.float64, device="cuda:0")
+    idx = torch.empty(N, dtype=torch.int64, device="cuda:0")
+    eng.resample(cdf, dev(g["U"][0]), x, out, N, 2, idx_out=idx, est_kind=L.EST_SUM, est_out=est)
+    assert np.array_equal(host(idx), g["idx"][0])
+    np.testing.assert_allclose(host(est), g["est"][0], rtol=RTOL64 if dtype == torch.float64 else RTOL32)
+
+
+def test_sample_n_not_equal_N_and_systematic(eng, golden):
+    g = golden("dirac_moments")
+    w, u = g["w"], g["tor_sample_u"]
+    N = w.shape[0]
+    cdf = torch.empty(N, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    x = dev(np.mod(g["tor_d"], 2 * np.pi))
+    out = torch.empty((u.shape[0], 3), dtype=torch.float64, device="cuda:0")
+    idx = torch.empty(u.shape[0], dtype=torch.int64, device="cuda:0")
+    eng.resample(cdf, dev(u), x, out, u.shape[0], 3, idx_out=idx)
+    assert np.array_equal(host(idx), g["tor_sample_idx"])
+    assert np.array_equal(host(out), g["tor_sample"])
+    for u0, n_out in ((0.37, N), (0.0, 2 * N + 1), (np.nextafter(1.0, 0), 17)):
+        idx = torch.empty(n_out, dtype=torch.int64, device="cuda:0")
+        eng.resample(cdf, dev(np.array([u0])), None, None, n_out, 1, systematic=True, idx_out=idx)
+        assert np.array_equal(host(idx), O.systematic_indices(w, u0, n_out))
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float64, RTOL64), (torch.float32, RTOL32)])
+def test_moments(eng, golden, dtype, rtol):
+    from pyrecest_b200 import _lib as L
+
+    g = golden("dirac_moments")
+    w = dev(g["w"])
+    r32 = (lambda a: a.astype(np.float32).astype(np.float64)) if dtype == torch.float32 else (lambda a: a)
+    x = dev(g["lin_d"], dtype)
+    m = eng.moments(L.MOM_MEAN, x, 4, w=w)
+    np.testing.assert_allclose(host(m)[:4], O.mean_linear(r32(g["lin_d"]), g["w"]), rtol=rtol)
+    np.testing.assert_allclose(host(m)[4], 1.0, rtol=1e-14)
+    cov = eng.moments(L.MOM_CENTRAL, x, 4, w=w, center=m)
+    np.testing.assert_allclose(host(cov)[:16].reshape(4, 4), O.covariance_linear(r32(g["lin_d"]), g["w"]), rtol=max(rtol, 1e-11))
+    x = dev(g["tor_d"], dtype)
+    for order, key in ((1, "tor_m1"), (2, "tor_m2")):
+        t = host(eng.moments(L.MOM_TRIG, x, 3, w=w, order=order))[:6].reshape(3, 2)
+        ref = O.trig_moment(r32(g["tor_d"]), g["w"], order)
+        np.testing.assert_allclose(t[:, 0] + 1j * t[:, 1], ref, rtol=rtol * 10)
+    x = dev(g["sph_d"], dtype)
+    np.testing.assert_allclose(host(eng.moments(L.MOM_MEAN, x, 3, w=w))[:3], O.mean_resultant(r32(g["sph_d"]), g["w"]), rtol=rtol)
+    np.testing.assert_allclose(host(eng.moments(L.MOM_SCATTER, x, 3, w=w))[:9].reshape(3, 3), O.scatter(r32(g["sph_d"]), g["w"]), rtol=rtol * 10, atol=1e-15)
+    # uniform weights (w = NULL)
+    mu = host(eng.moments(L.MOM_MEAN, x, 3))[:3]
+    np.testing.assert_allclose(mu, r32(g["sph_d"]).mean(axis=0), rtol=rtol * 10)
+
+
+def test_fused_predict_loglik_equals_separate_calls(eng, golden):
+    from pyrecest_b200 import _lib as L
+    from pyrecest_b200 import registry as R
+
+    g = golden("torus_t3")
+    rows = O.gaussian_rows(g["Z"][0], g["Cn"])
+    x = dev(g["d0"])
+    lp, keep = R.lik_params(_dist("HypertoroidalWrappedNormalDistribution", mu=g["zs"][0], C=g["Cl"]), 3, images_to_device=dev)
+    out1, out2 = torch.empty_like(x), torch.empty_like(x)
+    l1 = torch.empty(x.shape[0], dtype=torch.float64, device="cuda:0")
+    l2 = torch.empty_like(l1)
+    pp = pparams(L.PRED_TORUS_SHIFT, 3)
+    eng.predict(pp, x, out1, dev(rows))
+    eng.loglik(lp, out1, l1)
+    m1 = float(host(eng.stats)[0])
+    eng.predict_loglik(pp, lp, x, out2, dev(rows), l2)
+    assert np.array_equal(host(out1), host(out2)) and np.array_equal(host(l1), host(l2))
+    assert m1 == float(host(eng.stats)[0])
+    np.testing.assert_allclose(np.exp(host(l2)), g["lik"][0], rtol=RTOL64)
+
+
+def test_rejects_bad_arguments(eng):
+    from pyrecest_b200 import _lib as L
+
+    x = torch.zeros((4, 3), dtype=torch.float64, device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        eng.predict(pparams(L.PRED_SPHERE_VMF, 2, kappa=1.0), x[:, :2].contiguous(), x[:, :2].contiguous(), x)
+    with pytest.raises(ValueError):
+        eng.predict(pparams(L.PRED_EUCLID, 9), x, x, x)
+    lp = L.LikParams()
+    lp.kind, lp.dim = 17, 3
+    with pytest.raises(NotImplementedError):
+        eng.loglik(lp, x, torch.zeros(4, dtype=torch.float64, device="cuda:0"))
