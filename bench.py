@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the fused predict + update + resample + estimate step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload t3|s2|r2|r4] [--particles P]
+  python bench.py --impl reference ...      # the CPU restatement of the reference (oracle/) on host cores
+
+Workload at N=1 (BASELINE.json configs[1]): HypertoroidalParticleFilter on T^3, 1e8 particles, von Mises
+system noise (kappa = 10 per dim), wrapped-normal likelihood (cov 0.5 C, z = [1, 2, 3], m = 3, i.e. the
+reference's 343-image sum), multinomial resampling of N of N, mean-direction estimate.  fp64.
+N > 1 (torchrun): every rank runs an independent filter of the same size (independent Monte-Carlo runs shard
+with no communication -- north_star), "scaling": "weak".
+
+value : steps timed with CUDA events, noise draws + uniforms already resident in HBM (a ring of
+        pre-generated buffers larger than L2), 3 kernel launches per step through the C ABI.
+e2e   : the same step through the public API (pf.predict_identity / pf.update_identity /
+        pf.get_point_estimate), draws generated on the device inside the timed region, the measurement
+        coming from pinned host memory and the estimate + status word read back to the host every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C3 = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+METRIC = "particle-steps/s (predict+update+resample)"
+
+WORKLOADS = {
+    # name: (manifold, D, noise columns E, default particles, description)
+    "t3": ("torus", 3, 3, 10**8, "HypertoroidalParticleFilter T^3, von Mises noise + wrapped-normal likelihood"),
+    "s2": ("sphere", 3, 3, 10**8, "HypersphericalParticleFilter S^2, VMF noise + VMF likelihood, mean direction"),
+    "r2": ("euclid", 2, 2, 10**4, "EuclideanParticleFilter R^2 constant velocity, Gaussian noise + likelihood"),
+    "r4": ("euclid", 4, 4, 10**8, "EuclideanParticleFilter R^4 constant velocity, Gaussian noise + likelihood"),
+}
+
+
+def algorithmic_bytes(D, E):
+    """B = 8 (4D + E + 5) per particle-step, split per kernel."""
+    return {"predict_loglik": 8 * (2 * D + E + 1), "scan": 16, "resample": 8 * (2 * D + 2)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload definitions shared by both arms
+# ---------------------------------------------------------------------------------------------
+def cv_matrix(D):
+    F = np.eye(D)
+    for i in range(D // 2):
+        F[i, D // 2 + i] = 1.0
+    return F
+
+
+def workload_params(name):
+    manifold, D, E, _, _ = WORKLOADS[name]
+    if name == "t3":
+        return {"z": np.array([1.0, 2.0, 3.0]), "lik_C": 0.5 * C3, "kappa_noise": np.array([10.0, 10.0, 10.0]),
+                "prior_mu": np.array([1.0, 1.0, 1.0]) + math.pi / 2, "prior_C": C3}
+    if name == "s2":
+        return {"z": np.array([1.0, 1.0, 1.0]) / math.sqrt(3), "kappa_lik": 10.0, "kappa_noise": 50.0,
+                "prior_mu": np.array([0.0, 0.0, 1.0]), "prior_kappa": 5.0}
+    return {"z": np.full(D, 0.3), "F": cv_matrix(D), "Q": 0.1 * np.eye(D), "R": 0.5 * np.eye(D),
+            "prior_mu": np.zeros(D), "prior_C": np.eye(D)}
+
+
+def make_dists(name, P):
+    """(prior, transition, noise, likelihood-with-mode) as public-API objects."""
+    from pyrecest_b200 import distributions as Dn
+    from pyrecest_b200.filters import IdentityTransition, LinearTransition
+
+    if name == "t3":
+        return (Dn.HypertoroidalWrappedNormalDistribution(P["prior_mu"], P["prior_C"]), IdentityTransition(),
+                Dn.VonMisesDistribution(np.zeros(3), P["kappa_noise"]),
+                Dn.HypertoroidalWrappedNormalDistribution(np.zeros(3), P["lik_C"]))
+    if name == "s2":
+        return (Dn.VonMisesFisherDistribution(P["prior_mu"], P["prior_kappa"]), IdentityTransition(),
+                Dn.VonMisesFisherDistribution(np.array([0.0, 0.0, 1.0]), P["kappa_noise"]),
+                Dn.VonMisesFisherDistribution(P["z"], P["kappa_lik"]))
+    D = P["F"].shape[0]
+    return (Dn.GaussianDistribution(P["prior_mu"], P["prior_C"]), LinearTransition(P["F"]),
+            Dn.GaussianDistribution(np.zeros(D), P["Q"]), Dn.GaussianDistribution(np.zeros(D), P["R"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_fn(name, n, seed=0):
+    from oracle import pf_oracle as O
+
+    P = workload_params(name)
+    rng = np.random.default_rng(seed)
+    manifold, D, E, _, _ = WORKLOADS[name]
+    if name == "t3":
+        d = np.mod(O.gaussian_rows(rng.standard_normal((n, 3)), P["prior_C"], P["prior_mu"]), 2 * np.pi)
+        lik = ("wn_multi", {"mu": P["z"], "C": P["lik_C"]})
+        draw = lambda: rng.vonmises(0.0, 10.0, size=(n, 3))  # noqa: E731
+        kw = {}
+    elif name == "s2":
+        t0 = np.column_stack([rng.random(n), rng.standard_normal((n, 2))])
+        d = O.predict_sphere_vmf(np.tile(P["prior_mu"], (n, 1)), t0, P["prior_kappa"])
+        lik = ("vmf", {"mu": P["z"], "kappa": P["kappa_lik"]})
+        draw = lambda: np.column_stack([rng.random(n), rng.standard_normal((n, 2))])  # noqa: E731
+        kw = {"kappa_noise": P["kappa_noise"]}
+    else:
+        d = O.gaussian_rows(rng.standard_normal((n, D)), P["prior_C"], P["prior_mu"])
+        lik = ("gauss", {"mu": P["z"], "C": P["R"]})
+        draw = lambda: O.gaussian_rows(rng.standard_normal((n, D)), P["Q"])  # noqa: E731
+        kw = {"F": P["F"]}
+    state = {"d": d}
+
+    def step():
+        noise = draw()
+        u = rng.random(n)
+        t0 = time.perf_counter()
+        r = O.step(manifold, state["d"], noise, lik[0], lik[1], u, **kw)
+        dt = time.perf_counter() - t0
+        state["d"] = r["d"]
+        return dt
+
+    return step
+
+
+def run_cpu(name, n, steps, warmup):
+    step = cpu_step_fn(name, n)
+    for _ in range(warmup):
+        step()
+    total = sum(step() for _ in range(steps))
+    return n * steps / total, total / steps
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pyrecest_b200 import _lib as L
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200 import registry as R
+    from pyrecest_b200._engine import engine
+    from pyrecest_b200 import filters as Fl
+
+    name = args.workload
+    manifold, D, E, n_default, desc = WORKLOADS[name]
+    n = args.particles or n_default
+    P = workload_params(name)
+    prior, trans, noise_dist, lik_dist = make_dists(name, P)
+    eng = engine(dev)
+    prandom.seed(1234 + rank)
+
+    # ---- public-API filter (used for e2e and to build the initial particle set)
+    cls = {"torus": Fl.HypertoroidalParticleFilter, "sphere": Fl.HypersphericalParticleFilter,
+           "euclid": Fl.EuclideanParticleFilter}[manifold]
+    pf = cls(n, D if manifold != "sphere" else D - 1)
+    pf.filter_state = prior
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value leg: resident inputs, C-ABI calls ------------------------------------------------
+    nbuf = max(2, min(4, int(math.ceil(512e6 / (n * 8.0 * (E + 1))))))  # ring > L2 (126 MB)
+    src = prandom.source()
+    noise_ring, u_ring = [], []
+    for _ in range(nbuf):
+        if name == "t3":
+            noise_ring.append(src.vonmises((n, 3), torch.as_tensor(P["kappa_noise"]), dev))
+        elif name == "s2":
+            noise_ring.append(src.vmf_triples(n, dev))
+        else:
+            noise_ring.append(src.normals((n, D), dev))
+        u_ring.append(src.uniforms((n,), dev))
+    pp, _ = pf._predict_params(trans, noise_dist, pf._default_shift)  # parameter block only; its draws are dropped
+    del _
+    lp, keep = R.lik_params(lik_dist.set_mode(P["z"]), D, images_to_device=lambda t: torch.as_tensor(t, device=dev).contiguous())
+    x = pf.filter_state._records().clone()
+    alt = torch.empty_like(x)
+    logw = torch.empty(n, dtype=torch.float64, device=dev)
+    cdf = torch.empty(n, dtype=torch.float64, device=dev)
+    est = torch.empty(2 * L.PFB_MAXD, dtype=torch.float64, device=dev)
+    est_kind = L.EST_TRIG if manifold == "torus" else L.EST_SUM
+    exact = not args.fast_scan
+
+    def step(i, ev=None):
+        nonlocal x, alt
+        nb = noise_ring[i % nbuf]
+        ub = u_ring[i % nbuf]
+        if ev:
+            ev[0].record()
+        eng.predict_loglik(pp, lp, x, x, nb, logw)
+        if ev:
+            ev[1].record()
+        eng.scan(cdf, logw=logw, exact=exact)
+        if ev:
+            ev[2].record()
+        eng.resample(cdf, ub, x, alt, n, D, est_kind=est_kind, est_out=est)
+        if ev:
+            ev[3].record()
+        x, alt = alt, x
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launches
+    t_wall0 = time.time()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        step(args.warmup + i, evs[i])
+    end.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_total = start.elapsed_time(end)
+    gpu_launches = eng.launches - launches0
+    kt = np.array([[e[k].elapsed_time(e[k + 1]) for k in range(3)] for e in evs]).mean(axis=0)  # ms per kernel
+    flags = int(eng.stats[L.STAT_FLAGS].item())
+    est_host = est.cpu().numpy()
+    assert flags == 0 and np.all(np.isfinite(est_host[:D])), "bench step produced invalid weights"
+    assert eng.scan_error_flags() == 0
+
+    # ---- e2e leg: public API ------------------------------------------------------------------------
+    z_pinned = torch.as_tensor(P["z"]).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def api_step():
+        z = z_pinned.numpy()  # measurement arrives in pinned host memory; parameters ride in the launch
+        pf.predict_nonlinear(trans, noise_dist)
+        pf.update_identity(lik_dist, z)
+        return pf.get_point_estimate().cpu()  # D2H of the estimate (the status word is read inside update)
+
+    for _ in range(min(args.warmup, 3)):
+        api_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        api_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------
+    vals = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(vals[0]), float(vals[1])
+    ms_step = ms_total / args.steps
+    value = world * n / (ms_step * 1e-3)
+    e2e_value = world * n / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = algorithmic_bytes(D, E)
+        names = ["predict_loglik", "scan", "resample"]
+        k = int(np.argmax(kt))
+        achieved = ab[names[k]] * n / (kt[k] * 1e-3) / 1e9
+        step_gbs = sum(ab.values()) * n / (ms_step * 1e-3) / 1e9
+        cpu_n = args.cpu_particles
+        cpu_val, cpu_s = run_cpu(name, cpu_n, 2, 1) if not args.no_cpu else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "resampling": "multinomial",
+                       "scan": "sequential-exact" if exact else "fast", "likelihood_images": int(lp.n_images) if name == "t3" else None,
+                       "l2_policy": f"inputs larger than L2: ring of {nbuf} pre-generated noise/uniform buffers "
+                                    f"({n * 8 * (E + 1) / 1e6:.0f} MB each) + {n * 8 * D / 1e6:.0f} MB state",
+                       "parallelism": "1 filter per GPU, no collective" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(8 * len(P["z"])), "d2h_bytes_per_step": int(8 * D + 8 * L.STAT_COUNT),
+                    "path": "public API: predict_nonlinear + update_identity + get_point_estimate; draws generated on device"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": names[k], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": {nm: float(t) for nm, t in zip(names, kt)},
+                         "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
+                         "bytes_per_particle": ab},
+            "cpu_baseline": None if args.no_cpu else {
+                "value": cpu_val, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+                "sample": f"oracle/pf_oracle.py (vectorised numpy restatement) on {cpu_n} particles x 2 steps of the same workload, "
+                          f"{cpu_s:.2f} s/step; host has {os.cpu_count()} cores"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    manifold, D, E, n_default, desc = WORKLOADS[name]
+    n = args.cpu_particles
+    val, s_per_step = run_cpu(name, n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {desc}", "particles_per_gpu": args.particles or n_default,
+                   "note": "reference arm = the numpy restatement of pyRecEst's algorithm (oracle/pf_oracle.py); the real "
+                           "reference is pure Python, cannot travel to the GPU box and runs ~100x slower "
+                           "(1.05e4 particle-steps/s on T^3, BASELINE.md)"},
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{n} particles per step (bounded sample of the workload), {os.cpu_count()} host cores present, numpy single-threaded"},
+        "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="t3", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0)
+    ap.add_argument("--cpu-particles", type=int, default=200_000)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,394 @@
+"""Particle filters with the reference's class names, constructor signatures and method semantics
+(pyrecest/filters/*particle_filter.py, v0.9.1); predict / update / resample / estimate run in the
+libpfb.so kernels on the GPU.
+
+Differences a pyRecEst user must know (all from BASELINE.json's north_star):
+  * transitions and likelihoods come from a registry (registry.IdentityTransition /
+    LinearTransition; Gaussian, (hypertoroidal) wrapped-normal, von Mises, von Mises-Fisher
+    distributions).  Any other Python callable raises NotImplementedError -- it is not run on the CPU.
+  * extra, optional knobs: `resampling` ("multinomial" = reference, or "systematic"), `scan_exact`
+    (True = CDF bit-identical to numpy.cumsum), `validate` (read the device status word after each
+    update to raise the reference's AssertionErrors; costs one tiny D2H sync).
+  * HypersphericalParticleFilter exists (absent in the reference, configure_for_filter.py:90-100).
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import random as prandom
+from . import registry as R
+from ._engine import engine
+from .distributions import (
+    AbstractDiracDistribution,
+    CircularDiracDistribution,
+    HypersphericalDiracDistribution,
+    HypertoroidalDiracDistribution,
+    LinearDiracDistribution,
+    _as_device_tensor,
+    _default_device,
+)
+from .registry import IdentityTransition, LinearTransition  # noqa: F401  (re-export)
+
+TWO_PI = 2.0 * math.pi
+
+
+class AbstractParticleFilter:
+    """abstract_particle_filter.py:14-129 (+ abstract_filter.py:7-37)."""
+
+    _default_shift = True
+
+    def __init__(self, initial_filter_state=None):
+        self._filter_state = initial_filter_state
+        self.resampling = "multinomial"
+        self.scan_exact = True
+        self.validate = True
+        self._alt = None
+        self._logw = None
+        self._cdf = None
+        self._est = None
+        self.last_log_max = None
+
+    # ---- state ---------------------------------------------------------------------------------
+    @property
+    def filter_state(self):
+        return self._filter_state
+
+    @filter_state.setter
+    def filter_state(self, new_state):
+        self._set_filter_state(new_state)
+
+    def _set_filter_state(self, new_state):
+        """abstract_particle_filter.py:75-93."""
+        if self._filter_state is None:
+            self._filter_state = copy.deepcopy(new_state)
+        elif isinstance(new_state, type(self.filter_state)):
+            assert self.filter_state.d.shape == new_state.d.shape
+            self._filter_state = copy.deepcopy(new_state)
+        else:
+            n = self.filter_state.w.shape[0]
+            samples = new_state.sample(n)
+            samples = _as_device_tensor(samples, dtype=self._filter_state.d.dtype, device=self._filter_state.device)
+            assert samples.shape == self.filter_state.d.shape
+            self._filter_state._d = samples
+            self._filter_state._w = torch.full((n,), 1.0 / n, dtype=torch.float64, device=samples.device)
+            self._filter_state._uniform = True
+            self._filter_state._est_cache = None
+
+    @property
+    def dim(self):
+        return self.filter_state.dim
+
+    def _eng(self):
+        return engine(self._filter_state.device)
+
+    def _scratch(self):
+        st = self._filter_state
+        x = st._records()
+        N = x.shape[0]
+        if self._alt is None or self._alt.shape != x.shape or self._alt.dtype != x.dtype or self._alt.device != x.device:
+            self._alt = torch.empty_like(x)
+            self._logw = torch.empty(N, dtype=torch.float64, device=x.device)
+            self._cdf = torch.empty(N, dtype=torch.float64, device=x.device)
+            self._est = torch.empty(2 * L.PFB_MAXD, dtype=torch.float64, device=x.device)
+        return x
+
+    # ---- predict ----------------------------------------------------------------------------------
+    def predict_identity(self, noise_distribution):
+        """abstract_particle_filter.py:18-19 (dispatches the identity transition directly)."""
+        self.predict_nonlinear(IdentityTransition(), noise_distribution)
+
+    def _predict_params(self, f, noise_distribution, shift_instead_of_add):
+        raise NotImplementedError
+
+    def predict_nonlinear(self, f, noise_distribution=None, function_is_vectorized=True, shift_instead_of_add=None):
+        """abstract_particle_filter.py:21-54: d <- f(d), then one noise draw per particle."""
+        if shift_instead_of_add is None:
+            shift_instead_of_add = self._default_shift
+        st = self._filter_state
+        assert noise_distribution is None or self._noise_dim_ok(noise_distribution)
+        p, noise = self._predict_params(f, noise_distribution, shift_instead_of_add)
+        x = st._records()
+        self._eng().predict(p, x, x, noise)  # in place
+        st._d = x.reshape(st._d.shape)
+        st._est_cache = None
+
+    def _noise_dim_ok(self, noise):
+        return self.filter_state.dim == noise.dim
+
+    def predict_nonlinear_nonadditive(self, f, samples, weights):
+        raise NotImplementedError(
+            "predict_nonlinear_nonadditive needs an arbitrary f(x, noise) callable; it is the next row of the "
+            "scope table (SURVEY.md 8f-1) and not on the CUDA path yet."
+        )
+
+    def _fill_transition(self, p, f):
+        D = p.dim
+        F, b = R.transition_params(f, D)
+        if F is not None:
+            p.has_F = 1
+            p.F[: D * D] = np.asarray(F, dtype=np.float64).reshape(-1).tolist()
+        if b is not None:
+            p.has_b = 1
+            p.b[:D] = np.asarray(b, dtype=np.float64).reshape(-1).tolist()
+
+    # ---- update -----------------------------------------------------------------------------------
+    def update_identity(self, meas_noise, measurement, shift_instead_of_add=True):
+        """abstract_particle_filter.py:95-109."""
+        m = None if measurement is None else R._np(measurement)
+        assert m is None or m.shape == (meas_noise.dim,) or m.shape == (getattr(meas_noise, "input_dim", meas_noise.dim),) \
+            or meas_noise.dim == 1 and m.shape == ()
+        if not shift_instead_of_add:
+            raise NotImplementedError()
+        likelihood = meas_noise.set_mode(m).pdf
+        self.update_nonlinear_using_likelihood(likelihood)
+
+    def update_nonlinear_using_likelihood(self, likelihood, measurement=None):
+        """abstract_particle_filter.py:111-125: reweigh, resample N of N, uniform weights."""
+        dist = R.as_distribution(likelihood)
+        if measurement is not None:
+            dist = copy.deepcopy(dist).set_mode(R._np(measurement))
+        st = self._filter_state
+        x = self._scratch()
+        eng = self._eng()
+        N, D = x.shape
+        lp, keep = R.lik_params(dist, D, images_to_device=lambda t: torch.as_tensor(t, device=x.device).contiguous())
+        eng.loglik(lp, x, self._logw, w_prev=st._weights_or_none())
+        self._resample_from_logw(x, keep)
+
+    def _est_kind(self):
+        return L.EST_SUM
+
+    def _resample_from_logw(self, x, keep=None):
+        st = self._filter_state
+        eng = self._eng()
+        N, D = x.shape
+        if self.validate:
+            stats = eng.stats.cpu()
+            flags = int(stats[L.STAT_FLAGS])
+            self.last_log_max = float(stats[L.STAT_MAX])
+            assert not flags & 1, "All weights should be greater than or equal to 0."
+            assert not flags & 2, "The sum of all weights should be greater than 0."
+        eng.scan(self._cdf, logw=self._logw, exact=self.scan_exact)
+        systematic = self.resampling == "systematic"
+        if not systematic and self.resampling != "multinomial":
+            raise ValueError(f"unknown resampling scheme {self.resampling!r}")
+        u = prandom.source().uniforms((1,) if systematic else (N,), x.device)
+        eng.resample(self._cdf, u, x, self._alt, N, D, systematic=systematic, est_kind=self._est_kind(),
+                     est_out=self._est)
+        del keep
+        new = self._alt
+        self._alt = x
+        st._d = new.reshape(st._d.shape)
+        st._w = torch.full((N,), 1.0 / N, dtype=torch.float64, device=x.device) if not st._uniform else st._w
+        st._uniform = True
+        st._est_cache = self._estimate_from_sums(self._est, D)
+
+    def _estimate_from_sums(self, est, D):
+        return est[:D].clone()
+
+    def association_likelihood(self, likelihood):
+        """abstract_particle_filter.py:127-129: sum_i w_i pdf(d_i)."""
+        st = self._filter_state
+        dist = R.as_distribution(likelihood)
+        x = st._records()
+        lp, keep = R.lik_params(dist, x.shape[1], images_to_device=lambda t: torch.as_tensor(t, device=x.device).contiguous())
+        logw = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+        self._eng().loglik(lp, x, logw)
+        del keep
+        return torch.sum(torch.exp(logw) * st.w)
+
+    # ---- estimate ----------------------------------------------------------------------------------
+    def get_point_estimate(self):
+        return self.filter_state.mean()
+
+
+# -------------------------------------------------------------------------------------------------
+class EuclideanParticleFilter(AbstractParticleFilter):
+    """euclidean_particle_filter.py:18-69."""
+
+    _default_shift = False
+
+    def __init__(self, n_particles, dim, dtype=torch.float64, device=None):
+        if not (isinstance(n_particles, int) and n_particles > 0):
+            raise ValueError("n_particles must be a positive integer")
+        if not (isinstance(dim, int) and dim > 0):
+            raise ValueError("dim must be a positive integer")
+        device = _default_device() if device is None else torch.device(device)
+        initial = LinearDiracDistribution(torch.zeros((n_particles, dim), dtype=dtype, device=device))
+        AbstractParticleFilter.__init__(self, initial)
+
+    def _set_filter_state(self, new_state):
+        if not isinstance(new_state, LinearDiracDistribution):
+            dist_dirac = LinearDiracDistribution.from_distribution(new_state, self._filter_state.d.shape[0])
+            dist_dirac._d = dist_dirac._d.to(self._filter_state.d.dtype)
+        else:
+            dist_dirac = copy.deepcopy(new_state)
+        if self._filter_state.d.shape != dist_dirac.d.shape:
+            raise ValueError("The shape of new state does not match with the existing state.")
+        self._filter_state = dist_dirac
+
+    def _predict_params(self, f, noise, shift):
+        D = self._filter_state._stored_dim
+        p = L.PredictParams()
+        p.mode, p.dim = L.PRED_EUCLID, D
+        self._fill_transition(p, f)
+        kind, spec = R.predict_noise_spec(noise, D)
+        if kind is None:
+            return p, None
+        if kind != "gauss":
+            raise NotImplementedError("Euclidean filters take Gaussian system noise")
+        N = self._filter_state.w.shape[0]
+        z = prandom.source().normals((N, D), self._filter_state.device, self._filter_state.d.dtype)
+        p.noise_cols, p.has_A = D, 1
+        p.A[: D * D] = spec["A"].reshape(-1).tolist()
+        if not shift:  # add-mode keeps the noise mean; shift-mode replaces it by the particle
+            p.has_mu_noise = 1
+            p.mu_noise[:D] = spec["mu"].tolist()
+        return p, z
+
+    def get_point_estimate(self):
+        """abstract_euclidean_filter.py:9-11."""
+        return self.filter_state.mean()
+
+
+class HypertoroidalParticleFilter(AbstractParticleFilter):
+    """hypertoroidal_particle_filter.py:27-67."""
+
+    _default_shift = True
+
+    def __init__(self, n_particles, dim, dtype=torch.float64, device=None):
+        device = _default_device() if device is None else torch.device(device)
+        if dim == 1:
+            points = torch.linspace(0.0, TWO_PI, n_particles + 1, dtype=torch.float64, device=device)[:-1]
+        else:
+            col = torch.arange(n_particles, dtype=torch.float64, device=device) * (TWO_PI / n_particles)
+            points = col[:, None].expand(n_particles, dim)
+        filter_state = HypertoroidalDiracDistribution(points.to(dtype).contiguous(), dim=dim)
+        AbstractParticleFilter.__init__(self, filter_state)
+
+    def _predict_params(self, f, noise, shift):
+        st = self._filter_state
+        D = st._stored_dim
+        p = L.PredictParams()
+        p.mode, p.dim = (L.PRED_TORUS_SHIFT if shift else L.PRED_TORUS_ADD), D
+        self._fill_transition(p, f)
+        kind, spec = R.predict_noise_spec(noise, D)
+        if kind is None:
+            return p, None
+        N = st.w.shape[0]
+        src = prandom.source()
+        p.noise_cols = D
+        if kind in ("wn", "gauss"):
+            z = src.normals((N, D), st.device, st.d.dtype)
+            p.has_A = 1
+            p.A[: D * D] = spec["A"].reshape(-1).tolist()
+            mu = np.mod(spec["mu"], TWO_PI)
+        elif kind == "vm":
+            kap = spec["kappa"]
+            kap = np.broadcast_to(kap, (D,)) if kap.shape[0] in (1, D) else kap
+            z = src.vonmises((N, D), torch.as_tensor(np.ascontiguousarray(kap)), st.device, st.d.dtype)
+            mu = np.mod(np.broadcast_to(spec["mu"], (D,)), TWO_PI)
+        else:
+            raise NotImplementedError(f"{kind} noise is not defined on the hypertorus")
+        if not shift:
+            p.has_mu_noise = 1
+            p.mu_noise[:D] = np.asarray(mu, dtype=np.float64).tolist()
+        return p, z
+
+    def _noise_dim_ok(self, noise):
+        return self.filter_state.dim == noise.dim or R.kind_of(noise) == "vm"
+
+    def _est_kind(self):
+        return L.EST_TRIG
+
+    def _estimate_from_sums(self, est, D):
+        t = est[: 2 * D].reshape(D, 2)
+        m = torch.remainder(torch.atan2(t[:, 1], t[:, 0]), TWO_PI)
+        return m[0] if self._filter_state._one_d else m
+
+    def get_point_estimate(self):
+        """abstract_hypertoroidal_filter.py:17-25."""
+        return self.filter_state.mean_direction()
+
+
+class CircularParticleFilter(HypertoroidalParticleFilter):
+    """circular_particle_filter.py:13-37."""
+
+    def __init__(self, n_particles, dtype=torch.float64, device=None):
+        device = _default_device() if device is None else torch.device(device)
+        pts = torch.linspace(0.0, TWO_PI, n_particles + 1, dtype=torch.float64, device=device)[:-1]
+        AbstractParticleFilter.__init__(self, CircularDiracDistribution(pts.to(dtype).contiguous()))
+
+    def compute_association_likelihood(self, likelihood):
+        return self.association_likelihood(likelihood)
+
+
+class ToroidalParticleFilter(HypertoroidalParticleFilter):
+    """toroidal_particle_filter.py:9-11."""
+
+    def __init__(self, n_particles, dtype=torch.float64, device=None):
+        HypertoroidalParticleFilter.__init__(self, n_particles, 2, dtype=dtype, device=device)
+
+
+class HypersphericalParticleFilter(AbstractParticleFilter):
+    """New (the reference raises "HypersphericalParticleFilter not implemented yet",
+    evaluation/configure_for_filter.py:90-100).  State: HypersphericalDiracDistribution on S^dim,
+    stored as (N, dim + 1) unit vectors.  Predict follows the sphere pattern of
+    hyperhemisphere_cart_prod_particle_filter.py:90-95 (noise.set_mode(f(d)[j]); d[j] = noise.sample(1))
+    with von Mises-Fisher noise on S^2, or additive Gaussian noise in the embedding space followed by
+    renormalisation.  Estimate = mean direction (hyperspherical_dirac_distribution.py:38-44)."""
+
+    _default_shift = True
+
+    def __init__(self, n_particles, dim, dtype=torch.float64, device=None):
+        if not (isinstance(n_particles, int) and n_particles > 0):
+            raise ValueError("n_particles must be a positive integer")
+        if not (isinstance(dim, int) and dim > 0):
+            raise ValueError("dim must be a positive integer")
+        device = _default_device() if device is None else torch.device(device)
+        d = torch.zeros((n_particles, dim + 1), dtype=dtype, device=device)
+        d[:, -1] = 1.0
+        AbstractParticleFilter.__init__(self, HypersphericalDiracDistribution(d))
+
+    def _noise_dim_ok(self, noise):
+        return noise.dim == self.filter_state.dim or getattr(noise, "dim", None) == self.filter_state.input_dim
+
+    def _predict_params(self, f, noise, shift):
+        st = self._filter_state
+        D = st._stored_dim
+        p = L.PredictParams()
+        p.dim = D
+        p.mode = L.PRED_EUCLID
+        self._fill_transition(p, f)
+        kind, spec = R.predict_noise_spec(noise, D)
+        if kind is None:
+            return p, None
+        N = st.w.shape[0]
+        src = prandom.source()
+        if kind == "vmf":
+            if D != 3:
+                raise NotImplementedError("von Mises-Fisher system noise is implemented on S^2")
+            p.mode, p.noise_cols = L.PRED_SPHERE_VMF, 3
+            p.kappa = spec["kappa"]
+            p.exp_m2k = float(np.exp(-2 * spec["kappa"]))
+            return p, src.vmf_triples(N, st.device, st.d.dtype)
+        if kind == "gauss":
+            p.mode, p.noise_cols, p.has_A = L.PRED_SPHERE_ADD, D, 1
+            p.A[: D * D] = spec["A"].reshape(-1).tolist()
+            if np.any(spec["mu"] != 0):
+                p.has_mu_noise = 1
+                p.mu_noise[:D] = spec["mu"].tolist()
+            return p, src.normals((N, D), st.device, st.d.dtype)
+        raise NotImplementedError(f"{kind} noise is not defined on the hypersphere")
+
+    def _estimate_from_sums(self, est, D):
+        r = est[:D]
+        return r / torch.linalg.norm(r)
+
+    def get_point_estimate(self):
+        return self.filter_state.mean_direction()

@@ -1,0 +1,161 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/pfb.h declares, the
+ctypes structs mirror the header, the host-side registry logic, and the product's refusal to run
+without its CUDA library."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "pfb.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyrecest_b200 import _lib as L
+
+    names = header_functions()
+    assert set(names) == set(L.SIGNATURES), (names, sorted(L.SIGNATURES))
+    handle = ctypes.CDLL(L.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    lib = L.lib()
+    assert lib.pfb_abi_version() == 1
+    assert lib.pfb_workspace_bytes(0) >= 256
+    assert lib.pfb_workspace_bytes(10**8) > lib.pfb_workspace_bytes(0)
+
+
+def test_struct_sizes_match_header():
+    from pyrecest_b200 import _lib as L
+
+    assert ctypes.sizeof(L.PredictParams) == 8 * 4 + 8 * (36 + 6 + 36 + 6 + 2)
+    assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8
+
+
+def test_argument_validation_without_gpu():
+    """host-side validation returns error codes before any CUDA call"""
+    from pyrecest_b200 import _lib as L
+
+    lib = L.lib()
+    p = L.PredictParams()
+    p.dim = 99
+    assert lib.pfb_predict(ctypes.byref(p), 0, 10, None, None, None, None) == 1
+    assert b"dim" in lib.pfb_last_error()
+    lp = L.LikParams()
+    lp.kind, lp.dim = 42, 3
+    assert lib.pfb_loglik(ctypes.byref(lp), 0, 10, None, None, None, None, None, 0, None) == 4
+    assert lib.pfb_scan_cdf(0, 10, None, None, None, None, None, 0, None) == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from pyrecest_b200 import _lib as L
+
+    monkeypatch.setattr(L, "_LIB", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.PfbError):
+        L.lib()
+
+
+def test_no_gpu_means_no_engine():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pyrecest_b200._engine import Engine
+
+    with pytest.raises(RuntimeError):
+        Engine("cuda:0")
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pyrecest_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_registry_rejects_callables_and_maps_kinds():
+    from pyrecest_b200 import registry as R
+    from pyrecest_b200.distributions import GaussianDistribution, VonMisesFisherDistribution
+
+    g = GaussianDistribution(np.zeros(2), np.eye(2))
+    assert R.kind_of(g) == "gauss"
+    assert R.as_distribution(g.pdf) is g
+    with pytest.raises(NotImplementedError):
+        R.as_distribution(lambda x: x)
+    with pytest.raises(NotImplementedError):
+        R.transition_params(lambda x: x, 2)
+    assert R.transition_params(R.IdentityTransition(), 2) == (None, None)
+    with pytest.raises(ValueError):
+        R.transition_params(R.LinearTransition(np.eye(3)), 2)
+    v = VonMisesFisherDistribution(np.array([0.0, 0.0, 1.0]), 2.0)
+    np.testing.assert_allclose(v.C, 2.0 / (4 * np.pi * np.sinh(2.0)), rtol=1e-14)
+    for D, k in ((3, 0.5), (3, 700.0), (4, 10.0), (5, 3.0)):
+        ref = O.vmf_norm_const(k, D) if k < 600 else None
+        if ref is not None:
+            np.testing.assert_allclose(np.exp(R.vmf_log_norm_const(k, D)), ref, rtol=1e-13)
+        assert np.isfinite(R.vmf_log_norm_const(k, D))
+
+
+def test_registry_likelihood_parameters_follow_scipy():
+    from pyrecest_b200 import registry as R
+
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((3, 3))
+    C = A @ A.T + 0.2 * np.eye(3)
+    W, logdet = R.gaussian_whitening(C)
+    Wo, lo = O.gaussian_whitening(C)
+    assert np.array_equal(W, Wo) and logdet == lo
+    np.testing.assert_allclose(W @ W.T, np.linalg.inv(C), rtol=1e-10)
+    assert np.array_equal(R.gaussian_noise_factor(C), O.gaussian_noise_factor(C))
+    np.testing.assert_allclose(R.log_i0(3.0), np.log(np.i0(3.0)), rtol=1e-13)
+
+
+@pytest.mark.parametrize("scale,mu", [(0.5, [1.0, 2.0, 3.0]), (0.05, [6.2, 0.01, 3.1]), (1.0, [0.0, 0.0, 0.0]), (4.0, [3.0, 5.0, 1.0])])
+def test_wn_image_pruning_reproduces_the_full_343_term_sum(scale, mu):
+    """The pruned image table (host logic of the wn_multi kernel) evaluated in numpy equals the
+    reference's full (2m+1)^d sum to rounding, for points all over [0, 2pi]^3 incl. the edges."""
+    from pyrecest_b200 import registry as R
+
+    C3 = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+    C = scale * C3
+    mu = np.array(mu)
+    W, logdet = R.gaussian_whitening(C)
+    table, K = R.wn_image_table(mu, W @ W.T)
+    assert 1 <= K <= 343 and table.shape == (K, 7)
+    rng = np.random.default_rng(0)
+    x = rng.random((3000, 3)) * 2 * np.pi
+    x[:4] = [[0, 0, 0], [2 * np.pi] * 3, [np.pi] * 3, [np.pi, 0, 2 * np.pi]]
+    xs = (x + np.pi) % (2 * np.pi) - np.pi
+    dev = xs - mu
+    logc = -0.5 * (3 * np.log(2 * np.pi) + logdet)
+    tot = np.zeros(x.shape[0])
+    for row in table:
+        y = (dev + row[4:7]) @ W
+        tot += np.exp(logc - 0.5 * np.sum(y * y, axis=1))
+    ref = O.pdf_wn_multi(x, mu, C)
+    ok = ref > 1e-290
+    np.testing.assert_allclose(tot[ok], ref[ok], rtol=2e-12)  # |maha| up to ~1400: rounding of the exponent, not pruning
+    if scale <= 0.5:
+        assert K < 100  # pruning is effective for peaked likelihoods
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-particles", "2000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"

@@ -1,0 +1,256 @@
+"""The public API (pyrecest_b200.filters / .distributions) against the golden runs of the real
+reference with the same injected draws, plus the reference's own statistical filter tests."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def test_euclid_cv_against_reference_run(golden):
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200.filters import EuclideanParticleFilter, LinearTransition
+
+    g = golden("euclid_cv")
+    N, T = g["d0"].shape[0], g["Z"].shape[0]
+    pf = EuclideanParticleFilter(N, 2)
+    with prandom.inject(normals=np.concatenate([g["Z0"].ravel(), g["Z"].ravel()]), uniforms=g["U"]):
+        pf.filter_state = GaussianDistribution(g["prior_mu"], g["prior_C"])
+        np.testing.assert_allclose(host(pf.filter_state.d), g["d0"], rtol=1e-13, atol=1e-15)
+        for t in range(T):
+            pf.predict_nonlinear(LinearTransition(g["F"]), GaussianDistribution(np.zeros(2), g["Q"]))
+            np.testing.assert_allclose(host(pf.filter_state.d), g["d_pred"][t], rtol=1e-12, atol=1e-13)
+            pf.update_identity(GaussianDistribution(np.zeros(2), g["R"]), g["zs"][t])
+            np.testing.assert_allclose(host(pf.filter_state.d), g["d_post"][t], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(host(pf.filter_state.w), 1.0 / N)
+            np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t], rtol=1e-12)
+
+
+def test_torus_t3_against_reference_run(golden):
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN
+    from pyrecest_b200.filters import HypertoroidalParticleFilter
+
+    g = golden("torus_t3")
+    N, T = g["d0"].shape[0], g["Z"].shape[0]
+    pf = HypertoroidalParticleFilter(N, 3)
+    assert pf.filter_state.d.shape == (N, 3)
+    with prandom.inject(normals=np.concatenate([g["Z0"].ravel(), g["Z"].ravel()]), uniforms=g["U"]):
+        pf.filter_state = HWN(g["mu0"], g["C"])
+        assert np.abs(host(pf.filter_state.d) - g["d0"]).max() < 1e-13
+        for t in range(T):
+            pf.predict_identity(HWN(np.zeros(3), g["Cn"]))
+            assert np.abs(host(pf.filter_state.d) - g["d_pred"][t]).max() < 1e-12
+            pf.update_identity(HWN(np.zeros(3), g["Cl"]), g["zs"][t])
+            assert np.abs(host(pf.filter_state.d) - g["d_post"][t]).max() < 1e-12
+            np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t], rtol=1e-12)
+            # cached estimate == recomputed moment
+            pf.filter_state._est_cache = None
+            np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t], rtol=1e-12)
+
+
+def test_circle_against_reference_run(golden):
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import (
+        HypertoroidalWrappedNormalDistribution as HWN,
+        VonMisesDistribution,
+        WrappedNormalDistribution,
+    )
+    from pyrecest_b200.filters import CircularParticleFilter
+
+    g = golden("circle_case")
+    N = g["d0"].shape[0]
+    pf = CircularParticleFilter(N)
+    assert pf.filter_state.d.shape == (N,)
+    np.testing.assert_allclose(host(pf.filter_state.d), g["d0"], rtol=1e-15, atol=1e-15)
+    pf.filter_state.d = g["d0"]
+    liks = [VonMisesDistribution(np.array(2.0), 1.5), WrappedNormalDistribution(np.array(4.0), np.array(0.7))]
+    with prandom.inject(normals=g["Z"], uniforms=g["U"]):
+        for t in range(2):
+            pf.predict_identity(HWN(np.zeros(1), np.array([[float(g["sig_n"]) ** 2]])))
+            assert pf.filter_state.d.shape == (N,)
+            assert np.abs(host(pf.filter_state.d) - g["d_pred"][t]).max() < 1e-13
+            np.testing.assert_allclose(host(liks[t].pdf(pf.filter_state.d)), g["lik"][t], rtol=1e-12)
+            pf.update_nonlinear_using_likelihood(liks[t])
+            assert np.abs(host(pf.filter_state.d) - g["d_post"][t]).max() < 1e-13
+            np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t][0], rtol=1e-12)
+
+
+def test_sphere_filter_against_oracle():
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import VonMisesFisherDistribution as VMF
+    from pyrecest_b200.filters import HypersphericalParticleFilter
+
+    rng = np.random.default_rng(12)
+    N = 5000
+    trip0 = np.column_stack([rng.random(N), rng.standard_normal((N, 2))])
+    trip = np.column_stack([rng.random(2 * N), rng.standard_normal((2 * N, 2))]).reshape(2, N, 3)
+    U = rng.random((2, N))
+    z = np.array([1.0, 1.0, 1.0]) / math.sqrt(3)
+    pf = HypersphericalParticleFilter(N, 2)
+    with prandom.inject(vmf_triples=np.concatenate([trip0.ravel(), trip.ravel()]), uniforms=U):
+        pf.filter_state = VMF(np.array([0.0, 0.0, 1.0]), 5.0)
+        d = O.predict_sphere_vmf(np.tile([0.0, 0.0, 1.0], (N, 1)), trip0, 5.0)
+        np.testing.assert_allclose(host(pf.filter_state.d), d, atol=2e-14)
+        for t in range(2):
+            pf.predict_identity(VMF(np.array([0.0, 0.0, 1.0]), 50.0))
+            pf.update_nonlinear_using_likelihood(VMF(z, 10.0))
+            ref = O.step("sphere", d, trip[t], "vmf", {"mu": z, "kappa": 10.0}, U[t], kappa_noise=50.0)
+            np.testing.assert_allclose(host(pf.filter_state.d), ref["d"], atol=1e-13)
+            np.testing.assert_allclose(host(pf.get_point_estimate()), ref["est"], rtol=1e-12)
+            d = ref["d"]
+    # additive Gaussian noise + renormalise
+    from pyrecest_b200.distributions import GaussianDistribution
+
+    Zs = rng.standard_normal((N, 3))
+    with prandom.inject(normals=Zs):
+        pf.predict_identity(GaussianDistribution(np.zeros(3), 0.01 * np.eye(3)))
+    ref = O.predict_sphere_additive(d, O.gaussian_rows(Zs, 0.01 * np.eye(3)))
+    np.testing.assert_allclose(host(pf.filter_state.d), ref, rtol=1e-12, atol=1e-14)
+
+
+def test_von_mises_noise_on_torus_and_systematic_resampling():
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN, VonMisesDistribution
+    from pyrecest_b200.filters import HypertoroidalParticleFilter
+
+    rng = np.random.default_rng(13)
+    N = 4000
+    C3 = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+    d0 = rng.random((N, 3)) * 2 * np.pi
+    vm = rng.vonmises(0.0, 10.0, size=(N, 3))
+    z = np.array([1.0, 2.0, 3.0])
+    pf = HypertoroidalParticleFilter(N, 3)
+    pf.filter_state.d = d0
+    pf.resampling = "systematic"
+    with prandom.inject(vonmises=vm, uniforms=np.array([0.4321])):
+        pf.predict_identity(VonMisesDistribution(np.zeros(3), np.array([10.0, 10.0, 10.0])))
+        dp = O.predict_torus(d0, vm, shift=True)
+        assert np.array_equal(host(pf.filter_state.d), dp)
+        pf.update_identity(HWN(np.zeros(3), 0.5 * C3), z)
+    lik = O.pdf_wn_multi(dp, z, 0.5 * C3)
+    idx = O.systematic_indices(O.reweigh(O.uniform_w(N), lik), 0.4321)
+    got = host(pf.filter_state.d)
+    mism = np.any(got != dp[idx], axis=1).sum()
+    assert mism <= 2, f"{mism} particles differ from the oracle's systematic resampling"
+    assert np.all(np.diff(idx) >= 0)
+
+
+def test_statistical_convergence_like_reference_tests():
+    """pyrecest/tests/filters/test_euclidean_particle_filter.py:24-34 and
+    test_hypertoroidal_particle_filter.py:50-58 (device RNG, statistical tolerance)."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution, HypertoroidalWrappedNormalDistribution as HWN
+    from pyrecest_b200.filters import EuclideanParticleFilter, HypertoroidalParticleFilter
+
+    prandom.seed(42)
+    C = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+    mu = np.array([5.0, 6.0, 7.0])
+    pf = EuclideanParticleFilter(1000, 3)
+    pf.filter_state = GaussianDistribution(mu, C)
+    forced_mean = np.array([1.0, 2.0, 3.0])
+    sys_noise = GaussianDistribution(np.zeros(3), 0.5 * C)
+    for _ in range(50):
+        pf.predict_identity(sys_noise)
+        for _ in range(3):
+            pf.update_identity(sys_noise, forced_mean)
+    np.testing.assert_allclose(host(pf.get_point_estimate()), forced_mean, atol=0.15)
+
+    hpf = HypertoroidalParticleFilter(500, 3)
+    hpf.filter_state = HWN(np.array([1.0, 1.0, 1.0]) + math.pi / 2, C)
+    forced = np.array([1.0, 2.0, 3.0])
+    for _ in range(5):
+        hpf.predict_identity(HWN(np.zeros(3), 0.5 * C))
+        for _ in range(3):
+            hpf.update_identity(HWN(np.zeros(3), 0.5 * C), forced)
+    est = host(hpf.get_point_estimate())
+    assert est.shape == (3,)
+    np.testing.assert_allclose(est, forced, atol=0.15)
+
+
+def test_api_shapes_errors_and_rejections():
+    from pyrecest_b200.distributions import (
+        GaussianDistribution,
+        HypertoroidalDiracDistribution,
+        LinearDiracDistribution,
+    )
+    from pyrecest_b200.filters import EuclideanParticleFilter, HypertoroidalParticleFilter, LinearTransition
+
+    with pytest.raises(ValueError):
+        EuclideanParticleFilter(0, 2)
+    with pytest.raises(ValueError):
+        EuclideanParticleFilter(10, 0)
+    pf = EuclideanParticleFilter(100, 1)
+    assert pf.filter_state.d.shape == (100, 1)
+    with pytest.raises(ValueError):
+        pf.filter_state = LinearDiracDistribution(np.zeros((50, 1)))
+    pf = EuclideanParticleFilter(64, 3)
+    with pytest.raises(NotImplementedError):
+        pf.predict_nonlinear(lambda x: x**2, None)
+    with pytest.raises(NotImplementedError):
+        pf.update_nonlinear_using_likelihood(lambda x: np.ones(64))
+    with pytest.raises(ValueError):
+        pf.predict_nonlinear(LinearTransition(np.eye(2)), None)
+    # all particles infinitely far -> the reference's "sum of all weights > 0" assertion
+    pf.filter_state.d = np.full((64, 3), 1e200)
+    with pytest.raises(AssertionError):
+        pf.update_identity(GaussianDistribution(np.zeros(3), np.eye(3)), np.zeros(3))
+    # noise-free predict equals apply_function (test_circular_particle_filter.py:71-83 pattern)
+    hp = HypertoroidalParticleFilter(200, 2)
+    rng = np.random.default_rng(0)
+    d0 = rng.random((200, 2)) * 2 * np.pi
+    hp.filter_state = HypertoroidalDiracDistribution(d0)
+    F = np.array([[1.0, 0.5], [0.0, 1.0]])
+    expect = hp.filter_state.apply_function(LinearTransition(F))
+    hp.predict_nonlinear(LinearTransition(F), None)
+    assert np.array_equal(host(hp.filter_state.d), host(expect.d))
+    np.testing.assert_allclose(host(expect.d), np.mod(d0 @ F.T, 2 * np.pi), atol=1e-12)
+    # Dirac sample with n != N, weights renormalisation warning
+    with pytest.warns(RuntimeWarning):
+        dd = HypertoroidalDiracDistribution(d0, np.ones(200))
+    s = dd.sample(77)
+    assert s.shape == (77, 2)
+    np.testing.assert_allclose(host(dd.w).sum(), 1.0)
+
+
+def test_dirac_moments_api(golden):
+    from pyrecest_b200.distributions import (
+        CircularDiracDistribution,
+        HypersphericalDiracDistribution,
+        HypertoroidalDiracDistribution,
+        LinearDiracDistribution,
+    )
+
+    g = golden("dirac_moments")
+    w = g["w"]
+    ld = LinearDiracDistribution(g["lin_d"], w)
+    np.testing.assert_allclose(host(ld.mean()), g["lin_mean"], rtol=1e-12)
+    np.testing.assert_allclose(host(ld.covariance()), g["lin_cov"], rtol=1e-11)
+    td = HypertoroidalDiracDistribution(g["tor_d"], w)
+    np.testing.assert_allclose(host(td.trigonometric_moment(1)), g["tor_m1"], rtol=1e-12)
+    np.testing.assert_allclose(host(td.trigonometric_moment(2)), g["tor_m2"], rtol=1e-11)
+    np.testing.assert_allclose(host(td.mean_direction()), g["tor_meandir"], rtol=1e-12)
+    cd = CircularDiracDistribution(g["circ_d"], w)
+    np.testing.assert_allclose(host(cd.mean_direction()), g["circ_meandir"][0], rtol=1e-12)
+    sd = HypersphericalDiracDistribution(g["sph_d"], w)
+    np.testing.assert_allclose(host(sd.mean_resultant_vector()), g["sph_res"], rtol=1e-12)
+    np.testing.assert_allclose(host(sd.mean_direction()), g["sph_meandir"], rtol=1e-12)
+    np.testing.assert_allclose(host(sd.moment()), g["sph_scatter"], rtol=1e-11, atol=1e-15)
+    from pyrecest_b200 import random as prandom
+
+    with prandom.inject(uniforms=g["tor_sample_u"]):
+        smp = td.sample(1234)
+    assert np.array_equal(host(smp), g["tor_sample"])
+    from pyrecest_b200.distributions import GaussianDistribution
+
+    rw = ld.reweigh(GaussianDistribution(np.ones(4), np.eye(4)))
+    np.testing.assert_allclose(host(rw.w), g["lin_reweighed"], rtol=1e-12)
