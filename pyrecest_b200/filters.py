@@ -291,7 +291,7 @@ class HypertoroidalParticleFilter(AbstractParticleFilter):
         elif kind == "vm":
             kap = spec["kappa"]
             kap = np.broadcast_to(kap, (D,)) if kap.shape[0] in (1, D) else kap
-            z = src.vonmises((N, D), torch.as_tensor(np.ascontiguousarray(kap)), st.device, st.d.dtype)
+            z = src.vonmises((N, D), torch.as_tensor(np.array(kap, dtype=np.float64)), st.device, st.d.dtype)
             mu = np.mod(np.broadcast_to(spec["mu"], (D,)), TWO_PI)
         else:
             raise NotImplementedError(f"{kind} noise is not defined on the hypertorus")
