@@ -307,14 +307,17 @@ def run_gpu(args):
         pf.update_identity(lik_dist, z)
         return pf.get_point_estimate().cpu()  # D2H of the estimate (the status word is read inside update)
 
-    for _ in range(min(args.warmup, 3)):
-        api_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        api_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if args.e2e_steps > 0:
+        for _ in range(min(args.warmup, 3)):
+            api_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            api_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    else:
+        e2e_ms = float("nan")
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     vals = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)

@@ -44,12 +44,25 @@ constexpr int kGuideShift = 3;           // guide table: one bucket per 2^3 = 8 
 
 inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
 inline int64_t ws_header() { return kWsCounters + kWsPartials; }
+// guide table of the resampling search: M = 2^k buckets, M >= n / 2^kGuideShift (PFB_GUIDE_SHIFT overrides)
+int guide_shift();
+inline int64_t guide_buckets(int64_t n) {
+  int64_t want = n >> guide_shift();
+  int64_t M = 1;
+  while (M < want) M <<= 1;
+  return M;
+}
+inline int64_t guide_offset(int64_t n) {
+  return (ws_header() + scan_tiles(n) * kTileStateBytes + 255) & ~(int64_t)255;
+}
 
 struct Workspace {
   unsigned int* counters;
   double* partials;
   unsigned char* tiles;
   int64_t tile_bytes;
+  int32_t* guide;
+  int64_t guide_buckets;
 };
 int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out);
 
@@ -57,6 +70,14 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out);
 // numpy/_core/src/npymath: mod = fmod(a, b); if (mod) { if ((b < 0) != (mod < 0)) mod += b; }
 // else mod = copysign(0, b).   fmod is exact, the add is one IEEE rounding (can return 2*pi).
 __device__ __forceinline__ double np_mod_2pi(double a) {
+  // fast exact paths for |a| < 4 pi (every in-range particle +- noise lands here):
+  //   [0, 2pi): fmod = a.   [2pi, 4pi): fmod = a - 2pi, exact by Sterbenz.   (-2pi, 0): fmod = a, then += 2pi.
+  if (a >= 0.0) {
+    if (a < kTwoPi) return a + 0.0;          // -0.0 -> +0.0 like copysign(0, b)
+    if (a < 2.0 * kTwoPi) return a - kTwoPi;
+  } else if (a > -kTwoPi) {
+    return a + kTwoPi;
+  }
   double m = fmod(a, kTwoPi);
   if (m != 0.0) {
     if (m < 0.0) m += kTwoPi;

@@ -174,7 +174,9 @@ __device__ __forceinline__ double whitened_sq(const pfb_lik_params& L, const dou
 }
 
 constexpr double kPi = 3.141592653589793;
-constexpr double kImageCut = 90.0;  // drop images whose maha exceeds the best one by this much (e^-45)
+constexpr double kImageCut = 90.0;  // screen: drop images whose maha exceeds the best one by this much (e^-45)
+constexpr float kScreenCut = 92.0f; // the same cut for the fp32 screen, plus slack for its rounding
+constexpr double kTermCut = 76.0;   // a term e^-38 below the best one cannot change the fp64 sum
 
 template <int D, int KIND>
 __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const double (&x)[D],
@@ -185,39 +187,74 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     for (int c = 0; c < D; ++c) dev[c] = x[c] - L.mu[c];
     return L.logc - 0.5 * whitened_sq<D>(L, dev);
   } else if constexpr (KIND == PFB_LIK_WN_MULTI) {
-    // xs = (xs + pi) % (2 pi) - pi; sum over the image table of mvn.pdf(xs + 2 pi k)
+    // xs = (xs + pi) % (2 pi) - pi; sum over the image table of mvn.pdf(xs + 2 pi k).
+    // maha_k - maha_j = 2 (g_k - g_j).dev + (h_k - h_j) is linear in dev, so images are screened with
+    // r_k = 2 g_k.dev + h_k.  K <= 64 and D <= 3: the screen runs in fp32 on a float4 table and
+    // leaves a bit mask of candidates (a superset of {k : r_k <= min r + cut}); only those get the
+    // exact fp64 quadratic form and, if they can contribute more than e^-37, an exp.
     double dev[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kPi) - kPi) - L.mu[c];
-    const double q0 = whitened_sq<D>(L, dev);
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
-    // pass 1: cheap maha_k = q0 + 2 g_k.dev + h_k, find the minimum
+    double best = INFINITY, sum = 0.0;
+    auto accumulate = [&](const double* row) {
+      double sh[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) sh[c] = dev[c] + row[D + 1 + c];
+      const double ma = whitened_sq<D>(L, sh);
+      if (ma < best) {
+        const double d = best - ma;              // rescale what was summed so far to the new best
+        sum = (d <= kTermCut ? sum * exp(-0.5 * d) : 0.0) + 1.0;
+        best = ma;
+      } else {
+        const double d = ma - best;
+        if (d <= kTermCut) sum += exp(-0.5 * d);
+      }
+    };
+    if constexpr (D <= 3) {
+      if (K <= 64) {
+        const float4* scr = reinterpret_cast<const float4*>(images + K * ROW + ((K * ROW) & 1));
+        float df[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) df[c] = (c < D) ? (float)dev[c] : 0.0f;
+        float runmin = INFINITY;
+        unsigned long long mask = 0ULL;
+        for (int k = 0; k < K; ++k) {
+          const float4 t = scr[k];
+          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
+          if (r <= runmin + kScreenCut) mask |= (1ULL << k);
+          runmin = fminf(runmin, r);
+        }
+        const float lim = runmin + kScreenCut;
+        while (mask) {
+          const int k = __ffsll((long long)mask) - 1;
+          mask &= mask - 1ULL;
+          const float4 t = scr[k];
+          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
+          if (r <= lim) accumulate(images + k * ROW);
+        }
+        return L.logc - 0.5 * best + (sum == 1.0 ? 0.0 : log(sum));
+      }
+    }
+    // generic path (D > 3 or more than 64 images): the same screen in fp64, two passes
+    const double q0 = whitened_sq<D>(L, dev);
     double mmin = INFINITY;
     for (int k = 0; k < K; ++k) {
       const double* row = images + k * ROW;
       double lin = row[0] * dev[0];
 #pragma unroll
       for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
-      double m = fma(2.0, lin, q0) + row[D];
-      mmin = fmin(mmin, m);
+      mmin = fmin(mmin, fma(2.0, lin, q0) + row[D]);
     }
-    // pass 2: accurate maha for the images that matter, summed relative to the cheap minimum
-    double sum = 0.0;
     for (int k = 0; k < K; ++k) {
       const double* row = images + k * ROW;
       double lin = row[0] * dev[0];
 #pragma unroll
       for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
-      double m = fma(2.0, lin, q0) + row[D];
-      if (m - mmin <= kImageCut) {
-        double sh[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) sh[c] = dev[c] + row[D + 1 + c];
-        sum += exp(-0.5 * (whitened_sq<D>(L, sh) - mmin));
-      }
+      if (fma(2.0, lin, q0) + row[D] - mmin <= kImageCut) accumulate(row);
     }
-    return L.logc - 0.5 * mmin + log(sum);
+    return L.logc - 0.5 * best + (sum == 1.0 ? 0.0 : log(sum));
   } else if constexpr (KIND == PFB_LIK_WN_1D) {
     if (L.sigma > 10.0) return -log(kTwoPi);
     double xx = np_mod_2pi(x[0]);
@@ -287,8 +324,22 @@ __device__ __forceinline__ void finish_max(double tmax, double tnan, double* sta
 template <int D>
 __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, double* smem_img) {
   if (L.kind != PFB_LIK_WN_MULTI) return nullptr;
-  const int count = L.n_images * (2 * D + 1);
+  constexpr int ROW = 2 * D + 1;
+  const int K = L.n_images;
+  const int count = K * ROW;
   for (int k = threadIdx.x; k < count; k += blockDim.x) smem_img[k] = L.images_dev[k];
+  if (D <= 3 && K <= 64) {  // fp32 screen rows (g0, g1, g2, h) after the fp64 table (16-byte aligned: count*8 + pad)
+    float4* scr = reinterpret_cast<float4*>(smem_img + count + (count & 1));
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const double* row = L.images_dev + k * ROW;
+      float4 t;
+      t.x = (float)row[0];
+      t.y = D > 1 ? (float)row[1] : 0.0f;
+      t.z = D > 2 ? (float)row[2] : 0.0f;
+      t.w = (float)row[D];
+      scr[k] = t;
+    }
+  }
   __syncthreads();
   return smem_img;
 }
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int6
                                                           const double* __restrict__ w_prev,
                                                           double* __restrict__ logw, double* stats,
                                                           Workspace ws) {
-  extern __shared__ double smem_dyn[];
+  extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
   double tmax = -INFINITY, tnan = 0.0;
@@ -323,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
                                                                   const T* __restrict__ noise,
                                                                   double* __restrict__ logw,
                                                                   double* stats, Workspace ws) {
-  extern __shared__ double smem_dyn[];
+  extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
   double tmax = -INFINITY, tnan = 0.0;
@@ -373,13 +424,13 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
     if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
-    if ((int64_t)L->n_images * (2 * dim + 1) * 8 > 48 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 16) + 8 > 48 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
   }
   return PFB_OK;
 }
 
 static size_t lik_smem(const pfb_lik_params* L) {
-  return L->kind == PFB_LIK_WN_MULTI ? (size_t)L->n_images * (2 * L->dim + 1) * 8 : 0;
+  return L->kind == PFB_LIK_WN_MULTI ? (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 16 : 0;
 }
 
 #define PFB_DISPATCH_MODE(mode, ...)                                                       \

@@ -1,6 +1,7 @@
 // K(4b) multinomial / systematic resampling (search + gather + fused estimate), K(5) weighted moments,
 // and the small host-side plumbing of the C ABI (errors, workspace).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pfb_common.cuh"
@@ -33,6 +34,16 @@ int sm_count() {
   return cached[dev];
 }
 
+int guide_shift() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PFB_GUIDE_SHIFT");
+    v = e ? atoi(e) : kGuideShift;
+    if (v < 0 || v > 20) v = kGuideShift;
+  }
+  return v;
+}
+
 int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   if (!ws) { set_error("workspace pointer is NULL"); return PFB_ERR_WORKSPACE; }
   if (((uintptr_t)ws & 255) != 0) { set_error("workspace must be 256-byte aligned"); return PFB_ERR_WORKSPACE; }
@@ -47,6 +58,8 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   out->partials = reinterpret_cast<double*>(b + kWsCounters);
   out->tiles = b + ws_header();
   out->tile_bytes = ws_bytes - ws_header();
+  out->guide = reinterpret_cast<int32_t*>(b + guide_offset(n));
+  out->guide_buckets = guide_buckets(n);
   return PFB_OK;
 }
 
@@ -55,15 +68,47 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
 // ---------------------------------------------------------------------------------------------
 // idx = #{i : fl(c_i / total) <= u}.  fl(c/total) is monotone in c, so a binary search on the raw
 // running sums with the division done per probe equals numpy's `cdf /= cdf[-1]; searchsorted(u,'right')`.
-__device__ __forceinline__ int64_t search_right(const double* __restrict__ cdf, int64_t n, double total,
-                                                double u) {
-  int64_t lo = 0, hi = n;
+//
+// A random binary search over an 800 MB CDF costs ~27 dependent probes, the last ~7 of them DRAM
+// sectors.  A guide table removes most of it: G[b] = #{i : v_i < b/M} for M = 2^k buckets of [0, 1)
+// (M ~ n/8, int32, sized to stay L2-resident).  For u in bucket b = floor(u M) (exact: M is a power
+// of two) the answer lies in [G[b], G[b+1]], typically ~8 consecutive CDF entries.
+__device__ int g_ldmode = 0;  // experiment switch (PFB_LDMODE): 0 ld.global.nc, 1 ld.global.cg, 2 ld.global.ca, 3 nc + L1::no_allocate
+__device__ __forceinline__ double ld_rand_f64(const double* p) {
+  double v;
+  switch (g_ldmode) {
+    case 1: asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
+    case 2: asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
+    case 3: asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
+    default: v = __ldg(p);
+  }
+  return v;
+}
+template <bool RIGHT>
+__device__ __forceinline__ int64_t search_range(const double* __restrict__ cdf, int64_t lo, int64_t hi,
+                                                double total, double q) {
+  // RIGHT: first i in [lo, hi) with v_i > q (count of v_i <= q);  LEFT: first i with v_i >= q
   while (lo < hi) {
     const int64_t mid = lo + ((hi - lo) >> 1);
-    const double v = __ddiv_rn(__ldg(cdf + mid), total);
-    if (v <= u) lo = mid + 1; else hi = mid;
+    const double v = __ddiv_rn(ld_rand_f64(cdf + mid), total);
+    const bool go_right = RIGHT ? (v <= q) : (v < q);
+    if (go_right) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// bucket-driven: thread b searches b/M over the whole CDF; consecutive threads probe neighbouring
+// entries, so the probes are cache-line coalesced and the CDF is streamed from HBM about once.
+__global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double* __restrict__ cdf,
+                                                         const double* __restrict__ total_ptr,
+                                                         int32_t* __restrict__ guide, int64_t M) {
+  const double total = *total_ptr;
+  const double inv = 1.0 / (double)M;  // exact, M = 2^k
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= M; b += stride) {
+    const double q = (double)b * inv;
+    guide[b] = (int32_t)search_range<false>(cdf, 0, n, total, q);
+  }
 }
 
 template <typename T, int D, int EST>
@@ -73,7 +118,8 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
                                                             const double* __restrict__ total_ptr,
                                                             const T* __restrict__ x_in, T* __restrict__ x_out,
                                                             int64_t* __restrict__ idx_out, double* est_out,
-                                                            Workspace ws) {
+                                                            Workspace ws, const int32_t* __restrict__ guide,
+                                                            int64_t M) {
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
   const double total = *total_ptr;
@@ -85,12 +131,23 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += stride) {
     const double uj = systematic ? __ddiv_rn(__dadd_rn((double)j, u0), dn) : __ldg(u + j);
-    int64_t idx = search_right(cdf, n, total, uj);
-    if (idx > n - 1) idx = n - 1;
+    int64_t idx;
+    if (uj >= 1.0) {
+      idx = n - 1;
+    } else {
+      const int64_t b = (int64_t)(uj * (double)M);  // exact: M is a power of two
+      idx = search_range<true>(cdf, (int64_t)__ldg(guide + b), (int64_t)__ldg(guide + b + 1), total, uj);
+      if (idx > n - 1) idx = n - 1;
+    }
     if (idx_out) idx_out[j] = idx;
     if (x_in != nullptr) {
       double r[D];
-      load_rec<T, D>(x_in, idx, r);
+      if (sizeof(T) == 8 && g_ldmode != 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[c] = ld_rand_f64(reinterpret_cast<const double*>(x_in) + idx * D + c);
+      } else {
+        load_rec<T, D>(x_in, idx, r);
+      }
       store_rec<T, D>(x_out, j, r);
       if constexpr (EST == PFB_EST_SUM) {
 #pragma unroll
@@ -224,17 +281,17 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(int64_t n, const T* _
 template <typename T, int D>
 static int launch_resample(int64_t n, int64_t n_out, const double* cdf, const double* u, int systematic,
                            const double* stats, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
-                           double* est_out, Workspace W, cudaStream_t st) {
+                           double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M) {
   const int grid = stream_grid(n_out);
   switch (est_kind) {
     case PFB_EST_NONE:
-      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W);
+      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
       break;
     case PFB_EST_SUM:
-      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W);
+      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
       break;
     case PFB_EST_TRIG:
-      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W);
+      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
       break;
     default:
       set_error("bad est_kind %d", est_kind);
@@ -266,12 +323,19 @@ extern "C" const char* pfb_last_error(void) { return g_err; }
 
 extern "C" int64_t pfb_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  int64_t b = ws_header() + scan_tiles(n) * kTileStateBytes;
+  int64_t b = guide_offset(n) + (guide_buckets(n) + 2) * (int64_t)sizeof(int32_t);
   return (b + 255) & ~(int64_t)255;
 }
 
 extern "C" int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream) {
   if (!ws || ws_bytes < pfb_workspace_bytes(0)) { set_error("workspace too small"); return PFB_ERR_WORKSPACE; }
+  if (const char* e = getenv("PFB_LDMODE")) {
+    int v = atoi(e);
+    PFB_CUDA_OK(cudaMemcpyToSymbol(g_ldmode, &v, sizeof(int)));
+  }
+  if (const char* e = getenv("PFB_L2GRAN")) {
+    PFB_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
+  }
   PFB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)kWsCounters, (cudaStream_t)stream));
   return PFB_OK;
 }
@@ -285,13 +349,17 @@ extern "C" int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_o
   if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
   if (x_in && x_in == x_out) { set_error("resampling cannot run in place"); return PFB_ERR_INVALID; }
   if (est_kind != PFB_EST_NONE && (!est_out || !x_in)) { set_error("estimate requested without output / particles"); return PFB_ERR_INVALID; }
+  if (n >= ((int64_t)1 << 31)) { set_error("more than 2^31-1 particles per device are not supported"); return PFB_ERR_UNSUPPORTED; }
   Workspace W;
-  int rc = carve_workspace(ws, ws_bytes, 0, &W);
+  int rc = carve_workspace(ws, ws_bytes, n, &W);
   if (rc) return rc;
   // the raw total c_{n-1} is read on the device from the CDF itself
   cudaStream_t st = (cudaStream_t)stream;
   const double* stats_total = cdf + (n - 1);
-  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st))));
+  const int64_t M = W.guide_buckets;
+  guide_kernel<<<stream_grid(M + 1), kThreads, 0, st>>>(n, cdf, stats_total, W.guide, M);
+  PFB_LAUNCH_OK("guide_kernel");
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M))));
   if (rc) return rc;
   PFB_LAUNCH_OK("resample_kernel");
   return PFB_OK;

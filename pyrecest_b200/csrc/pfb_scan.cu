@@ -49,13 +49,16 @@ __host__ __device__ inline TileState make_tile_state(unsigned char* base, int64_
 struct PMap {
   long long e, o;  // increment when the incoming integer sum is even / odd
 };
+// Increments saturate at 2^60: anything >= 2^53 only ever means "this crosses into the next binade".
+constexpr long long kSat = 0x1000000000000000LL;
+__device__ __forceinline__ long long sat(long long v) { return v < kSat ? v : kSat; }
 __device__ __forceinline__ PMap pmap_then(PMap f, PMap g) {  // apply f first, then g
   PMap h;
-  h.e = f.e + ((f.e & 1LL) ? g.o : g.e);
-  h.o = f.o + (((f.o + 1LL) & 1LL) ? g.o : g.e);
+  h.e = sat(f.e + ((f.e & 1LL) ? g.o : g.e));
+  h.o = sat(f.o + (((f.o + 1LL) & 1LL) ? g.o : g.e));
   return h;
 }
-__device__ __forceinline__ long long pmap_apply(PMap f, long long S) { return S + ((S & 1LL) ? f.o : f.e); }
+__device__ __forceinline__ long long pmap_apply(PMap f, long long S) { return sat(S + ((S & 1LL) ? f.o : f.e)); }
 
 // map of one addend p >= 0 in the binade whose ulp is 2^ue  (ue = e - 52)
 __device__ __forceinline__ PMap pmap_of(double p, int ue) {
@@ -68,7 +71,7 @@ __device__ __forceinline__ PMap pmap_of(double p, int ue) {
   if (M == 0) { r.e = 0; r.o = 0; return r; }
   const int sh = ue - q;
   if (sh <= 0) {
-    long long k = (sh > -11) ? (M << (-sh)) : 0x4000000000000000LL;  // saturate: certainly a crossing
+    long long k = (sh > -7) ? (M << (-sh)) : kSat;  // M < 2^53: up to 2^59; beyond that certainly a crossing
     r.e = k; r.o = k;
   } else if (sh >= 63) {
     r.e = 0; r.o = 0;
@@ -228,6 +231,19 @@ __device__ __forceinline__ PMap block_excl_scan_pmap(PMap v, long long* smem /* 
   return pmap_then(wp, exc);
 }
 
+__device__ __forceinline__ int block_min_int(int v, int* smem /* 33 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  int x = (lane < (kThreads / 32)) ? smem[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
 // look-back on channel A (warp 0 only): exclusive fp64 prefix of tile sums
 __device__ __forceinline__ double lookback_A(const TileState& ts, int64_t tile) {
   const int lane = threadIdx.x & 31;
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
                                                         unsigned int* err) {
   __shared__ double s_dbl[40];
   __shared__ long long s_ll[72];
-  __shared__ double s_p[EXACT ? kScanTile : 2];
+  __shared__ int s_int[40];
   __shared__ int64_t s_tile;
   __shared__ double s_a0, s_cin;
   __shared__ int s_safe, s_e;
@@ -428,29 +444,92 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
         c[k] = (double)S * u;
       }
     } else {
-      // hard tile: exact incoming value, then real sequential fp64 adds
-#pragma unroll
-      for (int k = 0; k < kItems; ++k) s_p[threadIdx.x * kItems + k] = p[k];
+      // hard tile: wait for the exact incoming value, then walk the binades inside the tile.  Within
+      // one binade the tile is an integer scan (as in a safe tile); the first element whose sum
+      // reaches 2^53 is the crossing: it gets one real fp64 add, and the walk restarts behind it.
       if (threadIdx.x < 32) {
         double cin = 0.0;
         if (tile > 0) cin = lookback_B(ts, tile, err);
         if (threadIdx.x == 0) s_cin = cin;
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        double run = s_cin;
-        const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
-        for (int i = 0; i < cnt; ++i) { run = __dadd_rn(run, s_p[i]); s_p[i] = run; }
-        for (int i = cnt; i < kScanTile; ++i) s_p[i] = run;
-        st_relaxed_f64(ts.inclB + tile, run);
+      const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
+      const int tb = threadIdx.x * kItems;
+      double cur = s_cin;
+      int pos = 0;
+      while (true) {
+        if (cur == 0.0) {  // leading zeros: 0 + p = p exactly
+          int mine = 0x7fffffff;
+#pragma unroll
+          for (int k = kItems - 1; k >= 0; --k)
+            if (tb + k >= pos && tb + k < cnt && p[k] != 0.0) mine = tb + k;
+          const int first = block_min_int(mine, s_int);
+#pragma unroll
+          for (int k = 0; k < kItems; ++k)
+            if (tb + k >= pos && tb + k < first) c[k] = 0.0;
+          if (first >= cnt) break;
+          if (first >= tb && first < tb + kItems) {
+#pragma unroll
+            for (int k = 0; k < kItems; ++k)
+              if (tb + k == first) { c[k] = p[k]; s_cin = p[k]; }
+          }
+          __syncthreads();
+          cur = s_cin;
+          pos = first + 1;
+          __syncthreads();
+          continue;
+        }
+        int e = (int)((__double_as_longlong(cur) >> 52) & 0x7ff) - 1023;
+        if (e < -1022) e = -1022;
+        const int ue = e - 52;
+        const double u = ulp_value(ue);
+        bool ok;
+        const long long S0 = int_of(cur, e, &ok);
+        PMap f; f.e = 0; f.o = 0;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+          if (tb + k >= pos && tb + k < cnt) f = pmap_then(f, pmap_of(p[k], ue));
+        PMap tot;
+        const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+        long long S = pmap_apply(g, S0);
+        int mine = 0x7fffffff;
+        long long S_before = 0;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+          if (tb + k >= pos && tb + k < cnt) {
+            const long long Sp = S;
+            S = pmap_apply(pmap_of(p[k], ue), S);
+            if (S >= 0x0020000000000000LL) {
+              if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
+            } else {
+              c[k] = (double)S * u;
+            }
+          }
+        }
+        const int first = block_min_int(mine, s_int);
+        if (first >= cnt) break;  // no crossing left in this tile
+        if (first == mine) {
+#pragma unroll
+          for (int k = 0; k < kItems; ++k)
+            if (tb + k == first) {
+              const double cx = __dadd_rn((double)S_before * u, p[k]);
+              c[k] = cx;
+              s_cin = cx;
+            }
+        }
+        __syncthreads();
+        cur = s_cin;
+        pos = first + 1;
+        __syncthreads();
+      }
+      // publish the exact value at the end of the tile
+      if ((cnt - 1) / kItems == (int)threadIdx.x) {
+        const double cend = c[(cnt - 1) % kItems];
+        st_relaxed_f64(ts.inclB + tile, cend);
         st_release_u64(ts.flagB + tile, 2ULL);
       }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < kItems; ++k) c[k] = s_p[threadIdx.x * kItems + k];
     }
     }
-
     if (base + kItems <= n) {
       double2* q = reinterpret_cast<double2*>(cdf + base);
 #pragma unroll
@@ -507,17 +586,24 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
   PFB_CUDA_OK(cudaMemsetAsync(W.tiles, 0, (size_t)ntiles * 16, st));   // flagA + flagB
   PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
-  int64_t g = ntiles < (int64_t)sm_count() * 6 ? ntiles : (int64_t)sm_count() * 6;
-  const int grid = (int)g;
   const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
   const bool from_log = (logw != nullptr);
+  auto launch = [&](auto kern) -> int {
+    int per_sm = 0;
+    PFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    // persistent CTAs (tiles are handed out by ticket): exactly what is co-resident
+    int64_t g = (int64_t)sm_count() * per_sm;
+    if (g > ntiles) g = ntiles;
+    kern<<<(int)g, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    return PFB_OK;
+  };
   if (mode == PFB_SCAN_SEQEXACT) {
-    if (from_log) scan_kernel<true, true><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
-    else scan_kernel<true, false><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    rc = from_log ? launch(scan_kernel<true, true>) : launch(scan_kernel<true, false>);
   } else {
-    if (from_log) scan_kernel<false, true><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
-    else scan_kernel<false, false><<<grid, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    rc = from_log ? launch(scan_kernel<false, true>) : launch(scan_kernel<false, false>);
   }
+  if (rc) return rc;
   PFB_LAUNCH_OK("scan_kernel");
   return PFB_OK;
 }

@@ -183,7 +183,9 @@ def wn_image_table(mu, P, m=3, cut=None):
     lin_min = np.sum(np.minimum(2.0 * dg * lo, 2.0 * dg * hi), axis=-1)
     gap_min = lin_min + (h[:, None] - h[None, :])   # min over the box of maha_k - maha_j
     keep = ~np.any(gap_min > cut, axis=1)
-    return np.concatenate([g[keep], h[keep, None], offs[keep]], axis=1), int(keep.sum())
+    table = np.concatenate([g[keep], h[keep, None], offs[keep]], axis=1)
+    table = table[np.argsort(h[keep], kind="stable")]  # nearest images first: the kernel's running minimum settles early
+    return np.ascontiguousarray(table), int(keep.sum())
 
 
 def predict_noise_spec(noise, dim):
