@@ -66,48 +66,73 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
 // ---------------------------------------------------------------------------------------------
 // resampling
 // ---------------------------------------------------------------------------------------------
-// idx = #{i : fl(c_i / total) <= u}.  fl(c/total) is monotone in c, so a binary search on the raw
-// running sums with the division done per probe equals numpy's `cdf /= cdf[-1]; searchsorted(u,'right')`.
+// idx_j = #{i : fl(c_i / total) <= u_j}: numpy's `cdf /= cdf[-1]; cdf.searchsorted(u, 'right')`, with the
+// division applied per comparison instead of materialising the normalised CDF.
 //
-// A random binary search over an 800 MB CDF costs ~27 dependent probes, the last ~7 of them DRAM
-// sectors.  A guide table removes most of it: G[b] = #{i : v_i < b/M} for M = 2^k buckets of [0, 1)
-// (M ~ n/8, int32, sized to stay L2-resident).  For u in bucket b = floor(u M) (exact: M is a power
-// of two) the answer lies in [G[b], G[b+1]], typically ~8 consecutive CDF entries.
-__device__ int g_ldmode = 0;  // experiment switch (PFB_LDMODE): 0 ld.global.nc, 1 ld.global.cg, 2 ld.global.ca, 3 nc + L1::no_allocate
-__device__ __forceinline__ double ld_rand_f64(const double* p) {
-  double v;
-  switch (g_ldmode) {
-    case 1: asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
-    case 2: asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
-    case 3: asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); break;
-    default: v = __ldg(p);
-  }
-  return v;
+// A plain binary search over an 800 MB CDF is ~27 dependent probes per particle.  Instead:
+//   * guide table G[b] = #{i : v_i < b/M}, v_i = fl(c_i/total), for M = 2^k buckets of [0, 1) (M ~ n/8).
+//     For u in bucket b = floor(u M) (exact: M is a power of two) the answer lies in [G[b], G[b+1]].
+//   * the ~8 candidate CDF entries of a bucket are fetched with independent loads (one or two cache lines,
+//     one memory round trip) and counted; only windows longer than kWin fall back to a binary search.
+//   * v_i <= u is decided without a division for all but ties: with t = fl(u total),
+//       c_i <= t (1 - 2^-52)  =>  c_i/total <= u            =>  v_i <= u
+//       c_i >= t (1 + 2^-51)  =>  c_i/total >= u (1+2^-52)   =>  v_i >  u
+//     and the exact fl(c_i/total) <= u only in between.
+//   * each thread carries kBatch particles through the phases so the dependent chain
+//     u -> guide -> CDF window -> particle record is paid once per batch.
+constexpr int kWin = 8;
+constexpr int kBatch = 2;
+
+__device__ __forceinline__ bool cdf_le(double c, double total, double u, double tl, double th) {
+  if (c <= tl) return true;
+  if (c >= th) return false;
+  return __ddiv_rn(c, total) <= u;
 }
+
 template <bool RIGHT>
 __device__ __forceinline__ int64_t search_range(const double* __restrict__ cdf, int64_t lo, int64_t hi,
                                                 double total, double q) {
   // RIGHT: first i in [lo, hi) with v_i > q (count of v_i <= q);  LEFT: first i with v_i >= q
   while (lo < hi) {
     const int64_t mid = lo + ((hi - lo) >> 1);
-    const double v = __ddiv_rn(ld_rand_f64(cdf + mid), total);
+    const double v = __ddiv_rn(__ldg(cdf + mid), total);
     const bool go_right = RIGHT ? (v <= q) : (v < q);
     if (go_right) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
-// bucket-driven: thread b searches b/M over the whole CDF; consecutive threads probe neighbouring
-// entries, so the probes are cache-line coalesced and the CDF is streamed from HBM about once.
+// Element-driven guide build: b_i = floor(v_i M) is non-decreasing, and G[b] = first i with b_i >= b, so
+// element i owns the buckets (b_{i-1}, b_i].  The CDF is streamed once; long runs (a heavy particle
+// spans many buckets) are filled by the whole warp.
 __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double* __restrict__ cdf,
                                                          const double* __restrict__ total_ptr,
                                                          int32_t* __restrict__ guide, int64_t M) {
   const double total = *total_ptr;
-  const double inv = 1.0 / (double)M;  // exact, M = 2^k
+  const double dM = (double)M;
+  const int lane = threadIdx.x & 31;
+  const int64_t nround = (n + 31) & ~(int64_t)31;  // whole warps stay converged for the shuffles
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= M; b += stride) {
-    const double q = (double)b * inv;
-    guide[b] = (int32_t)search_range<false>(cdf, 0, n, total, q);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    int64_t bi = M;  // past-the-end elements own nothing
+    if (i < n) bi = (int64_t)(__ddiv_rn(__ldg(cdf + i), total) * dM);
+    int64_t bprev = __shfl_up_sync(0xffffffffu, bi, 1);
+    if (lane == 0) bprev = (i == 0) ? -1 : (i <= n ? (int64_t)(__ddiv_rn(__ldg(cdf + i - 1), total) * dM) : M);
+    if (i >= n) bprev = bi;  // nothing to write
+    int64_t len = bi - bprev;
+    // short runs: the owner writes them; long runs: warp-cooperative
+    if (len > 0 && len <= 4) {
+      for (int64_t b = bprev + 1; b <= bi; ++b) guide[b] = (int32_t)i;
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, len > 4);
+    while (longmask) {
+      const int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int64_t b0 = __shfl_sync(0xffffffffu, bprev, src) + 1;
+      const int64_t b1 = __shfl_sync(0xffffffffu, bi, src);
+      const int32_t val = (int32_t)__shfl_sync(0xffffffffu, i, src);
+      for (int64_t b = b0 + lane; b <= b1; b += 32) guide[b] = val;
+    }
   }
 }
 
@@ -125,42 +150,89 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
   const double total = *total_ptr;
   const double u0 = systematic ? u[0] : 0.0;
   const double dn = (double)n_out;
+  const double dM = (double)M;
   double acc[NE];
 #pragma unroll
   for (int k = 0; k < NE; ++k) acc[k] = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += stride) {
-    const double uj = systematic ? __ddiv_rn(__dadd_rn((double)j, u0), dn) : __ldg(u + j);
-    int64_t idx;
-    if (uj >= 1.0) {
-      idx = n - 1;
-    } else {
-      const int64_t b = (int64_t)(uj * (double)M);  // exact: M is a power of two
-      idx = search_range<true>(cdf, (int64_t)__ldg(guide + b), (int64_t)__ldg(guide + b + 1), total, uj);
-      if (idx > n - 1) idx = n - 1;
+  for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n_out; j0 += stride * kBatch) {
+    double uj[kBatch];
+    int32_t lo[kBatch], hi[kBatch];
+    bool live[kBatch];
+    // phase 1: uniforms, then the guide entries
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int64_t j = j0 + q * stride;
+      live[q] = j < n_out;
+      uj[q] = !live[q] ? 0.0 : (systematic ? __ddiv_rn(__dadd_rn((double)j, u0), dn) : __ldg(u + j));
     }
-    if (idx_out) idx_out[j] = idx;
-    if (x_in != nullptr) {
-      double r[D];
-      if (sizeof(T) == 8 && g_ldmode != 0) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) r[c] = ld_rand_f64(reinterpret_cast<const double*>(x_in) + idx * D + c);
+    for (int q = 0; q < kBatch; ++q) {
+      if (uj[q] >= 1.0) {  // only a rounded-up systematic point can get here
+        lo[q] = hi[q] = (int32_t)(n - 1);
       } else {
-        load_rec<T, D>(x_in, idx, r);
+        const int64_t b = (int64_t)(uj[q] * dM);  // exact
+        lo[q] = __ldg(guide + b);
+        hi[q] = __ldg(guide + b + 1);
       }
-      store_rec<T, D>(x_out, j, r);
-      if constexpr (EST == PFB_EST_SUM) {
+    }
+    // phase 2: the candidate windows, all loads independent
+    double win[kBatch][kWin];
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] += r[c];
-      } else if constexpr (EST == PFB_EST_TRIG) {
+    for (int q = 0; q < kBatch; ++q) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-          double sn, cs;
-          sincos(r[c], &sn, &cs);
-          acc[2 * c] += cs;
-          acc[2 * c + 1] += sn;
+      for (int k = 0; k < kWin; ++k) {
+        const int32_t i = lo[q] + k;
+        win[q][k] = (i < hi[q]) ? __ldg(cdf + i) : INFINITY;
+      }
+    }
+    // phase 3: count, with the binary search only for long windows
+    int64_t idx[kBatch];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const double t = uj[q] * total;
+      const double tl = t * (1.0 - 2.220446049250313e-16);
+      const double th = t * (1.0 + 4.440892098500626e-16);
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kWin; ++k) {
+        // windows are sorted: once an entry is > u the rest are too; counting all is branch-free
+        if (win[q][k] != INFINITY && cdf_le(win[q][k], total, uj[q], tl, th)) cnt = k + 1;
+      }
+      int64_t r = (int64_t)lo[q] + cnt;
+      if (cnt == kWin && hi[q] - lo[q] > kWin) r = search_range<true>(cdf, (int64_t)lo[q] + kWin, (int64_t)hi[q], total, uj[q]);
+      if (r > n - 1) r = n - 1;
+      idx[q] = r;
+    }
+    // phase 4: gather, store, estimate
+    if (x_in != nullptr) {
+      double r[kBatch][D];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (live[q]) load_rec<T, D>(x_in, idx[q], r[q]);
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        if (!live[q]) continue;
+        const int64_t j = j0 + q * stride;
+        store_rec<T, D>(x_out, j, r[q]);
+        if (idx_out) idx_out[j] = idx[q];
+        if constexpr (EST == PFB_EST_SUM) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) acc[c] += r[q][c];
+        } else if constexpr (EST == PFB_EST_TRIG) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            double sn, cs;
+            sincos(r[q][c], &sn, &cs);
+            acc[2 * c] += cs;
+            acc[2 * c + 1] += sn;
+          }
         }
       }
+    } else if (idx_out) {
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q)
+        if (live[q]) idx_out[j0 + q * stride] = idx[q];
     }
   }
   if constexpr (EST != PFB_EST_NONE) {
@@ -329,13 +401,6 @@ extern "C" int64_t pfb_workspace_bytes(int64_t n) {
 
 extern "C" int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream) {
   if (!ws || ws_bytes < pfb_workspace_bytes(0)) { set_error("workspace too small"); return PFB_ERR_WORKSPACE; }
-  if (const char* e = getenv("PFB_LDMODE")) {
-    int v = atoi(e);
-    PFB_CUDA_OK(cudaMemcpyToSymbol(g_ldmode, &v, sizeof(int)));
-  }
-  if (const char* e = getenv("PFB_L2GRAN")) {
-    PFB_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
-  }
   PFB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)kWsCounters, (cudaStream_t)stream));
   return PFB_OK;
 }
@@ -357,7 +422,7 @@ extern "C" int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_o
   cudaStream_t st = (cudaStream_t)stream;
   const double* stats_total = cdf + (n - 1);
   const int64_t M = W.guide_buckets;
-  guide_kernel<<<stream_grid(M + 1), kThreads, 0, st>>>(n, cdf, stats_total, W.guide, M);
+  guide_kernel<<<stream_grid(n, 4), kThreads, 0, st>>>(n, cdf, stats_total, W.guide, M);
   PFB_LAUNCH_OK("guide_kernel");
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M))));
   if (rc) return rc;
