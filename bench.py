@@ -266,7 +266,7 @@ def run_gpu(args):
         eng.scan(cdf, logw=logw, exact=exact)
         if ev:
             ev[2].record()
-        eng.resample(cdf, ub, x, alt, n, D, est_kind=est_kind, est_out=est)
+        eng.resample(cdf, ub, x, alt, n, D, systematic=args.resampling == "systematic", est_kind=est_kind, est_out=est)
         if ev:
             ev[3].record()
         x, alt = alt, x
@@ -341,7 +341,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "resampling": "multinomial",
+            "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "resampling": args.resampling,
                        "scan": "sequential-exact" if exact else "fast", "likelihood_images": int(lp.n_images) if name == "t3" else None,
                        "l2_policy": f"inputs larger than L2: ring of {nbuf} pre-generated noise/uniform buffers "
                                     f"({n * 8 * (E + 1) / 1e6:.0f} MB each) + {n * 8 * D / 1e6:.0f} MB state",
@@ -402,6 +402,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

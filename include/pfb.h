@@ -103,6 +103,9 @@ enum {
 };
 
 typedef enum { PFB_SCAN_FAST = 0, PFB_SCAN_SEQEXACT = 1 } pfb_scan_mode;
+/* OR into `mode`: the workspace still holds the per-tile (max, sum exp) that pfb_loglik /
+ * pfb_predict_loglik left for exactly this logw array, so pfb_scan_cdf can skip its own pass over it */
+#define PFB_SCAN_TILE_STATS_VALID 0x100
 typedef enum { PFB_EST_NONE = 0, PFB_EST_SUM = 1, PFB_EST_TRIG = 2 } pfb_est_kind;
 typedef enum { PFB_MOM_MEAN = 0, PFB_MOM_TRIG = 1, PFB_MOM_SCATTER = 2, PFB_MOM_CENTRAL = 3 } pfb_moment_kind;
 

@@ -35,6 +35,7 @@ class Engine:
         self.launches = 0  # kernels of libpfb launched through this engine
         self._ws = None
         self._ws_n = -1
+        self._tile_stats_key = None  # (logw ptr, n) whose per-tile stats are in the workspace
         self.stats = torch.zeros(L.STAT_COUNT, dtype=torch.float64, device=self.device)
         self._ensure_ws(0)
 
@@ -45,6 +46,7 @@ class Engine:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             assert self._ws.data_ptr() % 256 == 0
             self._ws_n = n
+            self._tile_stats_key = None
             L.check(self.lib.pfb_workspace_init(_ptr(self._ws), nbytes, _stream(self.device)))
         return _ptr(self._ws), self._ws.numel()
 
@@ -61,16 +63,18 @@ class Engine:
 
     def loglik(self, lik, x, logw, w_prev=None, stats=None):
         n = x.shape[0]
-        ws, wsb = self._ensure_ws(0)
+        ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
+        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr())
         L.check(self.lib.pfb_loglik(C.byref(lik), _DT[x.dtype], n, _ptr(x), _ptr(w_prev), _ptr(logw), _ptr(st), ws,
                                     wsb, _stream(self.device)))
         self.launches += 1
 
     def predict_loglik(self, params, lik, x_in, x_out, noise, logw, stats=None):
         n = x_in.shape[0]
-        ws, wsb = self._ensure_ws(0)
+        ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
+        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr())
         L.check(self.lib.pfb_predict_loglik(C.byref(params), C.byref(lik), _DT[x_in.dtype], n, _ptr(x_in),
                                             _ptr(x_out), _ptr(noise), _ptr(logw), _ptr(st), ws, wsb,
                                             _stream(self.device)))
@@ -87,9 +91,15 @@ class Engine:
         n = cdf.shape[0]
         ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
-        L.check(self.lib.pfb_scan_cdf(L.SCAN_SEQEXACT if exact else L.SCAN_FAST, n, _ptr(w), _ptr(logw), _ptr(cdf),
-                                      _ptr(st), ws, wsb, _stream(self.device)))
-        self.launches += 1
+        mode = L.SCAN_SEQEXACT if exact else L.SCAN_FAST
+        have = logw is not None and self._tile_stats_key == (logw.data_ptr(), n, st.data_ptr())
+        if have:
+            mode |= L.SCAN_TILE_STATS_VALID
+        else:  # pfb_scan_cdf recomputes the per-tile stats for this input
+            self._tile_stats_key = None if logw is None else (logw.data_ptr(), n, st.data_ptr())
+        L.check(self.lib.pfb_scan_cdf(mode, n, _ptr(w), _ptr(logw), _ptr(cdf), _ptr(st), ws, wsb,
+                                      _stream(self.device)))
+        self.launches += 2 if have else 3  # [tile_stats] + tile_prefix + scan
 
     def resample(self, cdf, u, x_in, x_out, n_out, dim, systematic=False, idx_out=None, est_kind=L.EST_NONE,
                  est_out=None):

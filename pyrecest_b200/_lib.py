@@ -22,6 +22,7 @@ LIK_GAUSS, LIK_WN_MULTI, LIK_WN_1D, LIK_VM, LIK_VMF = range(5)
 # stats words
 STAT_MAX, STAT_SUMEXP, STAT_SUMSQ, STAT_FLAGS, STAT_TOTAL, STAT_COUNT = 0, 1, 2, 3, 4, 8
 SCAN_FAST, SCAN_SEQEXACT = 0, 1
+SCAN_TILE_STATS_VALID = 0x100
 EST_NONE, EST_SUM, EST_TRIG = 0, 1, 2
 MOM_MEAN, MOM_TRIG, MOM_SCATTER, MOM_CENTRAL = 0, 1, 2, 3
 

@@ -63,7 +63,13 @@ struct Workspace {
   int64_t tile_bytes;
   int32_t* guide;
   int64_t guide_buckets;
+  double* tmax;   // per scan tile: max log-weight  } written by the weighting kernels,
+  double* tsum;   // per scan tile: sum exp(l - max) } read by pfb_scan_cdf
 };
+// tile-state columns (ntiles entries each): 0 flag, 1 aggE, 2 aggO, 3 incl, 4 tmax, 5 tsum, 6 aprefix (+ spare)
+inline double* tile_col(unsigned char* base, int64_t ntiles, int col) {
+  return reinterpret_cast<double*>(base) + (int64_t)col * ntiles;
+}
 int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out);
 
 // ---- numpy.mod(x, 2*pi) ----------------------------------------------------------------------
@@ -209,6 +215,15 @@ inline int stream_grid(int64_t n, int per_thread = 1) {
   if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
+}
+
+// grid for the tile-structured kernels: persistent CTAs striding over the scan tiles
+inline int tile_grid(int64_t n) {
+  int64_t tiles = scan_tiles(n);
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  if (tiles < 1) tiles = 1;
+  return (int)(tiles < cap ? tiles : cap);
 }
 
 // ---- acquire / release helpers for the look-back scans ------------------------------------------

@@ -344,6 +344,45 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
   return smem_img;
 }
 
+// Both weighting kernels walk the particle array in the scan's tiles (kScanTile consecutive particles
+// per CTA step, thread t takes particles t, t+256, ... of the tile: coalesced) and leave, per tile,
+// (max log-weight, sum exp(logw - max)) in the workspace: pfb_scan_cdf turns those into the approximate
+// prefix its sequential-exact scan needs, without another pass over the log-weights.
+constexpr int kTileItems = kScanTile / kThreads;
+
+template <typename EVAL>
+__device__ __forceinline__ void weight_tiles(int64_t n, double* __restrict__ logw, double* stats, Workspace ws,
+                                             double* red, EVAL eval) {
+  const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  double gmax = -INFINITY, gnan = 0.0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * kScanTile + threadIdx.x;
+    double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
+#pragma unroll 1
+    for (int k = 0; k < kTileItems; ++k) {
+      const int64_t i = base + (int64_t)k * kThreads;
+      if (i < n) {
+        const double v = eval(i);
+        logw[i] = v;
+        if (v != v) {
+          gnan = 1.0;
+        } else if (v > m) {
+          sacc = sacc * exp(m - v) + 1.0;  // m = -inf: 0 * 0 + 1
+          m = v;
+        } else if (v > -INFINITY) {
+          sacc += exp(v - m);
+        }
+      }
+    }
+    const double bm = block_max(m, red);
+    double sv[1] = {(m > -INFINITY) ? sacc * exp(m - bm) : 0.0};
+    block_sum<1>(sv, red);
+    if (threadIdx.x == 0) { ws.tmax[tile] = bm; ws.tsum[tile] = sv[0]; }
+    gmax = fmax(gmax, bm);
+  }
+  finish_max(gmax, gnan, stats, ws, red);
+}
+
 template <typename T, int D, int KIND>
 __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int64_t n,
                                                           const T* __restrict__ x,
@@ -353,18 +392,13 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int6
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  double tmax = -INFINITY, tnan = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  weight_tiles(n, logw, stats, ws, red, [&](int64_t i) {
     double r[D];
     load_rec<T, D>(x, i, r);
     double l = loglik_one<D, KIND>(L, r, images);
     if (w_prev != nullptr) l += log(w_prev[i]);
-    logw[i] = l;
-    if (l != l) tnan = 1.0;
-    tmax = fmax(tmax, l);
-  }
-  finish_max(tmax, tnan, stats, ws, red);
+    return l;
+  });
 }
 
 template <typename T, int D, int MODE, int KIND>
@@ -377,9 +411,7 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  double tmax = -INFINITY, tnan = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  weight_tiles(n, logw, stats, ws, red, [&](int64_t i) {
     double out[D];
     predict_one<T, D, MODE>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
@@ -388,12 +420,8 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
 #pragma unroll
       for (int c = 0; c < D; ++c) out[c] = (double)(float)out[c];
     }
-    double l = loglik_one<D, KIND>(L, out, images);
-    logw[i] = l;
-    if (l != l) tnan = 1.0;
-    tmax = fmax(tmax, l);
-  }
-  finish_max(tmax, tnan, stats, ws, red);
+    return loglik_one<D, KIND>(L, out, images);
+  });
 }
 
 template <typename T>
@@ -482,10 +510,10 @@ extern "C" int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n,
   if (n <= 0) return PFB_OK;
   if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, 0, &W);
+  rc = carve_workspace(ws, ws_bytes, n, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stream_grid(n);
+  const int grid = tile_grid(n);
   const size_t sm = lik_smem(lik);
   PFB_DISPATCH_DTYPE(dtype, {
     if (lik->kind == PFB_LIK_WN_1D) {
@@ -507,7 +535,7 @@ template <typename T, int D, int MODE, int KIND>
 static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* lik, int64_t n, const void* x_in,
                             void* x_out, const void* noise, double* logw, double* stats, Workspace W,
                             cudaStream_t st) {
-  predict_loglik_kernel<T, D, MODE, KIND><<<stream_grid(n), kThreads, lik_smem(lik), st>>>(
+  predict_loglik_kernel<T, D, MODE, KIND><<<tile_grid(n), kThreads, lik_smem(lik), st>>>(
       *p, *lik, n, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
   return PFB_OK;
 }
@@ -546,7 +574,7 @@ extern "C" int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_par
   if (n <= 0) return PFB_OK;
   if (!x_in || !x_out || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, 0, &W);
+  rc = carve_workspace(ws, ws_bytes, n, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PFB_DISPATCH_DTYPE(dtype, {

@@ -60,6 +60,8 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   out->tile_bytes = ws_bytes - ws_header();
   out->guide = reinterpret_cast<int32_t*>(b + guide_offset(n));
   out->guide_buckets = guide_buckets(n);
+  out->tmax = tile_col(out->tiles, scan_tiles(n), 4);
+  out->tsum = tile_col(out->tiles, scan_tiles(n), 5);
   return PFB_OK;
 }
 

@@ -2,14 +2,15 @@
 //
 // Sequential-exact scan: reproduces numpy.cumsum(p) (c_i = fl(c_{i-1} + p_i), fp64, ties to
 // even, p_i >= 0) bit for bit in ONE pass with a chained (decoupled look-back) scan:
-//   * channel A is an ordinary fp64 look-back scan of tile sums; it bounds the running sum at
-//     every tile boundary to a relative 4 n 2^-53, which tells most tiles with certainty which
-//     binade [2^e, 2^(e+1)) the sequential running sum is in while it crosses them ("safe" tiles);
+//   * per-tile sums (emitted by the weighting kernel, or by tile_stats_kernel) are prefix-summed
+//     by one CTA first; that approximate prefix bounds the running sum at every tile boundary to a
+//     relative 4 n 2^-53, which tells most tiles with certainty which binade [2^e, 2^(e+1)) the
+//     sequential running sum is in while it crosses them ("safe" tiles);
 //   * inside one binade a sequential fp add is an INTEGER add in units of ulp = 2^(e-52):
 //       S_i = S_{i-1} + k_i + [rem_i > half] + [rem_i == half and (S_{i-1} + k_i) odd]
 //     so each element is a map parity(S_{i-1}) -> increment, stored as (inc_even, inc_odd); maps
 //     compose associatively, (g o f)(pi) = f(pi) + g((pi + f(pi)) & 1), which is the operator of
-//     channel B's look-back; a safe tile publishes its composed map before it knows its prefix;
+//     the look-back; a safe tile publishes its composed map before it knows its prefix;
 //   * tiles that may contain a binade crossing (about one per binade) or start at 0 are "hard":
 //     they wait for the exact incoming value and add sequentially with real fp64 adds.
 // SURVEY.md appendix B has the derivation; tests/test_scan_model.py holds a numpy model of the
@@ -22,25 +23,25 @@ constexpr int kItems = kScanTile / kThreads;  // 8 consecutive elements per thre
 static_assert(kItems * kThreads == kScanTile, "tile shape");
 
 struct TileState {
-  unsigned long long* flagA;  // 0 none, 1 aggregate, 2 inclusive
   unsigned long long* flagB;  // low 2 bits: 0 none, 1 aggregate map, 2 inclusive; bits 8..: e + 2048
-  double* aggA;
-  double* inclA;
   long long* aggE;
   long long* aggO;
   double* inclB;
+  double* tmax;      // per-tile max of the log-weights (or the shift the sums were taken with)
+  double* tsum;      // per-tile sum of exp(logw - tmax)  (or of the weights)
+  double* aprefix;   // ntiles + 1 approximate exclusive prefix sums, relative to the global shift
   unsigned int* ticket;
 };
 
-__host__ __device__ inline TileState make_tile_state(unsigned char* base, int64_t ntiles, unsigned int* ticket) {
+inline TileState make_tile_state(unsigned char* base, int64_t ntiles, unsigned int* ticket) {
   TileState s;
-  s.flagA = reinterpret_cast<unsigned long long*>(base);
-  s.flagB = s.flagA + ntiles;
-  s.aggA = reinterpret_cast<double*>(s.flagB + ntiles);
-  s.inclA = s.aggA + ntiles;
-  s.aggE = reinterpret_cast<long long*>(s.inclA + ntiles);
-  s.aggO = s.aggE + ntiles;
-  s.inclB = reinterpret_cast<double*>(s.aggO + ntiles);
+  s.flagB = reinterpret_cast<unsigned long long*>(tile_col(base, ntiles, 0));
+  s.aggE = reinterpret_cast<long long*>(tile_col(base, ntiles, 1));
+  s.aggO = reinterpret_cast<long long*>(tile_col(base, ntiles, 2));
+  s.inclB = tile_col(base, ntiles, 3);
+  s.tmax = tile_col(base, ntiles, 4);
+  s.tsum = tile_col(base, ntiles, 5);
+  s.aprefix = tile_col(base, ntiles, 6);  // ntiles + 1 entries: the last one uses the spare eighth column
   s.ticket = ticket;
   return s;
 }
@@ -244,43 +245,29 @@ __device__ __forceinline__ int block_min_int(int v, int* smem /* 33 */) {
   return x;
 }
 
-// look-back on channel A (warp 0 only): exclusive fp64 prefix of tile sums
-__device__ __forceinline__ double lookback_A(const TileState& ts, int64_t tile) {
-  const int lane = threadIdx.x & 31;
-  double prefix = 0.0;
-  int64_t j0 = tile - 1;
-  while (true) {
-    const int64_t j = j0 - lane;
-    unsigned long long f = 2;  // tiles before 0 behave like an inclusive 0
-    if (j >= 0) {
-      do { f = ld_acquire_u64(ts.flagA + j); } while (f == 0);
-    }
-    double v = 0.0;
-    if (j >= 0) v = (f == 2) ? ld_relaxed_f64(ts.inclA + j) : ld_relaxed_f64(ts.aggA + j);
-    const unsigned incl_mask = __ballot_sync(0xffffffffu, f == 2);
-    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest tile with an inclusive value
-    // sum lanes 0..first (in tile order: far to near does not matter for a plain sum; keep fixed order)
-    double acc = 0.0;
-    for (int l = (first < 32 ? first : 31); l >= 0; --l) acc += __shfl_sync(0xffffffffu, v, l);
-    prefix = acc + prefix;
-    if (first < 32) break;
-    j0 -= 32;
-  }
-  return prefix;
-}
+// Look-back, run by the WHOLE CTA: exact value c at the start of `tile`.  Thread k inspects tile
+// (tile - 1 - k), so one step covers 256 predecessors (all tiles of a wave start together and publish
+// their maps at about the same time; a 32-wide window would need ~14 dependent steps to reach the
+// previous wave's inclusive values).  Each warp composes the parity maps of its 32-tile window with a
+// shuffle tree (far tile first) up to the nearest inclusive value; the per-warp results are chained in
+// shared memory.  Every thread returns the same value.
+struct LookbackSmem {
+  long long we[kThreads / 32], wo[kThreads / 32];
+  double wincl[kThreads / 32];
+  int wfirst[kThreads / 32], wexp[kThreads / 32];
+};
 
-// look-back on channel B (warp 0 only): exact value c at the start of `tile` (c_in) -- walks back
-// over published parity maps to the nearest exact inclusive value.
-__device__ __forceinline__ double lookback_B(const TileState& ts, int64_t tile, unsigned int* err) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ double lookback_block(const TileState& ts, int64_t tile, unsigned int* err,
+                                                 LookbackSmem& sm) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PMap composed; composed.e = 0; composed.o = 0;  // maps of the tiles after the inclusive one, in order
   int e_maps = 0;
   bool have_maps = false;
   double c_incl = 0.0;
   int64_t j0 = tile - 1;
   while (true) {
-    const int64_t j = j0 - lane;
-    unsigned long long f = 2;
+    const int64_t j = j0 - threadIdx.x;
+    unsigned long long f = 2;  // tiles before 0 behave like an inclusive 0
     if (j >= 0) {
       do { f = ld_acquire_u64(ts.flagB + j); } while ((f & 3ULL) == 0);
     }
@@ -292,26 +279,40 @@ __device__ __forceinline__ double lookback_B(const TileState& ts, int64_t tile, 
       else { m.e = ld_relaxed_s64(ts.aggE + j); m.o = ld_relaxed_s64(ts.aggO + j); }
     }
     const unsigned incl_mask = __ballot_sync(0xffffffffu, st == 2);
-    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-    // compose lanes first-1 .. 0 (tile order), then what we already had
-    PMap win; win.e = 0; win.o = 0;
-    const int top = (first < 32 ? first : 32) - 1;
-    for (int l = top; l >= 0; --l) {
+    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest lane holding an inclusive value
+    if (lane >= first) { m.e = 0; m.o = 0; }                     // only lanes first-1 .. 0 carry maps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // lane i <- then(lane i+o, lane i): far tile first
       PMap t;
-      t.e = __shfl_sync(0xffffffffu, m.e, l);
-      t.o = __shfl_sync(0xffffffffu, m.o, l);
-      win = pmap_then(win, t);
+      t.e = __shfl_down_sync(0xffffffffu, m.e, o);
+      t.o = __shfl_down_sync(0xffffffffu, m.o, o);
+      if (lane + o < 32) m = pmap_then(t, m);
     }
-    if (top >= 0) {
-      const unsigned long long f0 = __shfl_sync(0xffffffffu, f, 0);
-      const int e_here = (int)(f0 >> 8) - 2048;
-      if (have_maps && e_here != e_maps) atomicOr(err, 4u);
-      e_maps = e_here;
-      have_maps = true;
+    const double cfirst = __shfl_sync(0xffffffffu, ci, first & 31);
+    __syncthreads();  // previous round's shared values are consumed
+    if (lane == 0) {
+      sm.we[warp] = m.e; sm.wo[warp] = m.o;
+      sm.wfirst[warp] = first;
+      sm.wincl[warp] = cfirst;
+      sm.wexp[warp] = (int)(f >> 8) - 2048;  // binade of the nearest tile's map (meaningful if first > 0)
     }
-    composed = pmap_then(win, composed);
-    if (first < 32) { c_incl = __shfl_sync(0xffffffffu, ci, first); break; }
-    j0 -= 32;
+    __syncthreads();
+    bool done = false;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      if (done) continue;
+      const int fw = sm.wfirst[w];
+      if (fw > 0) {
+        PMap win; win.e = sm.we[w]; win.o = sm.wo[w];
+        if (have_maps && sm.wexp[w] != e_maps) atomicOr(err, 4u);
+        e_maps = sm.wexp[w];
+        have_maps = true;
+        composed = pmap_then(win, composed);
+      }
+      if (fw < 32) { c_incl = sm.wincl[w]; done = true; }
+    }
+    if (done) break;
+    j0 -= kThreads;
   }
   if (!have_maps) return c_incl;
   bool ok;
@@ -319,6 +320,74 @@ __device__ __forceinline__ double lookback_B(const TileState& ts, int64_t tile, 
   if (!ok) atomicOr(err, 8u);
   S = pmap_apply(composed, S);
   return (double)S * ulp_value(e_maps - 52);
+}
+
+// ---- tile sums and their prefix ------------------------------------------------------------------
+template <bool FROM_LOG>
+__global__ void __launch_bounds__(kThreads) tile_stats_kernel(int64_t n, const double* __restrict__ in,
+                                                              const double* __restrict__ stats, TileState ts,
+                                                              int64_t ntiles) {
+  __shared__ double red[32];
+  const double shift = FROM_LOG ? stats[PFB_STAT_MAX] : 0.0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * kScanTile;
+    double v[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      const int64_t i = base + k * kThreads + threadIdx.x;
+      if (i < n) v[0] += FROM_LOG ? exp(__ldg(in + i) - shift) : __ldg(in + i);
+    }
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) { ts.tmax[tile] = shift; ts.tsum[tile] = v[0]; }
+    __syncthreads();
+  }
+}
+
+// one CTA: aprefix[t] = sum_{s<t} tsum[s] exp(tmax[s] - M), t = 0 .. ntiles
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t ntiles,
+                                                           const double* __restrict__ max_ptr) {
+  __shared__ double s_warp[33];
+  __shared__ double s_carry;
+  const double M = max_ptr ? *max_ptr : 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  for (int64_t base = 0; base < ntiles; base += 1024) {
+    const int64_t t = base + threadIdx.x;
+    double v = 0.0;
+    if (t < ntiles) {
+      const double tm = ts.tmax[t];
+      const double sc = max_ptr ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0;
+      v = ts.tsum[t] * sc;
+    }
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      double w = s_warp[lane];
+      double wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double x = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += x;
+      }
+      s_warp[lane] = wi - w;
+      if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    const double carry = s_carry;
+    const double excl = carry + s_warp[warp] + (inc - v);
+    if (t < ntiles) ts.aprefix[t] = excl;
+    if (t == ntiles - 1) ts.aprefix[ntiles] = excl + v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + s_warp[32];
+    __syncthreads();
+  }
 }
 
 template <bool EXACT, bool FROM_LOG>
@@ -330,7 +399,8 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
   __shared__ long long s_ll[72];
   __shared__ int s_int[40];
   __shared__ int64_t s_tile;
-  __shared__ double s_a0, s_cin;
+  __shared__ double s_cin;
+  __shared__ LookbackSmem s_lb;
   __shared__ int s_safe, s_e;
 
   const double shift = FROM_LOG ? stats[PFB_STAT_MAX] : 0.0;
@@ -358,53 +428,32 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
 #pragma unroll
       for (int k = 0; k < kItems; ++k) p[k] = exp(p[k] - shift);  // exp(-inf) = 0
     }
-    double tsum = p[0];
-#pragma unroll
-    for (int k = 1; k < kItems; ++k) tsum += p[k];
-    double total;
-    const double toff = block_excl_scan(tsum, s_dbl, &total);
-
-    // ---- channel A: approximate prefix at the tile boundary
-    if (threadIdx.x < 32) {
-      if (threadIdx.x == 0) {
-        if (tile == 0) {
-          st_relaxed_f64(ts.inclA + tile, total);
-          st_release_u64(ts.flagA + tile, 2ULL);
-        } else {
-          st_relaxed_f64(ts.aggA + tile, total);
-          st_release_u64(ts.flagA + tile, 1ULL);
+    const double a0 = ts.aprefix[tile];
+    if (threadIdx.x == 0) {
+      if (EXACT) {
+        // certain binade?  every running sum inside the tile lies in [lo, hi]
+        const double lo = a0 * (1.0 - margin);
+        const double hi = ts.aprefix[tile + 1] * (1.0 + margin);
+        int safe = 0, e = 0;
+        if (tile > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
+          const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
+          const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
+          if (elo == ehi) { safe = 1; e = elo; }
         }
-      }
-      double a0 = 0.0;
-      if (tile > 0) {
-        a0 = lookback_A(ts, tile);
-        if (threadIdx.x == 0) {
-          st_relaxed_f64(ts.inclA + tile, a0 + total);
-          st_release_u64(ts.flagA + tile, 2ULL);
-        }
-      }
-      if (threadIdx.x == 0) {
-        s_a0 = a0;
-        if (EXACT) {
-          // certain binade?  every running sum inside the tile lies in [lo, hi]
-          const double lo = a0 * (1.0 - margin);
-          const double hi = (a0 + total) * (1.0 + margin);
-          int safe = 0, e = 0;
-          if (tile > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
-            const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
-            const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
-            if (elo == ehi) { safe = 1; e = elo; }
-          }
-          s_safe = safe;
-          s_e = e;
-        }
+        s_safe = safe;
+        s_e = e;
       }
     }
     __syncthreads();
 
     double c[kItems];
     if constexpr (!EXACT) {
-      double run = s_a0 + toff;
+      double tsum = p[0];
+#pragma unroll
+      for (int k = 1; k < kItems; ++k) tsum += p[k];
+      double total;
+      const double toff = block_excl_scan(tsum, s_dbl, &total);
+      double run = a0 + toff;
 #pragma unroll
       for (int k = 0; k < kItems; ++k) { run += p[k]; c[k] = run; }
     } else {
@@ -415,27 +464,23 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
       for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
       PMap tot;
       const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
-      if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) {
-          st_relaxed_s64(ts.aggE + tile, tot.e);
-          st_relaxed_s64(ts.aggO + tile, tot.o);
-          st_release_u64(ts.flagB + tile, 1ULL | ((unsigned long long)(s_e + 2048) << 8));
-        }
-        const double cin = lookback_B(ts, tile, err);
-        if (threadIdx.x == 0) {
-          bool ok;
-          long long S = int_of(cin, s_e, &ok);
-          if (!ok) atomicOr(err, 1u);
-          const long long Send = pmap_apply(tot, S);
-          if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // safe tile crossed a binade: bound violated
-          st_relaxed_f64(ts.inclB + tile, (double)Send * ulp_value(ue));
-          st_release_u64(ts.flagB + tile, 2ULL | ((unsigned long long)(s_e + 2048) << 8));
-          s_cin = cin;
-        }
+      if (threadIdx.x == 0) {
+        st_relaxed_s64(ts.aggE + tile, tot.e);
+        st_relaxed_s64(ts.aggO + tile, tot.o);
+        st_release_u64(ts.flagB + tile, 1ULL | ((unsigned long long)(s_e + 2048) << 8));
       }
-      __syncthreads();
+      const double cin = lookback_block(ts, tile, err, s_lb);
+      if (threadIdx.x == 0) {
+        bool ok0;
+        const long long S0 = int_of(cin, s_e, &ok0);
+        if (!ok0) atomicOr(err, 1u);
+        const long long Send = pmap_apply(tot, S0);
+        if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // safe tile crossed a binade: bound violated
+        st_relaxed_f64(ts.inclB + tile, (double)Send * ulp_value(ue));
+        st_release_u64(ts.flagB + tile, 2ULL | ((unsigned long long)(s_e + 2048) << 8));
+      }
       bool ok;
-      long long S = int_of(s_cin, s_e, &ok);
+      long long S = int_of(cin, s_e, &ok);
       S = pmap_apply(g, S);
       const double u = ulp_value(ue);
 #pragma unroll
@@ -447,15 +492,11 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
       // hard tile: wait for the exact incoming value, then walk the binades inside the tile.  Within
       // one binade the tile is an integer scan (as in a safe tile); the first element whose sum
       // reaches 2^53 is the crossing: it gets one real fp64 add, and the walk restarts behind it.
-      if (threadIdx.x < 32) {
-        double cin = 0.0;
-        if (tile > 0) cin = lookback_B(ts, tile, err);
-        if (threadIdx.x == 0) s_cin = cin;
-      }
-      __syncthreads();
+      double cin0 = 0.0;
+      if (tile > 0) cin0 = lookback_block(ts, tile, err, s_lb);
       const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
       const int tb = threadIdx.x * kItems;
-      double cur = s_cin;
+      double cur = cin0;
       int pos = 0;
       while (true) {
         if (cur == 0.0) {  // leading zeros: 0 + p = p exactly
@@ -573,6 +614,8 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
   if (n <= 0) return PFB_OK;
   if ((w == nullptr) == (logw == nullptr)) { set_error("exactly one of w / logw must be given"); return PFB_ERR_INVALID; }
   if (!cdf || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  const bool have_tile_stats = (mode & PFB_SCAN_TILE_STATS_VALID) != 0;
+  mode &= ~PFB_SCAN_TILE_STATS_VALID;
   if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
   const double* in = w ? w : logw;
   if (((uintptr_t)in & 15) || ((uintptr_t)cdf & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
@@ -584,10 +627,21 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
   unsigned int* ticket = W.counters + 1;
   unsigned int* err = W.counters + 2;
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
-  PFB_CUDA_OK(cudaMemsetAsync(W.tiles, 0, (size_t)ntiles * 16, st));   // flagA + flagB
-  PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
-  const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
   const bool from_log = (logw != nullptr);
+  PFB_CUDA_OK(cudaMemsetAsync(ts.flagB, 0, (size_t)ntiles * 8, st));
+  PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
+  // 1. per-tile sums, unless the weighting kernel already left them in the workspace
+  if (!have_tile_stats || !from_log) {
+    const int g = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
+    if (from_log) tile_stats_kernel<true><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
+    else tile_stats_kernel<false><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
+    PFB_LAUNCH_OK("tile_stats_kernel");
+  }
+  // 2. approximate prefix of the tile sums (one CTA)
+  tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr);
+  PFB_LAUNCH_OK("tile_prefix_kernel");
+  // 3. the scan proper
+  const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
   auto launch = [&](auto kern) -> int {
     int per_sm = 0;
     PFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
