@@ -243,9 +243,9 @@ def run_gpu(args):
         else:
             noise_ring.append(src.normals((n, D), dev))
         u_ring.append(src.uniforms((n,), dev))
-    pp, _ = pf._predict_params(trans, noise_dist, pf._default_shift)  # parameter block only; its draws are dropped
-    del _
-    lp, keep = R.lik_params(lik_dist.set_mode(P["z"]), D, images_to_device=lambda t: torch.as_tensor(t, device=dev).contiguous())
+    with prandom.null():  # parameter block for array-fed draws (rng_kind = 0): the value leg reads the ring
+        pp, _ = pf._predict_params(trans, noise_dist, pf._default_shift)
+    lp, keep = R.lik_params(lik_dist.set_mode(P["z"]), D, images_to_device=R.device_put(dev))
     x = pf.filter_state._records().clone()
     alt = torch.empty_like(x)
     logw = torch.empty(n, dtype=torch.float64, device=dev)

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 1
+#define PFB_ABI_VERSION 2
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -67,7 +67,23 @@ typedef struct {
   double mu_noise[PFB_MAXD];
   double kappa;              /* SPHERE_VMF */
   double exp_m2k;            /* SPHERE_VMF: exp(-2 kappa), computed by the host like scipy does */
+  /* device RNG (production path; the parity path injects draws through `noise`): when rng_kind != 0 the
+   * `noise` pointer is ignored and the draws are generated in the kernel with Philox4x32-10 keyed by
+   * (rng_seed, rng_offset, particle index) -- nothing is read from or written to HBM for them */
+  int32_t rng_kind;          /* pfb_rng_kind */
+  int32_t reserved;
+  uint64_t rng_seed;
+  uint64_t rng_offset;
+  double rng_kappa[PFB_MAXD]; /* PFB_RNG_VONMISES: concentration per dimension */
+  double rng_vm_r[PFB_MAXD];  /* PFB_RNG_VONMISES: Best-Fisher constant r(kappa) per dimension (host-computed) */
 } pfb_predict_params;
+
+typedef enum {
+  PFB_RNG_NONE = 0,
+  PFB_RNG_NORMAL = 1,     /* standard normals in place of the noise rows (combine with has_A / mu_noise) */
+  PFB_RNG_VONMISES = 2,   /* zero-mean von Mises draws per dimension */
+  PFB_RNG_VMF = 3         /* (u, z1, z2) triples for PFB_PRED_SPHERE_VMF */
+} pfb_rng_kind;
 
 /* likelihood registry ---------------------------------------------------------------------- */
 typedef enum {
@@ -162,6 +178,14 @@ int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const d
                  const double* u, int32_t systematic, const void* x_in, void* x_out,
                  int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes,
                  void* stream);
+/* The same with the uniforms generated in the kernel (u_j = Philox(seed, offset, j), or u0 =
+ * Philox(seed, offset, 0) for systematic): the production path, no uniform array in HBM. */
+int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                     uint64_t rng_seed, uint64_t rng_offset, int32_t systematic, const void* x_in,
+                     void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
+                     int64_t ws_bytes, void* stream);
+/* fill `out` (n doubles) with the uniforms pfb_resample_rng would use (tests, debugging) */
+int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream);
 
 /* K(5) weighted moments (w == NULL: uniform 1/n).  out (doubles):
  *   PFB_MOM_MEAN    sum w x              (D)      linear_dirac_distribution.py:19-21, hyperspherical_dirac_distribution.py:43-44

@@ -111,6 +111,20 @@ class Engine:
                                       _stream(self.device)))
         self.launches += 2  # guide_kernel + resample_kernel
 
+    def resample_rng(self, cdf, seed, offset, x_in, x_out, n_out, dim, systematic=False, idx_out=None,
+                     est_kind=L.EST_NONE, est_out=None):
+        n = cdf.shape[0]
+        ws, wsb = self._ensure_ws(n)
+        dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        L.check(self.lib.pfb_resample_rng(dt, dim, n, n_out, _ptr(cdf), seed, offset, 1 if systematic else 0,
+                                          _ptr(x_in), _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
+                                          _stream(self.device)))
+        self.launches += 2
+
+    def rng_uniform(self, out, seed, offset):
+        L.check(self.lib.pfb_rng_uniform(out.numel(), seed, offset, _ptr(out), _stream(self.device)))
+        self.launches += 1
+
     def moments(self, kind, x, dim, w=None, order=1, center=None, out=None):
         n = x.shape[0]
         ws, wsb = self._ensure_ws(0)

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
+ABI_VERSION = 2
+RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
 # predict modes
 PRED_EUCLID, PRED_TORUS_SHIFT, PRED_TORUS_ADD, PRED_SPHERE_VMF, PRED_SPHERE_ADD = range(5)
@@ -35,7 +37,21 @@ class PredictParams(C.Structure):
         ("F", C.c_double * (PFB_MAXD * PFB_MAXD)), ("b", C.c_double * PFB_MAXD),
         ("A", C.c_double * (PFB_MAXD * PFB_MAXD)), ("mu_noise", C.c_double * PFB_MAXD),
         ("kappa", C.c_double), ("exp_m2k", C.c_double),
+        ("rng_kind", C.c_int32), ("reserved", C.c_int32), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
+        ("rng_kappa", C.c_double * PFB_MAXD), ("rng_vm_r", C.c_double * PFB_MAXD),
     ]
+
+    def set_von_mises_rng(self, kappas):
+        """per-dimension concentration + the Best-Fisher constant r = (1 + rho^2) / (2 rho)"""
+        import math
+
+        for c, k in enumerate(kappas):
+            k = float(k)
+            self.rng_kappa[c] = k
+            if k >= 1e-8:
+                tau = 1.0 + math.sqrt(1.0 + 4.0 * k * k)
+                rho = (tau - math.sqrt(2.0 * tau)) / (2.0 * k)
+                self.rng_vm_r[c] = (1.0 + rho * rho) / (2.0 * rho)
 
 
 class LikParams(C.Structure):
@@ -61,6 +77,9 @@ SIGNATURES = {
     "pfb_normalize": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pfb_scan_cdf": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pfb_resample": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "pfb_resample_rng": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, C.c_uint64, C.c_uint64, _i32, _vp, _vp, _vp, _i32, _vp,
+                                   _vp, _i64, _vp]),
+    "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
 }
@@ -98,7 +117,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.pfb_abi_version() != 1:
+        if handle.pfb_abi_version() != ABI_VERSION:
             raise PfbError("libpfb ABI version mismatch")
         _LIB = handle
     return _LIB

@@ -93,6 +93,95 @@ __device__ __forceinline__ double np_mod_2pi(double a) {
   return m;
 }
 
+// ---- counter-based device RNG (Philox4x32-10) ------------------------------------------------------
+// Draws are a pure function of (seed, offset, particle index, slot): no state to carry, the same
+// particle gets the same draw whatever the grid shape.  oracle/pf_oracle.py restates it in numpy.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct RngKey {
+  uint64_t seed;    // stream of this filter
+  uint64_t offset;  // call counter (advanced by the host once per predict / resample)
+};
+__device__ __forceinline__ uint4 rng_block(const RngKey& k, uint64_t index, uint32_t slot) {
+  return philox4x32_10(make_uint4((uint32_t)index, (uint32_t)(index >> 32), slot, (uint32_t)k.offset),
+                       make_uint2((uint32_t)k.seed, (uint32_t)(k.seed >> 32) ^ (uint32_t)(k.offset >> 32)));
+}
+// 53-bit uniform in [0, 1) from two 32-bit words
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return (double)((((uint64_t)a << 32) | b) >> 11) * 1.1102230246251565e-16;
+}
+// two independent standard normals from one Philox block (Box-Muller; u1 in (0, 1])
+__device__ __forceinline__ void normal_pair(const uint4& r, double* z0, double* z1) {
+  const double u1 = 1.0 - u53(r.x, r.y);
+  const double u2 = u53(r.z, r.w);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  *z0 = rad * cs;
+  *z1 = rad * sn;
+}
+// Zero-mean von Mises draws in [-pi, pi] for D dimensions at once (Best & Fisher 1979: wrapped-Cauchy
+// envelope, rejection).  rr = (1 + rho^2)/(2 rho), rho = (tau - sqrt(2 tau))/(2 kappa),
+// tau = 1 + sqrt(1 + 4 kappa^2) comes from the host.  One Philox block per attempt: 53 bits for the
+// proposal, 32 for the acceptance uniform, 1 for the sign.  The accept/reject decision is evaluated in
+// fp32 (it only shapes the acceptance probability, to ~1e-6 relative); the accepted proposal is then
+// mapped to the angle in fp64 from its 53-bit uniform.  All dimensions share one loop (a lane works on
+// its lowest unfinished dimension) so that a warp pays max-over-lanes of the SUM of attempts, not the sum
+// of per-dimension maxima.
+template <int D>
+__device__ __forceinline__ void vonmises_draws(const RngKey& k, uint64_t index, const double* kappa,
+                                               const double* rr, double (&out)[D]) {
+  // phase 1 (divergent, fp32 + integer only): find the accepted proposal of every dimension
+  double u_acc[D];
+  uint32_t sign_acc = 0;
+  uint32_t attempt = 0;
+  int c = 0;
+  while (c < D) {
+    const float kf = (float)kappa[c], rf = (float)rr[c];
+    const uint4 r = rng_block(k, index, (uint32_t)c + (attempt << 8));
+    ++attempt;
+    const double u1 = u53(r.x, r.y);
+    bool accept = true;
+    if (kf >= 1e-8f) {
+      const float zf = cospif((float)u1);
+      const float ff = (1.0f + rf * zf) / (rf + zf);
+      const float cf = kf * (rf - ff);
+      const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f;
+      accept = (cf * (2.0f - cf) - u2 > 0.0f) || (__logf(cf / u2) + 1.0f - cf >= 0.0f) || attempt >= 64u;
+    }
+    if (accept) {
+#pragma unroll
+      for (int cc = 0; cc < D; ++cc)
+        if (cc == c) u_acc[cc] = u1;  // (static indices keep the array in registers)
+      sign_acc |= (r.w & 1u) << c;
+      ++c;
+      attempt = 0;
+    }
+  }
+  // phase 2 (uniform, fp64): proposal -> angle
+#pragma unroll
+  for (int cc = 0; cc < D; ++cc) {
+    double th;
+    if (kappa[cc] < 1e-8) {
+      th = 3.141592653589793 * u_acc[cc];  // uniform on the circle: |theta| uniform in [0, pi), sign below
+    } else {
+      const double z = cospi(u_acc[cc]);
+      const double f = (1.0 + rr[cc] * z) / (rr[cc] + z);
+      th = acos(fmin(1.0, fmax(-1.0, f)));
+    }
+    out[cc] = ((sign_acc >> cc) & 1u) ? th : -th;
+  }
+}
+
 // ---- record I/O ---------------------------------------------------------------------------
 // Particle records are row-major (n, D).  v1: straight per-thread loads; consecutive lanes read
 // consecutive records so a warp touches one contiguous 32*D*sizeof(T) byte span.

@@ -37,7 +37,27 @@ template <typename T, int D>
 __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T* __restrict__ noise,
                                            int64_t i, double (&n)[D]) {
   double z[D];
-  load_rec<T, D>(noise, i, z);
+  if (p.rng_kind == PFB_RNG_NORMAL) {
+    const RngKey key{p.rng_seed, p.rng_offset};
+#pragma unroll
+    for (int c = 0; c < D; c += 2) {
+      double z0, z1;
+      normal_pair(rng_block(key, (uint64_t)i, (uint32_t)(c >> 1)), &z0, &z1);
+      z[c] = z0;
+      if (c + 1 < D) z[c + 1] = z1;
+    }
+  } else if (p.rng_kind == PFB_RNG_VONMISES) {
+    const RngKey key{p.rng_seed, p.rng_offset};
+    vonmises_draws<D>(key, (uint64_t)i, p.rng_kappa, p.rng_vm_r, z);
+  } else {
+    load_rec<T, D>(noise, i, z);
+  }
+  if constexpr (sizeof(T) == 4) {
+    if (p.rng_kind != PFB_RNG_NONE) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) z[c] = (double)(float)z[c];  // what an fp32 noise array would have held
+    }
+  }
   if (p.has_A) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -62,7 +82,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   double x[D], y[D];
   load_rec<T, D>(x_in, i, x);
   apply_transition<D>(p, x, y);
-  const bool has_noise = (noise != nullptr) && p.noise_cols > 0;
+  const bool has_noise = (noise != nullptr || p.rng_kind != PFB_RNG_NONE) && p.noise_cols > 0;
   if constexpr (MODE == PFB_PRED_EUCLID) {
     if (has_noise) {
       double n[D];
@@ -104,7 +124,17 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
     static_assert(D == 3 || MODE != PFB_PRED_SPHERE_VMF, "VMF noise is implemented on S^2");
     if (has_noise) {
       double t[D];
-      load_rec<T, D>(noise, i, t);               // (u, z1, z2)
+      if (p.rng_kind == PFB_RNG_VMF) {
+        const RngKey key{p.rng_seed, p.rng_offset};
+        const uint4 r0 = rng_block(key, (uint64_t)i, 0u);
+        t[0] = u53(r0.x, r0.y);
+        double z0, z1;
+        normal_pair(rng_block(key, (uint64_t)i, 1u), &z0, &z1);
+        t[1 % D] = z0;
+        t[2 % D] = z1;
+      } else {
+        load_rec<T, D>(noise, i, t);             // (u, z1, z2)
+      }
       // scipy _rvs_3d: canonical draw around e1
       double xc = 1.0 + log(t[0] + (1.0 - t[0]) * p.exp_m2k) / p.kappa;
       double temp = sqrt(1.0 - xc * xc);

@@ -146,11 +146,16 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
                                                             const T* __restrict__ x_in, T* __restrict__ x_out,
                                                             int64_t* __restrict__ idx_out, double* est_out,
                                                             Workspace ws, const int32_t* __restrict__ guide,
-                                                            int64_t M) {
+                                                            int64_t M, RngKey key) {
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
   const double total = *total_ptr;
-  const double u0 = systematic ? u[0] : 0.0;
+  const bool use_rng = (u == nullptr);
+  double u0 = 0.0;
+  if (systematic) {
+    if (use_rng) { const uint4 r = rng_block(key, 0ULL, 7u); u0 = u53(r.x, r.y); }
+    else u0 = u[0];
+  }
   const double dn = (double)n_out;
   const double dM = (double)M;
   double acc[NE];
@@ -166,7 +171,10 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
     for (int q = 0; q < kBatch; ++q) {
       const int64_t j = j0 + q * stride;
       live[q] = j < n_out;
-      uj[q] = !live[q] ? 0.0 : (systematic ? __ddiv_rn(__dadd_rn((double)j, u0), dn) : __ldg(u + j));
+      if (!live[q]) uj[q] = 0.0;
+      else if (systematic) uj[q] = __ddiv_rn(__dadd_rn((double)j, u0), dn);
+      else if (use_rng) { const uint4 r = rng_block(key, (uint64_t)j, 7u); uj[q] = u53(r.x, r.y); }
+      else uj[q] = __ldg(u + j);
     }
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
@@ -355,17 +363,17 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(int64_t n, const T* _
 template <typename T, int D>
 static int launch_resample(int64_t n, int64_t n_out, const double* cdf, const double* u, int systematic,
                            const double* stats, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
-                           double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M) {
+                           double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M, RngKey key) {
   const int grid = stream_grid(n_out);
   switch (est_kind) {
     case PFB_EST_NONE:
-      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
+      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
       break;
     case PFB_EST_SUM:
-      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
+      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
       break;
     case PFB_EST_TRIG:
-      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M);
+      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
       break;
     default:
       set_error("bad est_kind %d", est_kind);
@@ -407,12 +415,12 @@ extern "C" int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream) {
   return PFB_OK;
 }
 
-extern "C" int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
-                            const double* u, int32_t systematic, const void* x_in, void* x_out,
-                            int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes,
-                            void* stream) {
+namespace pfb {
+static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf, const double* u,
+                         RngKey key, int32_t systematic, const void* x_in, void* x_out, int64_t* idx_out,
+                         int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream) {
   if (n <= 0 || n_out <= 0) return PFB_OK;
-  if (!cdf || !u) { set_error("NULL cdf / uniforms"); return PFB_ERR_INVALID; }
+  if (!cdf) { set_error("NULL cdf"); return PFB_ERR_INVALID; }
   if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
   if (x_in && x_in == x_out) { set_error("resampling cannot run in place"); return PFB_ERR_INVALID; }
   if (est_kind != PFB_EST_NONE && (!est_out || !x_in)) { set_error("estimate requested without output / particles"); return PFB_ERR_INVALID; }
@@ -426,9 +434,43 @@ extern "C" int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_o
   const int64_t M = W.guide_buckets;
   guide_kernel<<<stream_grid(n, 4), kThreads, 0, st>>>(n, cdf, stats_total, W.guide, M);
   PFB_LAUNCH_OK("guide_kernel");
-  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M))));
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M, key))));
   if (rc) return rc;
   PFB_LAUNCH_OK("resample_kernel");
+  return PFB_OK;
+}
+
+__global__ void __launch_bounds__(kThreads) rng_uniform_kernel(int64_t n, RngKey key, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint4 r = rng_block(key, (uint64_t)j, 7u);
+    out[j] = u53(r.x, r.y);
+  }
+}
+}  // namespace pfb
+
+extern "C" int pfb_resample(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                            const double* u, int32_t systematic, const void* x_in, void* x_out,
+                            int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes,
+                            void* stream) {
+  if (n > 0 && n_out > 0 && !u) { set_error("NULL uniforms (use pfb_resample_rng for in-kernel draws)"); return PFB_ERR_INVALID; }
+  return resample_impl(dtype, dim, n, n_out, cdf, u, RngKey{0, 0}, systematic, x_in, x_out, idx_out, est_kind, est_out,
+                       ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                                uint64_t rng_seed, uint64_t rng_offset, int32_t systematic, const void* x_in,
+                                void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
+                                int64_t ws_bytes, void* stream) {
+  return resample_impl(dtype, dim, n, n_out, cdf, nullptr, RngKey{rng_seed, rng_offset}, systematic, x_in, x_out,
+                       idx_out, est_kind, est_out, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if (!out) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  rng_uniform_kernel<<<stream_grid(n), kThreads, 0, (cudaStream_t)stream>>>(n, RngKey{rng_seed, rng_offset}, out);
+  PFB_LAUNCH_OK("rng_uniform_kernel");
   return PFB_OK;
 }
 

@@ -60,7 +60,7 @@ class _RegistryDistribution:
         x = _as_device_tensor(xs)
         x2 = x.reshape(-1, stored_dim).contiguous()
         eng = engine(x2.device)
-        lp, keep = R.lik_params(self, stored_dim, images_to_device=lambda t: torch.as_tensor(t, device=x2.device).contiguous())
+        lp, keep = R.lik_params(self, stored_dim, images_to_device=R.device_put(x2.device))
         logw = torch.empty(x2.shape[0], dtype=torch.float64, device=x2.device)
         eng.loglik(lp, x2, logw)
         del keep
@@ -470,8 +470,7 @@ class AbstractDiracDistribution:
         """log-likelihood weighting on the device; returns (logw, stats-after-normalise are in engine)."""
         dist_obj = R.as_distribution(likelihood)
         x = self._records()
-        lp, keep = R.lik_params(dist_obj, self._stored_dim,
-                                images_to_device=lambda t: torch.as_tensor(t, device=x.device).contiguous())
+        lp, keep = R.lik_params(dist_obj, self._stored_dim, images_to_device=R.device_put(x.device))
         logw = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
         self._eng().loglik(lp, x, logw, w_prev=self._weights_or_none())
         return logw, keep
@@ -501,9 +500,12 @@ class AbstractDiracDistribution:
         cdf = torch.empty(N, dtype=torch.float64, device=x.device)
         w = self._w
         eng.scan(cdf, w=w.contiguous(), exact=exact)
-        u = prandom.source().uniforms((n,), x.device)
         out = torch.empty((n, x.shape[1]), dtype=x.dtype, device=x.device)
-        eng.resample(cdf, u, x, out, n, x.shape[1])
+        src = prandom.source()
+        if src.fused:
+            eng.resample_rng(cdf, src.seed, src.next_offset(), x, out, n, x.shape[1])
+        else:
+            eng.resample(cdf, src.uniforms((n,), x.device), x, out, n, x.shape[1])
         return out.reshape(n) if self._one_d else out
 
     def entropy(self):

@@ -52,14 +52,31 @@ class AbstractParticleFilter:
         self._cdf = None
         self._est = None
         self.last_log_max = None
+        # predict is deferred until the particles are looked at, so that a following update runs the fused
+        # predict+weight kernel (one pass over the particles instead of two); reading `filter_state`
+        # materialises it, so the reference's observable semantics are unchanged
+        self.lazy_predict = True
+        self._pending = None
 
     # ---- state ---------------------------------------------------------------------------------
+    def _flush(self):
+        if self._pending is not None:
+            p, noise = self._pending
+            self._pending = None
+            st = self._filter_state
+            x = st._records()
+            self._eng().predict(p, x, x, noise)  # in place
+            st._d = x.reshape(st._d.shape)
+            st._est_cache = None
+
     @property
     def filter_state(self):
+        self._flush()
         return self._filter_state
 
     @filter_state.setter
     def filter_state(self, new_state):
+        self._pending = None  # a new state replaces whatever a deferred predict would have produced
         self._set_filter_state(new_state)
 
     def _set_filter_state(self, new_state):
@@ -109,13 +126,13 @@ class AbstractParticleFilter:
         """abstract_particle_filter.py:21-54: d <- f(d), then one noise draw per particle."""
         if shift_instead_of_add is None:
             shift_instead_of_add = self._default_shift
+        self._flush()
         st = self._filter_state
         assert noise_distribution is None or self._noise_dim_ok(noise_distribution)
-        p, noise = self._predict_params(f, noise_distribution, shift_instead_of_add)
-        x = st._records()
-        self._eng().predict(p, x, x, noise)  # in place
-        st._d = x.reshape(st._d.shape)
+        self._pending = self._predict_params(f, noise_distribution, shift_instead_of_add)
         st._est_cache = None
+        if not self.lazy_predict:
+            self._flush()
 
     def _noise_dim_ok(self, noise):
         return self.filter_state.dim == noise.dim
@@ -125,6 +142,13 @@ class AbstractParticleFilter:
             "predict_nonlinear_nonadditive needs an arbitrary f(x, noise) callable; it is the next row of the "
             "scope table (SURVEY.md 8f-1) and not on the CUDA path yet."
         )
+
+    def _normals_or_key(self, p, src, shape):
+        """standard normals: injected / torch-made array, or the in-kernel Philox key (production)"""
+        if src.fused:
+            p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_NORMAL, src.seed, src.next_offset()
+            return None
+        return src.normals(shape, self._filter_state.device, self._filter_state.d.dtype)
 
     def _fill_transition(self, p, f):
         D = p.dim
@@ -156,8 +180,18 @@ class AbstractParticleFilter:
         x = self._scratch()
         eng = self._eng()
         N, D = x.shape
-        lp, keep = R.lik_params(dist, D, images_to_device=lambda t: torch.as_tensor(t, device=x.device).contiguous())
-        eng.loglik(lp, x, self._logw, w_prev=st._weights_or_none())
+        lp, keep = R.lik_params(dist, D, images_to_device=R.device_put(x.device))
+        if self._pending is not None and st._uniform:
+            p, noise = self._pending
+            self._pending = None
+            try:
+                eng.predict_loglik(p, lp, x, x, noise, self._logw)  # fused K(1)+K(2), in place
+            except NotImplementedError:  # (mode, likelihood) pair without a fused instantiation
+                eng.predict(p, x, x, noise)
+                eng.loglik(lp, x, self._logw)
+        else:
+            self._flush()
+            eng.loglik(lp, x, self._logw, w_prev=st._weights_or_none())
         self._resample_from_logw(x, keep)
 
     def _est_kind(self):
@@ -177,9 +211,14 @@ class AbstractParticleFilter:
         systematic = self.resampling == "systematic"
         if not systematic and self.resampling != "multinomial":
             raise ValueError(f"unknown resampling scheme {self.resampling!r}")
-        u = prandom.source().uniforms((1,) if systematic else (N,), x.device)
-        eng.resample(self._cdf, u, x, self._alt, N, D, systematic=systematic, est_kind=self._est_kind(),
-                     est_out=self._est)
+        src = prandom.source()
+        if src.fused:
+            eng.resample_rng(self._cdf, src.seed, src.next_offset(), x, self._alt, N, D, systematic=systematic,
+                             est_kind=self._est_kind(), est_out=self._est)
+        else:
+            u = src.uniforms((1,) if systematic else (N,), x.device)
+            eng.resample(self._cdf, u, x, self._alt, N, D, systematic=systematic, est_kind=self._est_kind(),
+                         est_out=self._est)
         del keep
         new = self._alt
         self._alt = x
@@ -193,10 +232,10 @@ class AbstractParticleFilter:
 
     def association_likelihood(self, likelihood):
         """abstract_particle_filter.py:127-129: sum_i w_i pdf(d_i)."""
-        st = self._filter_state
+        st = self.filter_state
         dist = R.as_distribution(likelihood)
         x = st._records()
-        lp, keep = R.lik_params(dist, x.shape[1], images_to_device=lambda t: torch.as_tensor(t, device=x.device).contiguous())
+        lp, keep = R.lik_params(dist, x.shape[1], images_to_device=R.device_put(x.device))
         logw = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
         self._eng().loglik(lp, x, logw)
         del keep
@@ -243,7 +282,8 @@ class EuclideanParticleFilter(AbstractParticleFilter):
         if kind != "gauss":
             raise NotImplementedError("Euclidean filters take Gaussian system noise")
         N = self._filter_state.w.shape[0]
-        z = prandom.source().normals((N, D), self._filter_state.device, self._filter_state.d.dtype)
+        src = prandom.source()
+        z = self._normals_or_key(p, src, (N, D))
         p.noise_cols, p.has_A = D, 1
         p.A[: D * D] = spec["A"].reshape(-1).tolist()
         if not shift:  # add-mode keeps the noise mean; shift-mode replaces it by the particle
@@ -284,14 +324,19 @@ class HypertoroidalParticleFilter(AbstractParticleFilter):
         src = prandom.source()
         p.noise_cols = D
         if kind in ("wn", "gauss"):
-            z = src.normals((N, D), st.device, st.d.dtype)
+            z = self._normals_or_key(p, src, (N, D))
             p.has_A = 1
             p.A[: D * D] = spec["A"].reshape(-1).tolist()
             mu = np.mod(spec["mu"], TWO_PI)
         elif kind == "vm":
             kap = spec["kappa"]
             kap = np.broadcast_to(kap, (D,)) if kap.shape[0] in (1, D) else kap
-            z = src.vonmises((N, D), torch.as_tensor(np.array(kap, dtype=np.float64)), st.device, st.d.dtype)
+            if src.fused:
+                p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VONMISES, src.seed, src.next_offset()
+                p.set_von_mises_rng(np.array(kap, dtype=np.float64).tolist())
+                z = None
+            else:
+                z = src.vonmises((N, D), torch.as_tensor(np.array(kap, dtype=np.float64)), st.device, st.d.dtype)
             mu = np.mod(np.broadcast_to(spec["mu"], (D,)), TWO_PI)
         else:
             raise NotImplementedError(f"{kind} noise is not defined on the hypertorus")
@@ -376,6 +421,9 @@ class HypersphericalParticleFilter(AbstractParticleFilter):
             p.mode, p.noise_cols = L.PRED_SPHERE_VMF, 3
             p.kappa = spec["kappa"]
             p.exp_m2k = float(np.exp(-2 * spec["kappa"]))
+            if src.fused:
+                p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VMF, src.seed, src.next_offset()
+                return p, None
             return p, src.vmf_triples(N, st.device, st.d.dtype)
         if kind == "gauss":
             p.mode, p.noise_cols, p.has_A = L.PRED_SPHERE_ADD, D, 1
@@ -383,7 +431,7 @@ class HypersphericalParticleFilter(AbstractParticleFilter):
             if np.any(spec["mu"] != 0):
                 p.has_mu_noise = 1
                 p.mu_noise[:D] = spec["mu"].tolist()
-            return p, src.normals((N, D), st.device, st.d.dtype)
+            return p, self._normals_or_key(p, src, (N, D))
         raise NotImplementedError(f"{kind} noise is not defined on the hypersphere")
 
     def _estimate_from_sums(self, est, D):

@@ -11,9 +11,24 @@ import torch
 
 
 class DeviceDraws:
+    """Production source.  The per-step draws of the filters (system noise, resampling uniforms) are
+    generated INSIDE the predict / resample kernels by a counter-based Philox4x32-10 keyed with
+    (seed, call counter, particle index): `fused = True` tells the filters to pass the key instead of
+    arrays.  Prior sampling (`distribution.sample(n)`) uses the torch CUDA generator below."""
+
+    fused = True
+
     def __init__(self, seed=None):
+        import os
+
         self._gens = {}
         self._seed = seed
+        self.seed = int(seed) & (2**64 - 1) if seed is not None else int.from_bytes(os.urandom(8), "little")
+        self._offset = 0
+
+    def next_offset(self):
+        self._offset += 1
+        return self._offset
 
     def _gen(self, device):
         key = str(device)
@@ -49,6 +64,8 @@ class DeviceDraws:
 class InjectedDraws:
     """FIFO of host-provided draws (numpy arrays / tensors)."""
 
+    fused = False
+
     def __init__(self, normals=None, uniforms=None, vonmises=None, vmf_triples=None):
         self._q = {"normals": normals, "uniforms": uniforms, "vonmises": vonmises, "vmf": vmf_triples}
         self._pos = {k: 0 for k in self._q}
@@ -81,6 +98,17 @@ class InjectedDraws:
         return self._take("vmf", 3 * n, device, dtype).reshape(n, 3)
 
 
+class NullDraws:
+    """Hands out no draws at all (None): used to build a parameter block whose noise array the caller supplies."""
+
+    fused = False
+
+    def normals(self, *a, **k):
+        return None
+
+    uniforms = vonmises = vmf_triples = normals
+
+
 _SOURCE = DeviceDraws()
 
 
@@ -92,6 +120,17 @@ def seed(s):
     """Seed the device draw source (the analogue of pyrecest.backend.random.seed)."""
     global _SOURCE
     _SOURCE = DeviceDraws(seed=s)
+
+
+@contextlib.contextmanager
+def null():
+    global _SOURCE
+    saved = _SOURCE
+    _SOURCE = NullDraws()
+    try:
+        yield _SOURCE
+    finally:
+        _SOURCE = saved
 
 
 @contextlib.contextmanager

@@ -161,6 +161,38 @@ def vmf_log_norm_const(kappa, D):
     return (half - 1.0) * math.log(kappa) - half * math.log(TWO_PI) - _log_iv(half - 1.0, kappa)
 
 
+_IMAGE_TABLE_CACHE: dict = {}
+
+
+class device_put:
+    """callable host array -> contiguous device tensor, hashable per device for the table cache"""
+
+    def __init__(self, device):
+        self.device = device
+        self.cache_key = str(device)
+
+    def __call__(self, table):
+        import torch
+
+        return torch.as_tensor(table, device=self.device).contiguous()
+
+
+def wn_image_table_cached(mu, P, device_put=None):
+    """(table, n_images, device copy) memoised on (mu, P): a filter re-uses the same measurement-noise
+    covariance every step and often revisits measurements, and the pruning below costs milliseconds of
+    host time that would otherwise sit on the critical path of every update."""
+    key = (np.asarray(mu, dtype=np.float64).tobytes(), np.asarray(P, dtype=np.float64).tobytes(),
+           None if device_put is None else getattr(device_put, "cache_key", None))
+    hit = _IMAGE_TABLE_CACHE.get(key)
+    if hit is None:
+        table, n_img = wn_image_table(mu, P)
+        dev = device_put(table) if device_put is not None else None
+        if len(_IMAGE_TABLE_CACHE) > 256:
+            _IMAGE_TABLE_CACHE.clear()
+        hit = _IMAGE_TABLE_CACHE[key] = (table, n_img, dev)
+    return hit
+
+
 def wn_image_table(mu, P, m=3, cut=None):
     """Image list of HypertoroidalWrappedNormalDistribution.pdf
     (hypertoroidal_wrapped_normal_distribution.py:80-91): all offsets 2 pi k, k in {-m..m}^d, pruned to
@@ -232,14 +264,14 @@ def lik_params(dist, dim, images_to_device=None):
             raise AssertionError("likelihood dimension does not match the filter state")
         C = np.atleast_2d(_np(dist.C))
         W, logdet = gaussian_whitening(C)
-        table, n_img = wn_image_table(mu, W @ W.T)
+        table, n_img, dev_table = wn_image_table_cached(mu, W @ W.T, images_to_device)
         p.kind = L.LIK_WN_MULTI
         p.mu[:dim] = mu.tolist()
         p.W[: dim * dim] = W.reshape(-1).tolist()
         p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)
         p.n_images = n_img
-        if images_to_device is not None:
-            keep = images_to_device(table)
+        if dev_table is not None:
+            keep = dev_table
             p.images_dev = keep.data_ptr()
         else:
             keep = table

@@ -254,3 +254,28 @@ def test_dirac_moments_api(golden):
 
     rw = ld.reweigh(GaussianDistribution(np.ones(4), np.eye(4)))
     np.testing.assert_allclose(host(rw.w), g["lin_reweighed"], rtol=1e-12)
+
+
+def test_fused_rng_path_is_reproducible_and_seed_dependent():
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN, VonMisesDistribution
+    from pyrecest_b200.filters import HypertoroidalParticleFilter
+
+    C = np.array([[0.7, 0.4, 0.2], [0.4, 0.6, 0.1], [0.2, 0.1, 1.0]])
+
+    def run(seed):
+        prandom.seed(seed)
+        pf = HypertoroidalParticleFilter(20_000, 3)
+        pf.filter_state = HWN(np.array([1.0, 1.0, 1.0]) + math.pi / 2, C)
+        for _ in range(5):
+            pf.predict_identity(VonMisesDistribution(np.zeros(3), np.array([10.0, 10.0, 10.0])))
+            pf.update_identity(HWN(np.zeros(3), 0.5 * C), np.array([1.0, 2.0, 3.0]))
+        return host(pf.filter_state.d), host(pf.get_point_estimate())
+
+    d1, e1 = run(7)
+    d2, e2 = run(7)
+    d3, e3 = run(8)
+    assert np.array_equal(d1, d2) and np.array_equal(e1, e2)
+    assert not np.array_equal(d1, d3)
+    np.testing.assert_allclose(e1, [1.0, 2.0, 3.0], atol=0.1)
+    np.testing.assert_allclose(e3, [1.0, 2.0, 3.0], atol=0.1)

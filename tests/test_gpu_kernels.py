@@ -59,7 +59,7 @@ def pparams(mode, dim, noise_cols=None, F=None, b=None, A=None, mu=None, kappa=0
 def test_abi_version():
     from pyrecest_b200 import _lib as L
 
-    assert L.lib().pfb_abi_version() == 1
+    assert L.lib().pfb_abi_version() == 2
 
 
 def test_wrap_bitexact(eng, golden):
@@ -419,3 +419,69 @@ def test_rejects_bad_arguments(eng):
     lp.kind, lp.dim = 17, 3
     with pytest.raises(NotImplementedError):
         eng.loglik(lp, x, torch.zeros(4, dtype=torch.float64, device="cuda:0"))
+
+
+# ---- device RNG (production path) -------------------------------------------------------------------
+def test_rng_uniforms_match_philox_restatement(eng):
+    from oracle import philox as P
+
+    for seed, offset, n in ((0, 0, 1000), (0x1234567890ABCDEF, 7, 100_003), (2**64 - 1, 2**40 + 5, 4097)):
+        out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+        eng.rng_uniform(out, seed, offset)
+        ref = P.resample_uniforms(seed, offset, n)
+        assert np.array_equal(host(out), ref)
+        assert ref.min() >= 0.0 and ref.max() < 1.0
+
+
+def test_rng_resample_equals_injecting_the_same_uniforms(eng, golden):
+    from oracle import philox as P
+
+    g = golden("resample_cases")
+    w = g["lik_w"]
+    n = w.shape[0]
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    idx = torch.empty(n, dtype=torch.int64, device="cuda:0")
+    eng.resample_rng(cdf, 99, 3, None, None, n, 1, idx_out=idx)
+    assert np.array_equal(host(idx), O.multinomial_indices(w, P.resample_uniforms(99, 3, n)))
+    eng.resample_rng(cdf, 99, 4, None, None, n, 1, systematic=True, idx_out=idx)
+    assert np.array_equal(host(idx), O.systematic_indices(w, P.systematic_u0(99, 4), n))
+
+
+def test_rng_normals_and_von_mises_and_vmf(eng):
+    from oracle import philox as P
+    from pyrecest_b200 import _lib as L
+    from scipy.special import iv
+
+    n = 400_000
+    x = torch.zeros((n, 3), dtype=torch.float64, device="cuda:0")
+    out = torch.empty_like(x)
+    p = pparams(L.PRED_EUCLID, 3)
+    p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_NORMAL, 5, 11
+    eng.predict(p, x, out, None)
+    z = host(out)
+    np.testing.assert_allclose(z, P.normals(5, 11, n, 3), rtol=1e-12, atol=1e-14)
+    assert abs(z.mean()) < 5 / np.sqrt(3 * n) and abs(z.var() - 1) < 0.01
+    assert np.abs(np.corrcoef(z.T) - np.eye(3)).max() < 0.01
+    # von Mises per dimension: E cos = I1/I0, E sin = 0
+    p = pparams(L.PRED_TORUS_SHIFT, 3)
+    p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VONMISES, 5, 12
+    kap = [0.0, 2.0, 50.0]
+    p.set_von_mises_rng(kap)
+    eng.predict(p, x, out, None)
+    v = host(out)
+    assert v.min() >= 0 and v.max() <= 2 * np.pi
+    for c, k in enumerate(kap):
+        a = iv(1, k) / iv(0, k)
+        assert abs(np.cos(v[:, c]).mean() - a) < 5 / np.sqrt(n), (k, np.cos(v[:, c]).mean(), a)
+        assert abs(np.sin(v[:, c]).mean()) < 5 / np.sqrt(n)
+    # VMF on S^2 around e3: resultant length coth k - 1/k
+    modes = torch.zeros((n, 3), dtype=torch.float64, device="cuda:0")
+    modes[:, 2] = 1.0
+    p = pparams(L.PRED_SPHERE_VMF, 3, kappa=8.0)
+    p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VMF, 5, 13
+    eng.predict(p, modes, out, None)
+    s = host(out)
+    np.testing.assert_allclose(np.linalg.norm(s, axis=1), 1.0, atol=1e-14)
+    m = s.mean(axis=0)
+    assert abs(m[2] - (1 / np.tanh(8.0) - 1 / 8.0)) < 5 / np.sqrt(n) and np.abs(m[:2]).max() < 5 / np.sqrt(n)
