@@ -345,6 +345,47 @@ def update_resample(d, w, lik, u):
 
 
 # --------------------------------------------------------------------------------------
+# sharded filter -- PARITY UNPINNED: the reference has no multi-device path.
+# Definition: every shard g (a contiguous range of particles) forms its own sequential cumsum c^g of
+# p = exp(logw - M), M the global max; shard offsets are added sequentially in rank order,
+# O_0 = 0, O_{g+1} = fl(O_g + c^g[-1]); the global CDF is v_i = fl(fl(O_g + c^g_i) / O_G).  With one shard
+# this is exactly cdf_of().  Systematic resampling then runs on that global CDF.
+# --------------------------------------------------------------------------------------
+def sharded_cdf(p_shards):
+    cs = [np.cumsum(np.asarray(p, dtype=np.float64)) for p in p_shards]
+    offs = [0.0]
+    for c in cs:
+        offs.append(offs[-1] + (c[-1] if c.size else 0.0))
+    total = offs[-1]
+    v = np.concatenate([(offs[g] + cs[g]) / total for g in range(len(cs))])
+    return v, np.array(offs), cs
+
+
+def sharded_systematic_indices(p_shards, u0, n_out=None):
+    v, _, _ = sharded_cdf(p_shards)
+    n_out = v.shape[0] if n_out is None else n_out
+    idx = np.searchsorted(v, systematic_uniforms(u0, n_out), side="right").astype(np.int64)
+    return np.minimum(idx, v.shape[0] - 1)
+
+
+def offspring_boundaries(offs, u0, n_out):
+    """B_g = #{j : u_j < fl(O_g / O_G)}: offspring [B_g, B_{g+1}) of the comb come from shard g."""
+    total = offs[-1]
+    B = []
+    for g in range(len(offs)):
+        E = offs[g] / total
+        j = int(np.floor(E * n_out - u0))
+        j = min(max(j, 0), n_out)
+        while j < n_out and (np.float64(j) + np.float64(u0)) / np.float64(n_out) < E:
+            j += 1
+        while j > 0 and (np.float64(j - 1) + np.float64(u0)) / np.float64(n_out) >= E:
+            j -= 1
+        B.append(j)
+    B[-1] = n_out
+    return B
+
+
+# --------------------------------------------------------------------------------------
 # moments / estimates
 # --------------------------------------------------------------------------------------
 def uniform_w(N):

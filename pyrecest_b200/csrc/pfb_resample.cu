@@ -440,6 +440,32 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   return PFB_OK;
 }
 
+// one shard of a globally resampled filter: systematic comb, global CDF = offset + local running sums
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) resample_sharded_kernel(int64_t n, const double* __restrict__ cdf,
+                                                                    double cdf_offset, double total, double u0,
+                                                                    int64_t j_begin, int64_t count, double dn_total,
+                                                                    const T* __restrict__ x_in, T* __restrict__ x_out,
+                                                                    int64_t* __restrict__ idx_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const double uj = __ddiv_rn(__dadd_rn((double)(j_begin + k), u0), dn_total);
+    int64_t lo = 0, hi = n;  // neighbouring k search neighbouring entries: probes coalesce
+    while (lo < hi) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      const double v = __ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + mid)), total);
+      if (v <= uj) lo = mid + 1; else hi = mid;
+    }
+    if (lo > n - 1) lo = n - 1;
+    if (idx_out) idx_out[k] = lo;
+    if (x_in != nullptr) {
+      double r[D];
+      load_rec<T, D>(x_in, lo, r);
+      store_rec<T, D>(x_out, k, r);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) rng_uniform_kernel(int64_t n, RngKey key, double* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
@@ -464,6 +490,21 @@ extern "C" int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t
                                 int64_t ws_bytes, void* stream) {
   return resample_impl(dtype, dim, n, n_out, cdf, nullptr, RngKey{rng_seed, rng_offset}, systematic, x_in, x_out,
                        idx_out, est_kind, est_out, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, double cdf_offset,
+                                    double total, double u0, int64_t j_begin, int64_t count, int64_t n_total_out,
+                                    const void* x_in, void* x_out, int64_t* idx_out, void* stream) {
+  if (n <= 0 || count <= 0) return PFB_OK;
+  if (!cdf) { set_error("NULL cdf"); return PFB_ERR_INVALID; }
+  if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
+  if (!(total > 0.0) || n_total_out <= 0) { set_error("total weight and comb size must be positive"); return PFB_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(count);
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (resample_sharded_kernel<T, D><<<grid, kThreads, 0, st>>>(
+      n, cdf, cdf_offset, total, u0, j_begin, count, (double)n_total_out, (const T*)x_in, (T*)x_out, idx_out))));
+  PFB_LAUNCH_OK("resample_sharded_kernel");
+  return PFB_OK;
 }
 
 extern "C" int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream) {

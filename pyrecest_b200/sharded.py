@@ -1,0 +1,258 @@
+"""One particle filter whose particles are split across the GPUs of a torch.distributed group
+(BASELINE.json configs[4]: R^4, 1e9 particles over 2/4/8 B200 with global systematic
+resampling).  The reference has nothing comparable (single process, host memory).
+
+Shard g owns the contiguous global particle range [g n_loc, (g+1) n_loc).  Per step:
+
+  predict + weight   local (pfb_predict_loglik), no communication
+  global max         all_reduce(MAX) of one double           -> every shard exponentiates against the same shift
+  local CDF          sequential-exact scan of exp(logw - M)  (pfb_scan_cdf), shard total T_g
+  shard offsets      all_gather of the G totals; O_{g+1} = fl(O_g + T_g) summed in rank order on every
+                     rank (identical bits everywhere); global CDF v_i = fl(fl(O_g + c_i) / O_G)
+  resampling         systematic comb u_j = (j + u0)/N over the GLOBAL CDF: the offspring that fall into
+                     shard g are the contiguous range [B_g, B_{g+1}), B_g = #{j : u_j < fl(O_g/O_G)};
+                     shard g produces exactly those (pfb_resample_sharded) and an all_to_all_v moves each
+                     piece to the rank that owns those output slots.  Data volume: every particle crosses
+                     NVLink at most once; with evenly weighted shards most pieces stay on their rank.
+  estimate           local sums + all_reduce(SUM)
+
+This is exact global systematic resampling -- identical to a single filter holding all N particles, up to the
+rounding of the shard-offset adds (oracle: pf_oracle.sharded_cdf / sharded_systematic_indices).  The
+distributed logic below only talks to a small backend object, so it also runs on CPU tensors over gloo
+(tests/test_sharded_gloo.py drives it with a numpy backend built from the oracle).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------------
+# host-side plan
+# ----------------------------------------------------------------------------------------------------
+def shard_offsets(totals):
+    """O_0 = 0, O_{g+1} = fl(O_g + T_g), in rank order (float64, identical on every rank)."""
+    offs = [0.0]
+    for t in totals:
+        offs.append(float(np.float64(offs[-1]) + np.float64(t)))
+    return offs
+
+
+def offspring_boundaries(offs, u0, n_out):
+    """B_g = #{j in [0, n_out) : fl((j + u0)/n_out) < fl(O_g / O_G)} for g = 0..G; offspring
+    [B_g, B_{g+1}) of the systematic comb are drawn from shard g."""
+    total = np.float64(offs[-1])
+    nn = np.float64(n_out)
+    uu = np.float64(u0)
+    B = []
+    for g in range(len(offs)):
+        E = np.float64(offs[g]) / total
+        j = int(math.floor(float(E * nn - uu)))
+        j = min(max(j, 0), n_out)
+        while j < n_out and (np.float64(j) + uu) / nn < E:
+            j += 1
+        while j > 0 and (np.float64(j - 1) + uu) / nn >= E:
+            j -= 1
+        B.append(j)
+    B[0] = 0
+    B[-1] = n_out
+    return B
+
+
+def exchange_plan(B, rank, world, n_loc):
+    """(send_counts, recv_counts) in particles: this rank generates offspring [B[rank], B[rank+1]) and
+    output slot j lives on rank j // n_loc; it receives from source s the overlap of [B[s], B[s+1]) with
+    its own slot range."""
+    def overlap(a0, a1, b0, b1):
+        return max(0, min(a1, b1) - max(a0, b0))
+
+    send = [overlap(B[rank], B[rank + 1], r * n_loc, (r + 1) * n_loc) for r in range(world)]
+    recv = [overlap(B[s], B[s + 1], rank * n_loc, (rank + 1) * n_loc) for s in range(world)]
+    return send, recv
+
+
+# ----------------------------------------------------------------------------------------------------
+# the distributed resampling step (backend-agnostic)
+# ----------------------------------------------------------------------------------------------------
+def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None):
+    """x: (n_loc, D) local particles (already predicted), logw: (n_loc,), local_max: 1-element tensor.
+    Returns the new local particles (n_loc, D).  `backend` provides
+        scan(logw, shift) -> (cdf (n_loc,), total: 1-element tensor)
+        offspring(cdf, offset, total, u0, j_begin, count, n_total, x) -> (count, D) tensor
+    Collectives: all_reduce(MAX) of 1 double, all_gather of 1 double per rank, all_to_all_v of particles."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_loc, D = x.shape
+    n_total = n_loc * world
+    gmax = local_max.clone()
+    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    cdf, total = backend.scan(logw, gmax)
+    totals = [torch.empty_like(total) for _ in range(world)]
+    dist.all_gather(totals, total, group=group)
+    tot_host = [float(t.cpu()) for t in totals]  # the split sizes must be known on the host
+    if not all(math.isfinite(t) for t in tot_host) or not sum(tot_host) > 0.0:
+        raise AssertionError("The sum of all weights should be greater than 0.")
+    offs = shard_offsets(tot_host)
+    B = offspring_boundaries(offs, u0, n_total)
+    send, recv = exchange_plan(B, rank, world, n_loc)
+    count = B[rank + 1] - B[rank]
+    mine = backend.offspring(cdf, offs[rank], offs[-1], u0, B[rank], count, n_total, x)
+    out = torch.empty((n_loc, D), dtype=x.dtype, device=x.device)
+    assert sum(send) == count and sum(recv) == n_loc
+    dist.all_to_all_single(out.view(-1), mine.reshape(-1), [r * D for r in recv], [s * D for s in send], group=group)
+    return out, {"offsets": offs, "boundaries": B, "send": send, "recv": recv}
+
+
+def sharded_sum(local_sums, group=None):
+    s = local_sums.clone()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return s
+
+
+# ----------------------------------------------------------------------------------------------------
+# CUDA backend + the user-facing filter
+# ----------------------------------------------------------------------------------------------------
+class CudaShardBackend:
+    def __init__(self, device):
+        from ._engine import engine
+
+        self.eng = engine(device)
+        self._cdf = None
+
+    def scan(self, logw, shift):
+        from . import _lib as L
+
+        eng = self.eng
+        if self._cdf is None or self._cdf.shape != logw.shape:
+            self._cdf = torch.empty_like(logw)
+        eng.stats[L.STAT_MAX:L.STAT_MAX + 1].copy_(shift)  # the global shift replaces the shard's own max
+        eng.scan(self._cdf, logw=logw, exact=True)
+        return self._cdf, eng.stats[L.STAT_TOTAL:L.STAT_TOTAL + 1].clone()
+
+    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x):
+        out = torch.empty((count, x.shape[1]), dtype=x.dtype, device=x.device)
+        if count > 0:
+            self.eng.resample_sharded(cdf, offset, total, u0, j_begin, count, n_total, x, out, x.shape[1])
+        return out
+
+
+class ShardedParticleFilter:
+    """A single filter over `n_particles_total` particles spread over the ranks of `group`.
+
+        pf = ShardedParticleFilter("euclid", 10**9, 4)            # every rank, after init_process_group("nccl")
+        pf.set_local_particles(x_local)                            # or pf.filter_state = prior (sampled per shard)
+        pf.predict_nonlinear(LinearTransition(F), GaussianDistribution(0, Q))
+        pf.update_identity(GaussianDistribution(0, R), z)          # global systematic resampling
+        est = pf.get_point_estimate()                              # identical on every rank
+
+    It wraps the single-GPU filter of the manifold for the local work (same kernels, same parameter blocks)."""
+
+    def __init__(self, manifold, n_particles_total, dim, group=None, dtype=torch.float64, device=None):
+        from . import filters as F
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if n_particles_total % self.world:
+            raise ValueError("n_particles_total must be divisible by the number of shards")
+        self.n_total = n_particles_total
+        self.n_loc = n_particles_total // self.world
+        cls = {"euclid": F.EuclideanParticleFilter, "torus": F.HypertoroidalParticleFilter,
+               "sphere": F.HypersphericalParticleFilter}[manifold]
+        self.manifold = manifold
+        self.local = cls(self.n_loc, dim, dtype=dtype, device=device)
+        self.local.lazy_predict = True
+        self.backend = CudaShardBackend(self.local._filter_state.device)
+        self.last_plan = None
+
+    # -- state -------------------------------------------------------------------------------------------
+    @property
+    def filter_state(self):
+        """the LOCAL shard as a Dirac distribution (weights 1/n_loc locally = 1/N globally after resampling)"""
+        return self.local.filter_state
+
+    @filter_state.setter
+    def filter_state(self, prior):
+        self.local.filter_state = prior  # every shard samples its own n_loc particles (seed differs per rank)
+
+    def set_local_particles(self, x):
+        self.local.filter_state.d = x
+
+    def gather_particles(self):
+        x = self.local.filter_state._records()
+        parts = [torch.empty_like(x) for _ in range(self.world)]
+        dist.all_gather(parts, x, group=self.group)
+        return torch.cat(parts, dim=0)
+
+    # -- predict / update ----------------------------------------------------------------------------------
+    def predict_identity(self, noise_distribution):
+        self.local.predict_identity(noise_distribution)
+
+    def predict_nonlinear(self, f, noise_distribution=None, function_is_vectorized=True, shift_instead_of_add=None):
+        self.local.predict_nonlinear(f, noise_distribution, function_is_vectorized, shift_instead_of_add)
+
+    def update_identity(self, meas_noise, measurement, shift_instead_of_add=True):
+        from . import registry as R
+
+        if not shift_instead_of_add:
+            raise NotImplementedError()
+        self.update_nonlinear_using_likelihood(meas_noise.set_mode(R._np(measurement)))
+
+    def update_nonlinear_using_likelihood(self, likelihood, measurement=None, u0=None):
+        import copy
+
+        from . import _lib as L
+        from . import random as prandom
+        from . import registry as R
+
+        loc = self.local
+        dist_obj = R.as_distribution(likelihood)
+        if measurement is not None:
+            dist_obj = copy.deepcopy(dist_obj).set_mode(R._np(measurement))
+        st = loc._filter_state
+        x = loc._scratch()
+        eng = loc._eng()
+        lp, keep = R.lik_params(dist_obj, x.shape[1], images_to_device=R.device_put(x.device))
+        if loc._pending is not None:
+            p, noise = loc._pending
+            loc._pending = None
+            try:
+                eng.predict_loglik(p, lp, x, x, noise, loc._logw)
+            except NotImplementedError:
+                eng.predict(p, x, x, noise)
+                eng.loglik(lp, x, loc._logw)
+        else:
+            eng.loglik(lp, x, loc._logw)
+        del keep
+        local_max = eng.stats[L.STAT_MAX:L.STAT_MAX + 1].clone()
+        if u0 is None:  # one comb offset for the whole filter: drawn on rank 0, broadcast
+            src = prandom.source()
+            t = src.uniforms((1,), x.device) if not src.fused else torch.rand(1, dtype=torch.float64, device=x.device)
+            dist.broadcast(t, src=0, group=self.group)
+            u0 = float(t.cpu())
+        new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group)
+        self.last_plan = plan
+        st._d = new.reshape(st._d.shape)
+        st._uniform = True
+        st._est_cache = None
+
+    # -- estimate ------------------------------------------------------------------------------------------
+    def get_point_estimate(self):
+        from . import _lib as L
+
+        loc = self.local
+        st = loc.filter_state
+        x = st._records()
+        D = x.shape[1]
+        if self.manifold == "torus":
+            s = loc._eng().moments(L.MOM_TRIG, x, D)[: 2 * D].clone()
+            s = sharded_sum(s, self.group).reshape(D, 2)
+            return torch.remainder(torch.atan2(s[:, 1], s[:, 0]), 2.0 * math.pi)
+        s = loc._eng().moments(L.MOM_MEAN, x, D)[:D].clone()
+        s = sharded_sum(s, self.group) / self.world  # local sums carry weights 1/n_loc
+        if self.manifold == "sphere":
+            return s / torch.linalg.norm(s)
+        return s
