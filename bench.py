@@ -41,6 +41,8 @@ WORKLOADS = {
     "s2": ("sphere", 3, 3, 10**8, "HypersphericalParticleFilter S^2, VMF noise + VMF likelihood, mean direction"),
     "r2": ("euclid", 2, 2, 10**4, "EuclideanParticleFilter R^2 constant velocity, Gaussian noise + likelihood"),
     "r4": ("euclid", 4, 4, 10**8, "EuclideanParticleFilter R^4 constant velocity, Gaussian noise + likelihood"),
+    # BASELINE.json configs[4]: ONE filter sharded over the GPUs, global systematic resampling (weak: 1.25e8 per GPU)
+    "r4s": ("euclid", 4, 4, 125_000_000, "ShardedParticleFilter R^4 constant velocity, particles sharded over the GPUs, global systematic resampling"),
 }
 
 
@@ -366,6 +368,100 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """configs[4]: one EuclideanParticleFilter over all ranks (pyrecest_b200.sharded), in-kernel Philox noise,
+    global systematic resampling over NCCL (all_reduce max, all_gather totals, all_to_all_v offspring)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200._engine import engine
+    from pyrecest_b200.sharded import ShardedParticleFilter
+
+    name = args.workload
+    manifold, D, E, n_default, desc = WORKLOADS[name]
+    n = args.particles or n_default
+    P = workload_params(name)
+    prior, trans, noise_dist, lik_dist = make_dists(name, P)
+    prandom.seed(1234 + rank)
+    eng = engine(dev)
+    pf = ShardedParticleFilter(manifold, n * world, D)
+    pf.filter_state = prior
+    z_pinned = torch.as_tensor(P["z"]).pin_memory()
+    rng = np.random.default_rng(7)
+
+    def step():
+        pf.predict_nonlinear(trans, noise_dist)
+        pf.update_nonlinear_using_likelihood(lik_dist.set_mode(z_pinned.numpy()), u0=float(rng.random()))
+        return pf.get_point_estimate()
+
+    for _ in range(args.warmup):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = eng.launches
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    start.record()
+    for _ in range(args.steps):
+        est = step()
+    end.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    gpu_launches = eng.launches - l0
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # e2e: the same call sequence with the estimate read back to the host every step
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.e2e_steps)):
+        est_host = step().cpu()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / max(1, args.e2e_steps)], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    assert bool(torch.isfinite(est_host).all())
+    if rank == 0:
+        ms_step = float(ms) / args.steps
+        peak, peak_src = peaks()
+        ab = sum(algorithmic_bytes(D, 0).values()) - 8  # in-kernel noise, one comb offset: no noise / uniform arrays
+        gbs = ab * n / (ms_step * 1e-3) / 1e9
+        cpu_val, cpu_s = run_cpu("r4", args.cpu_particles, 2, 1) if not args.no_cpu else (None, None)
+        print(json.dumps({
+            "metric": METRIC, "value": world * n / (ms_step * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "particles_total": n * world,
+                       "resampling": "systematic (global)", "scan": "sequential-exact per shard",
+                       "l2_policy": f"state {n * 8 * D / 1e6:.0f} MB per GPU, far larger than L2",
+                       "parallelism": f"particles sharded over {world} GPU(s); all_reduce(max) + all_gather(totals) + all_to_all_v(offspring) per step"},
+            "e2e": {"value": world * n / (float(e2e_ms) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(e2e_ms),
+                    "h2d_bytes_per_step": int(8 * D), "d2h_bytes_per_step": int(8 * D + 8 * world),
+                    "path": "public API: ShardedParticleFilter.predict_nonlinear + update + get_point_estimate"},
+            "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                         "frac": gbs / peak, "traffic": None, "peak_source": peak_src, "bytes_per_particle": ab},
+            "cpu_baseline": None if args.no_cpu else {"value": cpu_val, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+                                                      "sample": f"oracle port, unsharded R^4 step on {args.cpu_particles} particles"},
+        }))
+    dist.destroy_process_group()
+
+
 def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -407,7 +503,11 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
+        if args.workload == "r4s":
+            args.workload = "r4"
         run_reference(args)
+    elif args.workload == "r4s":
+        run_sharded(args)
     else:
         run_gpu(args)
 

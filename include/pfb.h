@@ -106,6 +106,8 @@ typedef struct {
   double kappa;              /* VM / VMF */
   double sigma;              /* WN_1D */
   const double* images_dev;  /* WN_MULTI: DEVICE table (n_images, 2D + 1): g_k = P o_k (D), h_k = o_k^T P o_k, o_k (D) */
+  const double* mu_batch_dev; /* *_batched only: DEVICE (n_runs, D) likelihood centres, one measurement per run
+                                 (NULL: `mu` for every run) */
 } pfb_lik_params;
 
 /* stats words written by the weighting / normalise kernels (device doubles) */
@@ -131,6 +133,7 @@ const char* pfb_last_error(void);
 /* scratch needed by any entry point for up to n particles (flags, tile states, partials).
  * The first pfb_workspace_bytes(0) bytes must be zeroed once (pfb_workspace_init). */
 int64_t pfb_workspace_bytes(int64_t n);
+int64_t pfb_workspace_bytes_batched(int64_t n_runs, int64_t run_len);  /* for the *_batched entry points */
 int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream);
 
 /* K(1) predict.  Replaces AbstractParticleFilter.predict_nonlinear
@@ -151,6 +154,31 @@ int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void
 int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
                        int64_t n, const void* x_in, void* x_out, const void* noise,
                        double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream);
+
+/* Batched Monte-Carlo runs (BASELINE.json configs[3]; pyrecest/evaluation/iterate_configs_and_runs.py:33-49 loops
+ * over runs sequentially): n_runs independent filters of run_len particles each in ONE launch.  Particles are
+ * (n_runs * run_len, D) run-major; per-particle scalars use a padded stride run_pad = ceil(run_len/2048)*2048
+ * (logw_pad / cdf_pad hold n_runs * run_pad doubles; padding carries weight 0) so that scan tiles never straddle
+ * runs.  The measurement of run r is lik->mu_batch_dev[r]; all other parameters are shared. */
+int pfb_loglik_batched(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n_runs, int64_t run_len,
+                       const void* x, double* logw_pad, double* stats, void* ws, int64_t ws_bytes, void* stream);
+int pfb_predict_loglik_batched(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
+                               int64_t n_runs, int64_t run_len, const void* x_in, void* x_out,
+                               const void* noise, double* logw_pad, double* stats, void* ws, int64_t ws_bytes,
+                               void* stream);
+/* per-run sequential-exact CDFs (each run's CDF equals numpy.cumsum of that run's weights, shifted by the
+ * run's own max); must follow one of the two calls above (mode | PFB_SCAN_TILE_STATS_VALID) */
+int pfb_scan_cdf_batched(int32_t mode, int64_t n_runs, int64_t run_len, const double* logw_pad,
+                         double* cdf_pad, double* stats, void* ws, int64_t ws_bytes, void* stream);
+/* per-run resampling: run r draws n_out_run offspring from its own CDF with uniforms u[r * n_out_run + k]
+ * (or in-kernel Philox draws when u == NULL; systematic: one u0 per run, u[r]); x_out is (n_runs*n_out_run, D) */
+int pfb_resample_batched(pfb_dtype dtype, int32_t dim, int64_t n_runs, int64_t run_len, int64_t n_out_run,
+                         const double* cdf_pad, const double* u, uint64_t rng_seed, uint64_t rng_offset,
+                         int32_t systematic, const void* x_in, void* x_out, int64_t* idx_out, void* ws,
+                         int64_t ws_bytes, void* stream);
+/* per-run moments: out is (n_runs, count) with the layout of pfb_moments per run; uniform weights 1/run_len */
+int pfb_moments_batched(int32_t kind, pfb_dtype dtype, int32_t dim, int64_t n_runs, int64_t run_len,
+                        const void* x, int32_t order, double* out, void* stream);
 
 /* K(3) max / log-sum-exp normalisation: stats <- (max, sum exp, sum exp^2, flags); if w_out
  * != NULL, w_out_i = exp(logw_i - max) / sumexp  (the posterior weights reweigh() returns). */

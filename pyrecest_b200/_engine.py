@@ -43,6 +43,9 @@ class Engine:
     def _ensure_ws(self, n):
         if n > self._ws_n:
             nbytes = int(self.lib.pfb_workspace_bytes(n))
+            if self._ws is not None and self._ws.numel() >= nbytes:  # e.g. grown by a batched call
+                self._ws_n = n
+                return _ptr(self._ws), self._ws.numel()
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             assert self._ws.data_ptr() % 256 == 0
             self._ws_n = n
@@ -131,6 +134,58 @@ class Engine:
     def rng_uniform(self, out, seed, offset):
         L.check(self.lib.pfb_rng_uniform(out.numel(), seed, offset, _ptr(out), _stream(self.device)))
         self.launches += 1
+
+    # -- batched runs (n_runs independent filters of run_len particles in one launch) ------------------------
+    def _ensure_ws_batched(self, n_runs, run_len):
+        need = int(self.lib.pfb_workspace_bytes_batched(n_runs, run_len))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_n = -1  # single-filter calls re-check their own size against numel below
+            self._tile_stats_key = None
+            L.check(self.lib.pfb_workspace_init(_ptr(self._ws), need, _stream(self.device)))
+        return _ptr(self._ws), self._ws.numel()
+
+    @staticmethod
+    def run_pad(run_len):
+        return (run_len + 2047) // 2048 * 2048
+
+    def loglik_batched(self, lik, x, n_runs, run_len, logw_pad):
+        ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        L.check(self.lib.pfb_loglik_batched(C.byref(lik), _DT[x.dtype], n_runs, run_len, _ptr(x), _ptr(logw_pad),
+                                            _ptr(self.stats), ws, wsb, _stream(self.device)))
+        self.launches += 1
+
+    def predict_loglik_batched(self, params, lik, x_in, x_out, noise, n_runs, run_len, logw_pad):
+        ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        L.check(self.lib.pfb_predict_loglik_batched(C.byref(params), C.byref(lik), _DT[x_in.dtype], n_runs, run_len,
+                                                    _ptr(x_in), _ptr(x_out), _ptr(noise), _ptr(logw_pad),
+                                                    _ptr(self.stats), ws, wsb, _stream(self.device)))
+        self.launches += 1
+
+    def scan_batched(self, logw_pad, cdf_pad, n_runs, run_len, exact=True):
+        ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        mode = (L.SCAN_SEQEXACT if exact else L.SCAN_FAST) | L.SCAN_TILE_STATS_VALID
+        L.check(self.lib.pfb_scan_cdf_batched(mode, n_runs, run_len, _ptr(logw_pad), _ptr(cdf_pad), _ptr(self.stats),
+                                              ws, wsb, _stream(self.device)))
+        self.launches += 2
+
+    def resample_batched(self, cdf_pad, x_in, x_out, n_runs, run_len, dim, u=None, seed=0, offset=0, systematic=False,
+                         idx_out=None, n_out_run=None):
+        ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        n_out_run = run_len if n_out_run is None else n_out_run
+        dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        L.check(self.lib.pfb_resample_batched(dt, dim, n_runs, run_len, n_out_run, _ptr(cdf_pad), _ptr(u), seed, offset,
+                                              1 if systematic else 0, _ptr(x_in), _ptr(x_out), _ptr(idx_out), ws, wsb,
+                                              _stream(self.device)))
+        self.launches += 2
+
+    def moments_batched(self, kind, x, n_runs, run_len, dim, order=1, out=None):
+        if out is None:
+            out = torch.empty((n_runs, dim * dim + 2 * dim + 2), dtype=torch.float64, device=self.device)
+        L.check(self.lib.pfb_moments_batched(kind, _DT[x.dtype], dim, n_runs, run_len, _ptr(x), order, _ptr(out),
+                                             _stream(self.device)))
+        self.launches += 1
+        return out
 
     def moments(self, kind, x, dim, w=None, order=1, center=None, out=None):
         n = x.shape[0]

@@ -59,7 +59,7 @@ class LikParams(C.Structure):
         ("kind", C.c_int32), ("dim", C.c_int32), ("n_images", C.c_int32), ("reserved", C.c_int32),
         ("mu", C.c_double * PFB_MAXD), ("W", C.c_double * (PFB_MAXD * PFB_MAXD)),
         ("logc", C.c_double), ("kappa", C.c_double), ("sigma", C.c_double),
-        ("images_dev", C.c_void_p),
+        ("images_dev", C.c_void_p), ("mu_batch_dev", C.c_void_p),
     ]
 
 
@@ -69,11 +69,19 @@ SIGNATURES = {
     "pfb_abi_version": (C.c_int, []),
     "pfb_last_error": (C.c_char_p, []),
     "pfb_workspace_bytes": (_i64, [_i64]),
+    "pfb_workspace_bytes_batched": (_i64, [_i64, _i64]),
     "pfb_workspace_init": (C.c_int, [_vp, _i64, _vp]),
     "pfb_predict": (C.c_int, [C.POINTER(PredictParams), C.c_int, _i64, _vp, _vp, _vp, _vp]),
     "pfb_loglik": (C.c_int, [C.POINTER(LikParams), C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pfb_predict_loglik": (C.c_int, [C.POINTER(PredictParams), C.POINTER(LikParams), C.c_int, _i64, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_loglik_batched": (C.c_int, [C.POINTER(LikParams), C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_predict_loglik_batched": (C.c_int, [C.POINTER(PredictParams), C.POINTER(LikParams), C.c_int, _i64, _i64, _vp,
+                                             _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_scan_cdf_batched": (C.c_int, [_i32, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pfb_resample_batched": (C.c_int, [C.c_int, _i32, _i64, _i64, _i64, _vp, _vp, C.c_uint64, C.c_uint64, _i32, _vp, _vp,
+                                       _vp, _vp, _i64, _vp]),
+    "pfb_moments_batched": (C.c_int, [_i32, C.c_int, _i32, _i64, _i64, _vp, _i32, _vp, _vp]),
     "pfb_normalize": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pfb_scan_cdf": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pfb_resample": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),

@@ -209,12 +209,13 @@ constexpr float kScreenCut = 92.0f; // the same cut for the fp32 screen, plus sl
 constexpr double kTermCut = 76.0;   // a term e^-38 below the best one cannot change the fp64 sum
 
 template <int D, int KIND>
-__device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const double (&x)[D],
+__device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const double* __restrict__ mu,
+                                             const double (&x)[D],
                                              const double* __restrict__ images /* smem or null */) {
   if constexpr (KIND == PFB_LIK_GAUSS) {
     double dev[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) dev[c] = x[c] - L.mu[c];
+    for (int c = 0; c < D; ++c) dev[c] = x[c] - mu[c];
     return L.logc - 0.5 * whitened_sq<D>(L, dev);
   } else if constexpr (KIND == PFB_LIK_WN_MULTI) {
     // xs = (xs + pi) % (2 pi) - pi; sum over the image table of mvn.pdf(xs + 2 pi k).
@@ -224,7 +225,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     // exact fp64 quadratic form and, if they can contribute more than e^-37, an exp.
     double dev[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kPi) - kPi) - L.mu[c];
+    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kPi) - kPi) - mu[c];
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
     double best = INFINITY, sum = 0.0;
@@ -288,7 +289,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
   } else if constexpr (KIND == PFB_LIK_WN_1D) {
     if (L.sigma > 10.0) return -log(kTwoPi);
     double xx = np_mod_2pi(x[0]);
-    xx -= L.mu[0];
+    xx -= mu[0];
     const double tmp = -1.0 / (2.0 * (L.sigma * L.sigma));
     double result = exp(xx * xx * tmp);
     for (int k = 1; k <= 1000; ++k) {
@@ -300,11 +301,11 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     }
     return log(result) + L.logc;  // logc = log(1/sqrt(2 pi)/sigma)
   } else if constexpr (KIND == PFB_LIK_VM) {
-    return fma(L.kappa, cos(x[0] - L.mu[0]), L.logc);  // logc = -log(2 pi I0(kappa))
+    return fma(L.kappa, cos(x[0] - mu[0]), L.logc);  // logc = -log(2 pi I0(kappa))
   } else {  // PFB_LIK_VMF
-    double dot = L.mu[0] * x[0];
+    double dot = mu[0] * x[0];
 #pragma unroll
-    for (int c = 1; c < D; ++c) dot = fma(L.mu[c], x[c], dot);
+    for (int c = 1; c < D; ++c) dot = fma(mu[c], x[c], dot);
     return fma(L.kappa, dot, L.logc);  // logc = log C(kappa)
   }
 }
@@ -380,20 +381,33 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
 // prefix its sequential-exact scan needs, without another pass over the log-weights.
 constexpr int kTileItems = kScanTile / kThreads;
 
+// runs of a batched launch: n_runs independent filters of run_len particles each; their log-weights
+// live at logw[run * run_pad + k] (run_pad = tpr * kScanTile, padded with -inf, so that no scan tile
+// straddles two runs).  A plain launch is one run with run_pad = run_len.
+struct Seg {
+  int64_t n_runs, run_len, run_pad, tpr;
+};
+inline Seg seg_single(int64_t n) { return Seg{1, n, n, (n + kScanTile - 1) / kScanTile}; }
+inline Seg seg_batched(int64_t n_runs, int64_t run_len) {
+  const int64_t tpr = (run_len + kScanTile - 1) / kScanTile;
+  return Seg{n_runs, run_len, tpr * kScanTile, tpr};
+}
+
 template <typename EVAL>
-__device__ __forceinline__ void weight_tiles(int64_t n, double* __restrict__ logw, double* stats, Workspace ws,
+__device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, double* stats, Workspace ws,
                                              double* red, EVAL eval) {
-  const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  const int64_t ntiles = sg.n_runs * sg.tpr;
   double gmax = -INFINITY, gnan = 0.0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kScanTile + threadIdx.x;
+    const int64_t run = tile / sg.tpr;
+    const int64_t lbase = (tile - run * sg.tpr) * kScanTile + threadIdx.x;
     double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
 #pragma unroll 1
     for (int k = 0; k < kTileItems; ++k) {
-      const int64_t i = base + (int64_t)k * kThreads;
-      if (i < n) {
-        const double v = eval(i);
-        logw[i] = v;
+      const int64_t local = lbase + (int64_t)k * kThreads;
+      if (local < sg.run_len) {
+        const double v = eval(run * sg.run_len + local, run);
+        logw[run * sg.run_pad + local] = v;
         if (v != v) {
           gnan = 1.0;
         } else if (v > m) {
@@ -402,6 +416,8 @@ __device__ __forceinline__ void weight_tiles(int64_t n, double* __restrict__ log
         } else if (v > -INFINITY) {
           sacc += exp(v - m);
         }
+      } else if (local < sg.run_pad) {
+        logw[run * sg.run_pad + local] = -INFINITY;  // padding of a batched run: weight 0
       }
     }
     const double bm = block_max(m, red);
@@ -414,7 +430,7 @@ __device__ __forceinline__ void weight_tiles(int64_t n, double* __restrict__ log
 }
 
 template <typename T, int D, int KIND>
-__global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int64_t n,
+__global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg sg,
                                                           const T* __restrict__ x,
                                                           const double* __restrict__ w_prev,
                                                           double* __restrict__ logw, double* stats,
@@ -422,10 +438,11 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int6
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles(n, logw, stats, ws, red, [&](int64_t i) {
+  weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double r[D];
     load_rec<T, D>(x, i, r);
-    double l = loglik_one<D, KIND>(L, r, images);
+    const double* mu = L.mu_batch_dev ? L.mu_batch_dev + run * D : L.mu;
+    double l = loglik_one<D, KIND>(L, mu, r, images);
     if (w_prev != nullptr) l += log(w_prev[i]);
     return l;
   });
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, int6
 
 template <typename T, int D, int MODE, int KIND>
 __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_params p,
-                                                                  pfb_lik_params L, int64_t n,
+                                                                  pfb_lik_params L, Seg sg,
                                                                   const T* __restrict__ x_in, T* x_out,
                                                                   const T* __restrict__ noise,
                                                                   double* __restrict__ logw,
@@ -441,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles(n, logw, stats, ws, red, [&](int64_t i) {
+  weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double out[D];
     predict_one<T, D, MODE>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
@@ -450,7 +467,8 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
 #pragma unroll
       for (int c = 0; c < D; ++c) out[c] = (double)(float)out[c];
     }
-    return loglik_one<D, KIND>(L, out, images);
+    const double* mu = L.mu_batch_dev ? L.mu_batch_dev + run * D : L.mu;
+    return loglik_one<D, KIND>(L, mu, out, images);
   });
 }
 
@@ -531,47 +549,48 @@ extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t
   return PFB_OK;
 }
 
-extern "C" int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void* x,
-                          const double* w_prev, double* logw, double* stats, void* ws, int64_t ws_bytes,
-                          void* stream) {
+namespace pfb {
+static int tile_grid_seg(const Seg& sg) { return tile_grid(sg.n_runs * sg.tpr * (int64_t)kScanTile); }
+
+static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const void* x, const double* w_prev,
+                       double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream) {
   if (!lik) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
   int rc = check_lik(lik, lik->dim);
   if (rc) return rc;
-  if (n <= 0) return PFB_OK;
+  if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
   if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, n, &W);
+  rc = carve_workspace(ws, ws_bytes, sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = tile_grid(n);
+  const int grid = tile_grid_seg(sg);
   const size_t sm = lik_smem(lik);
   PFB_DISPATCH_DTYPE(dtype, {
     if (lik->kind == PFB_LIK_WN_1D) {
-      loglik_kernel<T, 1, PFB_LIK_WN_1D><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W);
+      loglik_kernel<T, 1, PFB_LIK_WN_1D><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);
     } else if (lik->kind == PFB_LIK_VM) {
-      loglik_kernel<T, 1, PFB_LIK_VM><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W);
+      loglik_kernel<T, 1, PFB_LIK_VM><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);
     } else {
-      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND><<<grid, kThreads, sm, st>>>(*lik, n, (const T*)x, w_prev, logw, stats, W))));
+      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W))));
     }
   });
   PFB_LAUNCH_OK("loglik_kernel");
   return PFB_OK;
 }
 
-namespace pfb {
 // Only manifold-consistent (mode, likelihood) pairs are instantiated:
 //   Euclidean <-> gauss;  torus <-> wn_multi (any D), wn_1d / vm (D = 1);  sphere <-> vmf.
 template <typename T, int D, int MODE, int KIND>
-static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* lik, int64_t n, const void* x_in,
+static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* lik, Seg sg, const void* x_in,
                             void* x_out, const void* noise, double* logw, double* stats, Workspace W,
                             cudaStream_t st) {
-  predict_loglik_kernel<T, D, MODE, KIND><<<tile_grid(n), kThreads, lik_smem(lik), st>>>(
-      *p, *lik, n, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  predict_loglik_kernel<T, D, MODE, KIND><<<tile_grid_seg(sg), kThreads, lik_smem(lik), st>>>(
+      *p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
   return PFB_OK;
 }
 
 template <typename T, int D, int MODE>
-static int launch_fused(const pfb_predict_params* p, const pfb_lik_params* lik, int64_t n, const void* x_in,
+static int launch_fused(const pfb_predict_params* p, const pfb_lik_params* lik, Seg n, const void* x_in,
                         void* x_out, const void* noise, double* logw, double* stats, Workspace W,
                         cudaStream_t st) {
   constexpr bool torus = (MODE == PFB_PRED_TORUS_SHIFT || MODE == PFB_PRED_TORUS_ADD);
@@ -592,31 +611,59 @@ static int launch_fused(const pfb_predict_params* p, const pfb_lik_params* lik, 
   set_error("likelihood kind %d is not defined on the manifold of predict mode %d (dim %d)", lik->kind, MODE, D);
   return PFB_ERR_UNSUPPORTED;
 }
-}  // namespace pfb
 
-extern "C" int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
-                                  int64_t n, const void* x_in, void* x_out, const void* noise, double* logw,
-                                  double* stats, void* ws, int64_t ws_bytes, void* stream) {
+static int predict_loglik_impl(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype, Seg sg,
+                               const void* x_in, void* x_out, const void* noise, double* logw, double* stats,
+                               void* ws, int64_t ws_bytes, void* stream) {
   int rc = check_predict(p);
   if (rc) return rc;
   rc = check_lik(lik, p->dim);
   if (rc) return rc;
-  if (n <= 0) return PFB_OK;
+  if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
   if (!x_in || !x_out || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, n, &W);
+  rc = carve_workspace(ws, ws_bytes, sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PFB_DISPATCH_DTYPE(dtype, {
     if (p->mode == PFB_PRED_SPHERE_VMF) {
-      rc = launch_fused<T, 3, PFB_PRED_SPHERE_VMF>(p, lik, n, x_in, x_out, noise, logw, stats, W, st);
+      rc = launch_fused<T, 3, PFB_PRED_SPHERE_VMF>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st);
     } else {
-      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (rc = launch_fused<T, D, MODE>(p, lik, n, x_in, x_out, noise, logw, stats, W, st))));
+      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (rc = launch_fused<T, D, MODE>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st))));
     }
   });
   if (rc) return rc;
   PFB_LAUNCH_OK("predict_loglik_kernel");
   return PFB_OK;
+}
+}  // namespace pfb
+
+extern "C" int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void* x,
+                          const double* w_prev, double* logw, double* stats, void* ws, int64_t ws_bytes,
+                          void* stream) {
+  if (lik && lik->mu_batch_dev) { set_error("mu_batch_dev is only valid with the *_batched entry points"); return PFB_ERR_INVALID; }
+  return loglik_impl(lik, dtype, seg_single(n), x, w_prev, logw, stats, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
+                                  int64_t n, const void* x_in, void* x_out, const void* noise, double* logw,
+                                  double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  if (lik && lik->mu_batch_dev) { set_error("mu_batch_dev is only valid with the *_batched entry points"); return PFB_ERR_INVALID; }
+  return predict_loglik_impl(p, lik, dtype, seg_single(n), x_in, x_out, noise, logw, stats, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_loglik_batched(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n_runs, int64_t run_len,
+                                  const void* x, double* logw_pad, double* stats, void* ws, int64_t ws_bytes,
+                                  void* stream) {
+  return loglik_impl(lik, dtype, seg_batched(n_runs, run_len), x, nullptr, logw_pad, stats, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_predict_loglik_batched(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
+                                          int64_t n_runs, int64_t run_len, const void* x_in, void* x_out,
+                                          const void* noise, double* logw_pad, double* stats, void* ws,
+                                          int64_t ws_bytes, void* stream) {
+  return predict_loglik_impl(p, lik, dtype, seg_batched(n_runs, run_len), x_in, x_out, noise, logw_pad, stats, ws,
+                             ws_bytes, stream);
 }
 
 extern "C" int pfb_wrap_2pi(pfb_dtype dtype, int64_t count, const void* x_in, void* x_out, void* stream) {

@@ -108,23 +108,29 @@ __device__ __forceinline__ int64_t search_range(const double* __restrict__ cdf, 
 // element i owns the buckets (b_{i-1}, b_i].  The CDF is streamed once; long runs (a heavy particle
 // spans many buckets) are filled by the whole warp.
 __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double* __restrict__ cdf,
-                                                         const double* __restrict__ total_ptr,
-                                                         int32_t* __restrict__ guide, int64_t M) {
-  const double total = *total_ptr;
+                                                         int32_t* __restrict__ guide, int64_t M,
+                                                         int64_t run_pad) {
+  // n: elements over all runs (padded); run r occupies cdf[r run_pad, (r+1) run_pad) and guide row r (M + 2 ints).
+  // run_pad is a multiple of 32 when there is more than one run, so a warp never straddles two runs.
   const double dM = (double)M;
   const int lane = threadIdx.x & 31;
   const int64_t nround = (n + 31) & ~(int64_t)31;  // whole warps stay converged for the shuffles
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const int64_t run = (i < n ? i : n - 1) / run_pad;
+    const int64_t k = i - run * run_pad;  // position inside the run
+    const int64_t last = (run + 1) * run_pad - 1;
+    const double total = __ldg(cdf + (last < n ? last : n - 1));
+    int32_t* g = guide + run * (M + 2);
     int64_t bi = M;  // past-the-end elements own nothing
     if (i < n) bi = (int64_t)(__ddiv_rn(__ldg(cdf + i), total) * dM);
     int64_t bprev = __shfl_up_sync(0xffffffffu, bi, 1);
-    if (lane == 0) bprev = (i == 0) ? -1 : (i <= n ? (int64_t)(__ddiv_rn(__ldg(cdf + i - 1), total) * dM) : M);
+    if (lane == 0 || k == 0) bprev = (k == 0) ? -1 : (i <= n ? (int64_t)(__ddiv_rn(__ldg(cdf + i - 1), total) * dM) : M);
     if (i >= n) bprev = bi;  // nothing to write
     int64_t len = bi - bprev;
-    // short runs: the owner writes them; long runs: warp-cooperative
+    // short runs of buckets: the owner writes them; long ones: warp-cooperative
     if (len > 0 && len <= 4) {
-      for (int64_t b = bprev + 1; b <= bi; ++b) guide[b] = (int32_t)i;
+      for (int64_t b = bprev + 1; b <= bi; ++b) g[b] = (int32_t)k;
     }
     unsigned longmask = __ballot_sync(0xffffffffu, len > 4);
     while (longmask) {
@@ -132,8 +138,10 @@ __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double
       longmask &= longmask - 1;
       const int64_t b0 = __shfl_sync(0xffffffffu, bprev, src) + 1;
       const int64_t b1 = __shfl_sync(0xffffffffu, bi, src);
-      const int32_t val = (int32_t)__shfl_sync(0xffffffffu, i, src);
-      for (int64_t b = b0 + lane; b <= b1; b += 32) guide[b] = val;
+      const int32_t val = (int32_t)__shfl_sync(0xffffffffu, k, src);
+      const int64_t grow = __shfl_sync(0xffffffffu, run, src);
+      int32_t* gs = guide + grow * (M + 2);
+      for (int64_t b = b0 + lane; b <= b1; b += 32) gs[b] = val;
     }
   }
 }
@@ -146,44 +154,55 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
                                                             const T* __restrict__ x_in, T* __restrict__ x_out,
                                                             int64_t* __restrict__ idx_out, double* est_out,
                                                             Workspace ws, const int32_t* __restrict__ guide,
-                                                            int64_t M, RngKey key) {
+                                                            int64_t M, RngKey key, int64_t run_pad, int64_t run_len,
+                                                            int64_t n_out_run) {
+  // runs: output j belongs to run j / n_out_run and is drawn from cdf[run run_pad, +run_len) / x_in[run run_len, ..)
+  // (a plain call is one run: run_pad = run_len = n, n_out_run = n_out)
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
-  const double total = *total_ptr;
+  (void)total_ptr; (void)n;
   const bool use_rng = (u == nullptr);
-  double u0 = 0.0;
-  if (systematic) {
-    if (use_rng) { const uint4 r = rng_block(key, 0ULL, 7u); u0 = u53(r.x, r.y); }
-    else u0 = u[0];
-  }
-  const double dn = (double)n_out;
+  const double dn = (double)n_out_run;
   const double dM = (double)M;
   double acc[NE];
 #pragma unroll
   for (int k = 0; k < NE; ++k) acc[k] = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n_out; j0 += stride * kBatch) {
-    double uj[kBatch];
+    double uj[kBatch], total[kBatch];
     int32_t lo[kBatch], hi[kBatch];
+    int64_t run[kBatch];
     bool live[kBatch];
     // phase 1: uniforms, then the guide entries
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       const int64_t j = j0 + q * stride;
       live[q] = j < n_out;
-      if (!live[q]) uj[q] = 0.0;
-      else if (systematic) uj[q] = __ddiv_rn(__dadd_rn((double)j, u0), dn);
-      else if (use_rng) { const uint4 r = rng_block(key, (uint64_t)j, 7u); uj[q] = u53(r.x, r.y); }
-      else uj[q] = __ldg(u + j);
+      run[q] = live[q] ? j / n_out_run : 0;
+      total[q] = __ldg(cdf + (run[q] + 1) * run_pad - 1);
+      if (!live[q]) {
+        uj[q] = 0.0;
+      } else if (systematic) {
+        double u0;
+        if (use_rng) { const uint4 r = rng_block(key, (uint64_t)run[q], 7u); u0 = u53(r.x, r.y); }
+        else u0 = __ldg(u + run[q]);
+        uj[q] = __ddiv_rn(__dadd_rn((double)(j - run[q] * n_out_run), u0), dn);
+      } else if (use_rng) {
+        const uint4 r = rng_block(key, (uint64_t)j, 7u);
+        uj[q] = u53(r.x, r.y);
+      } else {
+        uj[q] = __ldg(u + j);
+      }
     }
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       if (uj[q] >= 1.0) {  // only a rounded-up systematic point can get here
-        lo[q] = hi[q] = (int32_t)(n - 1);
+        lo[q] = hi[q] = (int32_t)(run_len - 1);
       } else {
         const int64_t b = (int64_t)(uj[q] * dM);  // exact
-        lo[q] = __ldg(guide + b);
-        hi[q] = __ldg(guide + b + 1);
+        const int32_t* g = guide + run[q] * (M + 2);
+        lo[q] = __ldg(g + b);
+        hi[q] = __ldg(g + b + 1);
       }
     }
     // phase 2: the candidate windows, all loads independent
@@ -193,25 +212,26 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
 #pragma unroll
       for (int k = 0; k < kWin; ++k) {
         const int32_t i = lo[q] + k;
-        win[q][k] = (i < hi[q]) ? __ldg(cdf + i) : INFINITY;
+        win[q][k] = (i < hi[q]) ? __ldg(cdf + run[q] * run_pad + i) : INFINITY;
       }
     }
     // phase 3: count, with the binary search only for long windows
     int64_t idx[kBatch];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
-      const double t = uj[q] * total;
+      const double t = uj[q] * total[q];
       const double tl = t * (1.0 - 2.220446049250313e-16);
       const double th = t * (1.0 + 4.440892098500626e-16);
       int cnt = 0;
 #pragma unroll
       for (int k = 0; k < kWin; ++k) {
         // windows are sorted: once an entry is > u the rest are too; counting all is branch-free
-        if (win[q][k] != INFINITY && cdf_le(win[q][k], total, uj[q], tl, th)) cnt = k + 1;
+        if (win[q][k] != INFINITY && cdf_le(win[q][k], total[q], uj[q], tl, th)) cnt = k + 1;
       }
       int64_t r = (int64_t)lo[q] + cnt;
-      if (cnt == kWin && hi[q] - lo[q] > kWin) r = search_range<true>(cdf, (int64_t)lo[q] + kWin, (int64_t)hi[q], total, uj[q]);
-      if (r > n - 1) r = n - 1;
+      if (cnt == kWin && hi[q] - lo[q] > kWin)
+        r = search_range<true>(cdf + run[q] * run_pad, (int64_t)lo[q] + kWin, (int64_t)hi[q], total[q], uj[q]);
+      if (r > run_len - 1) r = run_len - 1;
       idx[q] = r;
     }
     // phase 4: gather, store, estimate
@@ -219,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
       double r[kBatch][D];
 #pragma unroll
       for (int q = 0; q < kBatch; ++q)
-        if (live[q]) load_rec<T, D>(x_in, idx[q], r[q]);
+        if (live[q]) load_rec<T, D>(x_in, run[q] * run_len + idx[q], r[q]);
 #pragma unroll
       for (int q = 0; q < kBatch; ++q) {
         if (!live[q]) continue;
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
       block_sum<NE>(t, red);
       if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < NE; ++k) est_out[k] = t[k] / dn;
+        for (int k = 0; k < NE; ++k) est_out[k] = t[k] / (double)n_out;
       }
     }
   }
@@ -360,20 +380,92 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(int64_t n, const T* _
   }
 }
 
+// per-run moments for batched runs: one CTA per run (deterministic), uniform weights 1/run_len
+template <typename T, int D, int KIND>
+__global__ void __launch_bounds__(kThreads) moments_batched_kernel(int64_t n_runs, int64_t run_len,
+                                                                   const T* __restrict__ x, int order,
+                                                                   double* __restrict__ out) {
+  constexpr int NE = MomentCount<D, KIND>::value;
+  __shared__ double red[NE * 32];
+  const double wu = 1.0 / (double)run_len;
+  const double ord = (double)order;
+  for (int64_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    double acc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+    for (int64_t i = threadIdx.x; i < run_len; i += blockDim.x) {
+      double r[D];
+      load_rec<T, D>(x, run * run_len + i, r);
+      if constexpr (KIND == PFB_MOM_MEAN) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fma(wu, r[c], acc[c]);
+      } else if constexpr (KIND == PFB_MOM_TRIG) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double sn, cs;
+          sincos(ord * r[c], &sn, &cs);
+          acc[2 * c] = fma(wu, cs, acc[2 * c]);
+          acc[2 * c + 1] = fma(wu, sn, acc[2 * c + 1]);
+        }
+      } else {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+#pragma unroll
+          for (int b = a; b < D; ++b) { acc[k] = fma(r[a] * wu, r[b], acc[k]); ++k; }
+        }
+      }
+      acc[NE - 1] += wu;
+    }
+    block_sum<NE>(acc, red);
+    if (threadIdx.x == 0) {
+      double* o = out + run * (D * D + 2 * D + 2);
+      if constexpr (KIND == PFB_MOM_MEAN || KIND == PFB_MOM_TRIG) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) o[k] = acc[k];
+      } else {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+#pragma unroll
+          for (int b = a; b < D; ++b) { o[a * D + b] = acc[k]; o[b * D + a] = acc[k]; ++k; }
+        }
+        o[D * D] = acc[NE - 1];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int D>
+static int launch_moments_batched(int kind, int64_t n_runs, int64_t run_len, const void* x, int order, double* out,
+                                  cudaStream_t st) {
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(n_runs < cap ? n_runs : cap);
+  switch (kind) {
+    case PFB_MOM_MEAN: moments_batched_kernel<T, D, PFB_MOM_MEAN><<<grid, kThreads, 0, st>>>(n_runs, run_len, (const T*)x, order, out); break;
+    case PFB_MOM_TRIG: moments_batched_kernel<T, D, PFB_MOM_TRIG><<<grid, kThreads, 0, st>>>(n_runs, run_len, (const T*)x, order, out); break;
+    case PFB_MOM_SCATTER: moments_batched_kernel<T, D, PFB_MOM_SCATTER><<<grid, kThreads, 0, st>>>(n_runs, run_len, (const T*)x, order, out); break;
+    default: set_error("bad moment kind %d for a batched call", kind); return PFB_ERR_INVALID;
+  }
+  return PFB_OK;
+}
+
 template <typename T, int D>
 static int launch_resample(int64_t n, int64_t n_out, const double* cdf, const double* u, int systematic,
                            const double* stats, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
-                           double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M, RngKey key) {
+                           double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M, RngKey key,
+                           int64_t run_pad, int64_t run_len, int64_t n_out_run) {
   const int grid = stream_grid(n_out);
   switch (est_kind) {
     case PFB_EST_NONE:
-      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
+      resample_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key, run_pad, run_len, n_out_run);
       break;
     case PFB_EST_SUM:
-      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
+      resample_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key, run_pad, run_len, n_out_run);
       break;
     case PFB_EST_TRIG:
-      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key);
+      resample_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, systematic, stats, (const T*)x_in, (T*)x_out, idx_out, est_out, W, guide, M, key, run_pad, run_len, n_out_run);
       break;
     default:
       set_error("bad est_kind %d", est_kind);
@@ -432,9 +524,9 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   cudaStream_t st = (cudaStream_t)stream;
   const double* stats_total = cdf + (n - 1);
   const int64_t M = W.guide_buckets;
-  guide_kernel<<<stream_grid(n, 4), kThreads, 0, st>>>(n, cdf, stats_total, W.guide, M);
+  guide_kernel<<<stream_grid(n, 4), kThreads, 0, st>>>(n, cdf, W.guide, M, n);
   PFB_LAUNCH_OK("guide_kernel");
-  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M, key))));
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M, key, n, n, n_out))));
   if (rc) return rc;
   PFB_LAUNCH_OK("resample_kernel");
   return PFB_OK;
@@ -490,6 +582,54 @@ extern "C" int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t
                                 int64_t ws_bytes, void* stream) {
   return resample_impl(dtype, dim, n, n_out, cdf, nullptr, RngKey{rng_seed, rng_offset}, systematic, x_in, x_out,
                        idx_out, est_kind, est_out, ws, ws_bytes, stream);
+}
+
+extern "C" int64_t pfb_workspace_bytes_batched(int64_t n_runs, int64_t run_len) {
+  if (n_runs < 1) n_runs = 1;
+  if (run_len < 0) run_len = 0;
+  const int64_t n_pad = n_runs * scan_tiles(run_len) * kScanTile;
+  int64_t b = guide_offset(n_pad) + n_runs * (guide_buckets(run_len) + 2) * (int64_t)sizeof(int32_t);
+  b = (b + 255) & ~(int64_t)255;
+  const int64_t single = pfb_workspace_bytes(n_pad);  // the weighting / scan calls size themselves on n_pad
+  return b > single ? b : single;
+}
+
+extern "C" int pfb_resample_batched(pfb_dtype dtype, int32_t dim, int64_t n_runs, int64_t run_len, int64_t n_out_run,
+                                    const double* cdf_pad, const double* u, uint64_t rng_seed, uint64_t rng_offset,
+                                    int32_t systematic, const void* x_in, void* x_out, int64_t* idx_out, void* ws,
+                                    int64_t ws_bytes, void* stream) {
+  if (n_runs <= 0 || run_len <= 0 || n_out_run <= 0) return PFB_OK;
+  if (!cdf_pad) { set_error("NULL cdf"); return PFB_ERR_INVALID; }
+  if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
+  if (x_in && x_in == x_out) { set_error("resampling cannot run in place"); return PFB_ERR_INVALID; }
+  const int64_t run_pad = scan_tiles(run_len) * kScanTile;
+  const int64_t n_pad = n_runs * run_pad;
+  if (ws_bytes < pfb_workspace_bytes_batched(n_runs, run_len)) { set_error("workspace too small for %lld runs of %lld", (long long)n_runs, (long long)run_len); return PFB_ERR_WORKSPACE; }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  int32_t* guide = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + guide_offset(n_pad));
+  const int64_t M = guide_buckets(run_len);
+  cudaStream_t st = (cudaStream_t)stream;
+  guide_kernel<<<stream_grid(n_pad, 4), kThreads, 0, st>>>(n_pad, cdf_pad, guide, M, run_pad);
+  PFB_LAUNCH_OK("guide_kernel");
+  const int64_t n_out = n_runs * n_out_run;
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n_pad, n_out, cdf_pad, u, systematic, cdf_pad, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st, guide, M, RngKey{rng_seed, rng_offset}, run_pad, run_len, n_out_run))));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("resample_kernel");
+  return PFB_OK;
+}
+
+extern "C" int pfb_moments_batched(int32_t kind, pfb_dtype dtype, int32_t dim, int64_t n_runs, int64_t run_len,
+                                   const void* x, int32_t order, double* out, void* stream) {
+  if (n_runs <= 0 || run_len <= 0) return PFB_OK;
+  if (!x || !out) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  int rc = PFB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_moments_batched<T, D>(kind, n_runs, run_len, x, order, out, st))));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("moments_batched_kernel");
+  return PFB_OK;
 }
 
 extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, double cdf_offset,

@@ -257,8 +257,8 @@ struct LookbackSmem {
   int wfirst[kThreads / 32], wexp[kThreads / 32];
 };
 
-__device__ __forceinline__ double lookback_block(const TileState& ts, int64_t tile, unsigned int* err,
-                                                 LookbackSmem& sm) {
+__device__ __forceinline__ double lookback_block(const TileState& ts, int64_t tile, int64_t run_first,
+                                                 unsigned int* err, LookbackSmem& sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PMap composed; composed.e = 0; composed.o = 0;  // maps of the tiles after the inclusive one, in order
   int e_maps = 0;
@@ -267,14 +267,14 @@ __device__ __forceinline__ double lookback_block(const TileState& ts, int64_t ti
   int64_t j0 = tile - 1;
   while (true) {
     const int64_t j = j0 - threadIdx.x;
-    unsigned long long f = 2;  // tiles before 0 behave like an inclusive 0
-    if (j >= 0) {
+    unsigned long long f = 2;  // tiles before the start of this run behave like an inclusive 0
+    if (j >= run_first) {
       do { f = ld_acquire_u64(ts.flagB + j); } while ((f & 3ULL) == 0);
     }
     const int st = (int)(f & 3ULL);
     PMap m; m.e = 0; m.o = 0;
     double ci = 0.0;
-    if (j >= 0) {
+    if (j >= run_first) {
       if (st == 2) ci = ld_relaxed_f64(ts.inclB + j);
       else { m.e = ld_relaxed_s64(ts.aggE + j); m.o = ld_relaxed_s64(ts.aggO + j); }
     }
@@ -343,7 +343,46 @@ __global__ void __launch_bounds__(kThreads) tile_stats_kernel(int64_t n, const d
   }
 }
 
-// one CTA: aprefix[t] = sum_{s<t} tsum[s] exp(tmax[s] - M), t = 0 .. ntiles
+// Segmented variant for batched runs: one warp per run.  The shift of a run is the max over its tiles.
+__global__ void __launch_bounds__(kThreads) tile_prefix_runs_kernel(TileState ts, int64_t n_runs, int tpr,
+                                                                    int from_log) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t run = warp_global; run < n_runs; run += nwarps) {
+    const int64_t t0 = run * tpr;
+    double M = 0.0;
+    if (from_log) {
+      M = -INFINITY;
+      for (int t = lane; t < tpr; t += 32) M = fmax(M, ts.tmax[t0 + t]);
+      M = warp_max(M);
+    }
+    double carry = 0.0;
+    for (int base = 0; base < tpr; base += 32) {
+      const int t = base + lane;
+      double v = 0.0;
+      if (t < tpr) {
+        const double tm = ts.tmax[t0 + t];
+        const double sc = from_log ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0;
+        v = ts.tsum[t0 + t] * sc;
+      }
+      double inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+      }
+      if (t < tpr) {
+        ts.aprefix[t0 + t] = carry + (inc - v);
+        ts.tsum[t0 + t] = v;
+        ts.tmax[t0 + t] = M;
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+}
+
+// one CTA: aprefix[t] = sum_{s<t} tsum[s] exp(tmax[s] - M), t = 0 .. ntiles - 1
 __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t ntiles,
                                                            const double* __restrict__ max_ptr) {
   __shared__ double s_warp[33];
@@ -382,8 +421,11 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
     __syncthreads();
     const double carry = s_carry;
     const double excl = carry + s_warp[warp] + (inc - v);
-    if (t < ntiles) ts.aprefix[t] = excl;
-    if (t == ntiles - 1) ts.aprefix[ntiles] = excl + v;
+    if (t < ntiles) {
+      ts.aprefix[t] = excl;
+      ts.tsum[t] = v;    // tile sum relative to the shift the scan will use
+      ts.tmax[t] = M;    // ... which is that shift
+    }
     __syncthreads();
     if (threadIdx.x == 0) s_carry = carry + s_warp[32];
     __syncthreads();
@@ -393,7 +435,7 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
 template <bool EXACT, bool FROM_LOG>
 __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double* __restrict__ in,
                                                         double* __restrict__ cdf, double* stats,
-                                                        TileState ts, int64_t ntiles, double margin,
+                                                        TileState ts, int64_t ntiles, int64_t tpr, double margin,
                                                         unsigned int* err) {
   __shared__ double s_dbl[40];
   __shared__ long long s_ll[72];
@@ -403,13 +445,15 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
   __shared__ LookbackSmem s_lb;
   __shared__ int s_safe, s_e;
 
-  const double shift = FROM_LOG ? stats[PFB_STAT_MAX] : 0.0;
   while (true) {
     __syncthreads();
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ts.ticket, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= ntiles) break;
+    const int64_t lt = tile % tpr;           // tile index inside its run (tpr = ntiles: a single run)
+    const int64_t run_first = tile - lt;
+    const double shift = FROM_LOG ? ts.tmax[tile] : 0.0;  // left there by the tile-prefix kernel
     const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
 
     double p[kItems];
@@ -433,9 +477,9 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
       if (EXACT) {
         // certain binade?  every running sum inside the tile lies in [lo, hi]
         const double lo = a0 * (1.0 - margin);
-        const double hi = ts.aprefix[tile + 1] * (1.0 + margin);
+        const double hi = (a0 + ts.tsum[tile]) * (1.0 + margin);
         int safe = 0, e = 0;
-        if (tile > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
+        if (lt > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
           const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
           const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
           if (elo == ehi) { safe = 1; e = elo; }
@@ -469,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
         st_relaxed_s64(ts.aggO + tile, tot.o);
         st_release_u64(ts.flagB + tile, 1ULL | ((unsigned long long)(s_e + 2048) << 8));
       }
-      const double cin = lookback_block(ts, tile, err, s_lb);
+      const double cin = lookback_block(ts, tile, run_first, err, s_lb);
       if (threadIdx.x == 0) {
         bool ok0;
         const long long S0 = int_of(cin, s_e, &ok0);
@@ -493,7 +537,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double*
       // one binade the tile is an integer scan (as in a safe tile); the first element whose sum
       // reaches 2^53 is the crossing: it gets one real fp64 add, and the walk restarts behind it.
       double cin0 = 0.0;
-      if (tile > 0) cin0 = lookback_block(ts, tile, err, s_lb);
+      if (lt > 0) cin0 = lookback_block(ts, tile, run_first, err, s_lb);
       const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
       const int tb = threadIdx.x * kItems;
       double cur = cin0;
@@ -609,39 +653,36 @@ extern "C" int pfb_normalize(int64_t n, const double* logw, double* w_out, doubl
   return PFB_OK;
 }
 
-extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const double* logw, double* cdf,
-                            double* stats, void* ws, int64_t ws_bytes, void* stream) {
-  if (n <= 0) return PFB_OK;
-  if ((w == nullptr) == (logw == nullptr)) { set_error("exactly one of w / logw must be given"); return PFB_ERR_INVALID; }
-  if (!cdf || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
-  const bool have_tile_stats = (mode & PFB_SCAN_TILE_STATS_VALID) != 0;
-  mode &= ~PFB_SCAN_TILE_STATS_VALID;
-  if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
-  const double* in = w ? w : logw;
-  if (((uintptr_t)in & 15) || ((uintptr_t)cdf & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
-  Workspace W;
-  int rc = carve_workspace(ws, ws_bytes, n, &W);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t ntiles = scan_tiles(n);
+namespace pfb {
+// n: elements in the (possibly padded) array; n_runs runs of tpr tiles each (n_runs = 1: tpr = all tiles)
+static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, double* cdf, double* stats,
+                     Workspace W, int64_t n_runs, int64_t tpr, bool have_tile_stats, cudaStream_t st) {
+  const int64_t ntiles = n_runs * tpr;
   unsigned int* ticket = W.counters + 1;
   unsigned int* err = W.counters + 2;
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
-  const bool from_log = (logw != nullptr);
   PFB_CUDA_OK(cudaMemsetAsync(ts.flagB, 0, (size_t)ntiles * 8, st));
   PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
   // 1. per-tile sums, unless the weighting kernel already left them in the workspace
-  if (!have_tile_stats || !from_log) {
+  if (!have_tile_stats) {
     const int g = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
     if (from_log) tile_stats_kernel<true><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
     else tile_stats_kernel<false><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
     PFB_LAUNCH_OK("tile_stats_kernel");
   }
-  // 2. approximate prefix of the tile sums (one CTA)
-  tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr);
-  PFB_LAUNCH_OK("tile_prefix_kernel");
+  // 2. approximate prefix of the tile sums (one CTA; one warp per run when batched)
+  if (n_runs == 1) {
+    tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr);
+    PFB_LAUNCH_OK("tile_prefix_kernel");
+  } else {
+    const int64_t warps = (int64_t)sm_count() * 8 * (kThreads / 32);
+    const int g = (int)((n_runs < warps ? n_runs : warps) * 32 + kThreads - 1) / kThreads;
+    tile_prefix_runs_kernel<<<g, kThreads, 0, st>>>(ts, n_runs, (int)tpr, from_log ? 1 : 0);
+    PFB_LAUNCH_OK("tile_prefix_runs_kernel");
+  }
   // 3. the scan proper
   const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
+  int rc = PFB_OK;
   auto launch = [&](auto kern) -> int {
     int per_sm = 0;
     PFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
@@ -649,7 +690,7 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
     // persistent CTAs (tiles are handed out by ticket): exactly what is co-resident
     int64_t g = (int64_t)sm_count() * per_sm;
     if (g > ntiles) g = ntiles;
-    kern<<<(int)g, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, margin, err);
+    kern<<<(int)g, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, tpr, margin, err);
     return PFB_OK;
   };
   if (mode == PFB_SCAN_SEQEXACT) {
@@ -660,4 +701,37 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
   if (rc) return rc;
   PFB_LAUNCH_OK("scan_kernel");
   return PFB_OK;
+}
+}  // namespace pfb
+
+extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const double* logw, double* cdf,
+                            double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if ((w == nullptr) == (logw == nullptr)) { set_error("exactly one of w / logw must be given"); return PFB_ERR_INVALID; }
+  if (!cdf || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  const bool have_tile_stats = (mode & PFB_SCAN_TILE_STATS_VALID) != 0 && logw != nullptr;
+  mode &= ~PFB_SCAN_TILE_STATS_VALID;
+  if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
+  const double* in = w ? w : logw;
+  if (((uintptr_t)in & 15) || ((uintptr_t)cdf & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, n, &W);
+  if (rc) return rc;
+  return scan_impl(mode, n, in, logw != nullptr, cdf, stats, W, 1, scan_tiles(n), have_tile_stats, (cudaStream_t)stream);
+}
+
+extern "C" int pfb_scan_cdf_batched(int32_t mode, int64_t n_runs, int64_t run_len, const double* logw_pad,
+                                    double* cdf_pad, double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  if (n_runs <= 0 || run_len <= 0) return PFB_OK;
+  if (!logw_pad || !cdf_pad || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  if (!(mode & PFB_SCAN_TILE_STATS_VALID)) { set_error("pfb_scan_cdf_batched must follow pfb_loglik_batched / pfb_predict_loglik_batched on the same buffers"); return PFB_ERR_INVALID; }
+  mode &= ~PFB_SCAN_TILE_STATS_VALID;
+  if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
+  if (((uintptr_t)logw_pad & 15) || ((uintptr_t)cdf_pad & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
+  const int64_t tpr = scan_tiles(run_len);
+  const int64_t n_pad = n_runs * tpr * kScanTile;
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, n_pad, &W);
+  if (rc) return rc;
+  return scan_impl(mode, n_pad, logw_pad, true, cdf_pad, stats, W, n_runs, tpr, true, (cudaStream_t)stream);
 }

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     from pyrecest_b200 import _lib as L
 
     assert ctypes.sizeof(L.PredictParams) == 8 * 4 + 8 * (36 + 6 + 36 + 6 + 2) + 8 + 16 + 48 + 48
-    assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8
+    assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8 + 8
 
 
 def test_argument_validation_without_gpu():
