@@ -42,6 +42,8 @@ WORKLOADS = {
     "r2": ("euclid", 2, 2, 10**4, "EuclideanParticleFilter R^2 constant velocity, Gaussian noise + likelihood"),
     "r4": ("euclid", 4, 4, 10**8, "EuclideanParticleFilter R^4 constant velocity, Gaussian noise + likelihood"),
     # BASELINE.json configs[4]: ONE filter sharded over the GPUs, global systematic resampling (weak: 1.25e8 per GPU)
+    # BASELINE.json configs[3]: independent Monte-Carlo runs, batched (1250 runs x 1e5 particles per GPU = 10k runs on 8)
+    "t2mc": ("torus", 2, 2, 100_000, "BatchedParticleFilter: 1250 independent T^2 filter runs x 1e5 particles per GPU, WN noise + WN likelihood"),
     "r4s": ("euclid", 4, 4, 125_000_000, "ShardedParticleFilter R^4 constant velocity, particles sharded over the GPUs, global systematic resampling"),
 }
 
@@ -368,6 +370,106 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_mc(args):
+    """configs[3]: independent Monte-Carlo runs packed into one launch per step (pyrecest_b200.evaluation),
+    runs sharded over the GPUs with no communication."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200._engine import engine
+    from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN
+    from pyrecest_b200.evaluation import BatchedParticleFilter
+
+    n = args.particles or 100_000
+    runs = args.runs
+    D = 2
+    prandom.seed(99 + rank)
+    eng = engine(dev)
+    C = 0.5 * np.eye(2)
+    bf = BatchedParticleFilter("torus", runs, n, D)
+    bf.set_prior(HWN(np.array([1.0, 2.0]), C))
+    rng = np.random.default_rng(rank)
+    T = args.steps + args.warmup + args.e2e_steps + 1
+    meas = np.mod(np.array([1.0, 2.0]) + np.cumsum(rng.standard_normal((T, runs, D)) * 0.3, axis=0), 2 * np.pi)
+    meas_pinned = torch.as_tensor(meas).pin_memory()
+    sys_noise, meas_noise = HWN(np.zeros(2), C), HWN(np.zeros(2), C)
+    state = {"t": 0}
+
+    def step():
+        z = meas_pinned[state["t"]].numpy()
+        state["t"] += 1
+        bf.update_identity(meas_noise, z)       # update -> estimate -> predict, the reference's loop order
+        est = bf.get_point_estimates()
+        bf.predict_identity(sys_noise)
+        return est
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = eng.launches
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    end.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    gpu_launches = eng.launches - l0
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.e2e_steps)):
+        est_host = step().cpu()
+    barrier()
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / max(1, args.e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    assert bool(torch.isfinite(est_host).all()) and not bool(bf.failed.any())
+    if rank == 0:
+        ms_step = float(ms) / args.steps
+        per_gpu = runs * n
+        peak, peak_src = peaks()
+        ab = sum(algorithmic_bytes(D, 0).values()) - 8
+        gbs = ab * per_gpu / (ms_step * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": world * per_gpu / (ms_step * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"t2mc: {WORKLOADS['t2mc'][4]}", "runs_per_gpu": runs, "particles_per_run": n,
+                       "particles_per_gpu": per_gpu, "resampling": "multinomial", "scan": "sequential-exact per run",
+                       "l2_policy": f"state {per_gpu * 8 * D / 1e6:.0f} MB per GPU, far larger than L2",
+                       "parallelism": "runs sharded over GPUs, no collective"},
+            "e2e": {"value": world * per_gpu / (float(e2e) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(e2e),
+                    "h2d_bytes_per_step": int(runs * D * 8), "d2h_bytes_per_step": int(runs * D * 8),
+                    "path": "public API: BatchedParticleFilter.update_identity + get_point_estimates + predict_identity"},
+            "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                         "frac": gbs / peak, "traffic": None, "peak_source": peak_src, "bytes_per_particle": ab},
+            "cpu_baseline": None,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_sharded(args):
     """configs[4]: one EuclideanParticleFilter over all ranks (pyrecest_b200.sharded), in-kernel Philox noise,
     global systematic resampling over NCCL (all_reduce max, all_gather totals, all_to_all_v offspring)."""
@@ -498,6 +600,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -505,9 +608,13 @@ def main():
     if args.impl == "reference":
         if args.workload == "r4s":
             args.workload = "r4"
+        if args.workload == "t2mc":
+            args.workload = "t3"
         run_reference(args)
     elif args.workload == "r4s":
         run_sharded(args)
+    elif args.workload == "t2mc":
+        run_mc(args)
     else:
         run_gpu(args)
 
