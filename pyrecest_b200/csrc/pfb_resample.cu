@@ -85,6 +85,19 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
 constexpr int kWin = 8;
 constexpr int kBatch = 2;
 
+// guide entries are the only data of the kernel that is re-used (every bucket is hit ~2^shift times): ask L2
+// to keep them (evict_last) while the streams and the random CDF / particle lines pass through
+__device__ __forceinline__ uint64_t make_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int32_t ld_guide(const int32_t* p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 __device__ __forceinline__ bool cdf_le(double c, double total, double u, double tl, double th) {
   if (c <= tl) return true;
   if (c >= th) return false;
@@ -161,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
   (void)total_ptr; (void)n;
+  const uint64_t pol = make_evict_last_policy();
   const bool use_rng = (u == nullptr);
   const double dn = (double)n_out_run;
   const double dM = (double)M;
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
   for (int k = 0; k < NE; ++k) acc[k] = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n_out; j0 += stride * kBatch) {
-    double uj[kBatch], total[kBatch];
+    double uj[kBatch], total[kBatch], frac[kBatch];
     int32_t lo[kBatch], hi[kBatch];
     int64_t run[kBatch];
     bool live[kBatch];
@@ -198,20 +212,35 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
     for (int q = 0; q < kBatch; ++q) {
       if (uj[q] >= 1.0) {  // only a rounded-up systematic point can get here
         lo[q] = hi[q] = (int32_t)(run_len - 1);
+        frac[q] = 0.0;
       } else {
-        const int64_t b = (int64_t)(uj[q] * dM);  // exact
+        const double ub = uj[q] * dM;             // exact
+        const int64_t b = (int64_t)ub;
+        frac[q] = ub - (double)b;                 // position of u inside its bucket, [0, 1)
         const int32_t* g = guide + run[q] * (M + 2);
-        lo[q] = __ldg(g + b);
-        hi[q] = __ldg(g + b + 1);
+        lo[q] = ld_guide(g + b, pol);
+        hi[q] = ld_guide(g + b + 1, pol);
       }
     }
-    // phase 2: the candidate windows, all loads independent
+    // phase 2: one 64-byte window of the CDF per particle, all loads independent.  Buckets longer than
+    // the window are entered where linear interpolation of u inside the bucket points (the CDF is close to
+    // linear over a few dozen randomly ordered particles), aligned to the 64-byte DRAM burst.
     double win[kBatch][kWin];
+    int32_t wst[kBatch];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
+      const int32_t len = hi[q] - lo[q];
+      int32_t s0 = lo[q];
+      if (len > kWin) {
+        s0 = lo[q] + (int32_t)(frac[q] * (double)len) - kWin / 2;
+        const int64_t abs0 = (run[q] * run_pad + s0) & ~(int64_t)(kWin - 1);
+        s0 = (int32_t)(abs0 - run[q] * run_pad);
+        if (s0 < lo[q]) s0 = lo[q];
+      }
+      wst[q] = s0;
 #pragma unroll
       for (int k = 0; k < kWin; ++k) {
-        const int32_t i = lo[q] + k;
+        const int32_t i = s0 + k;
         win[q][k] = (i < hi[q]) ? __ldg(cdf + run[q] * run_pad + i) : INFINITY;
       }
     }
@@ -228,9 +257,11 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
         // windows are sorted: once an entry is > u the rest are too; counting all is branch-free
         if (win[q][k] != INFINITY && cdf_le(win[q][k], total[q], uj[q], tl, th)) cnt = k + 1;
       }
-      int64_t r = (int64_t)lo[q] + cnt;
-      if (cnt == kWin && hi[q] - lo[q] > kWin)
-        r = search_range<true>(cdf + run[q] * run_pad, (int64_t)lo[q] + kWin, (int64_t)hi[q], total[q], uj[q]);
+      int64_t r = (int64_t)wst[q] + cnt;
+      if (cnt == 0 && wst[q] > lo[q])            // everything in the window is > u: the answer lies to its left
+        r = search_range<true>(cdf + run[q] * run_pad, (int64_t)lo[q], (int64_t)wst[q], total[q], uj[q]);
+      else if (cnt == kWin && wst[q] + kWin < hi[q])  // everything is <= u: to its right
+        r = search_range<true>(cdf + run[q] * run_pad, (int64_t)wst[q] + kWin, (int64_t)hi[q], total[q], uj[q]);
       if (r > run_len - 1) r = run_len - 1;
       idx[q] = r;
     }

@@ -245,83 +245,6 @@ __device__ __forceinline__ int block_min_int(int v, int* smem /* 33 */) {
   return x;
 }
 
-// Look-back, run by the WHOLE CTA: exact value c at the start of `tile`.  Thread k inspects tile
-// (tile - 1 - k), so one step covers 256 predecessors (all tiles of a wave start together and publish
-// their maps at about the same time; a 32-wide window would need ~14 dependent steps to reach the
-// previous wave's inclusive values).  Each warp composes the parity maps of its 32-tile window with a
-// shuffle tree (far tile first) up to the nearest inclusive value; the per-warp results are chained in
-// shared memory.  Every thread returns the same value.
-struct LookbackSmem {
-  long long we[kThreads / 32], wo[kThreads / 32];
-  double wincl[kThreads / 32];
-  int wfirst[kThreads / 32], wexp[kThreads / 32];
-};
-
-__device__ __forceinline__ double lookback_block(const TileState& ts, int64_t tile, int64_t run_first,
-                                                 unsigned int* err, LookbackSmem& sm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  PMap composed; composed.e = 0; composed.o = 0;  // maps of the tiles after the inclusive one, in order
-  int e_maps = 0;
-  bool have_maps = false;
-  double c_incl = 0.0;
-  int64_t j0 = tile - 1;
-  while (true) {
-    const int64_t j = j0 - threadIdx.x;
-    unsigned long long f = 2;  // tiles before the start of this run behave like an inclusive 0
-    if (j >= run_first) {
-      do { f = ld_acquire_u64(ts.flagB + j); } while ((f & 3ULL) == 0);
-    }
-    const int st = (int)(f & 3ULL);
-    PMap m; m.e = 0; m.o = 0;
-    double ci = 0.0;
-    if (j >= run_first) {
-      if (st == 2) ci = ld_relaxed_f64(ts.inclB + j);
-      else { m.e = ld_relaxed_s64(ts.aggE + j); m.o = ld_relaxed_s64(ts.aggO + j); }
-    }
-    const unsigned incl_mask = __ballot_sync(0xffffffffu, st == 2);
-    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest lane holding an inclusive value
-    if (lane >= first) { m.e = 0; m.o = 0; }                     // only lanes first-1 .. 0 carry maps
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {  // lane i <- then(lane i+o, lane i): far tile first
-      PMap t;
-      t.e = __shfl_down_sync(0xffffffffu, m.e, o);
-      t.o = __shfl_down_sync(0xffffffffu, m.o, o);
-      if (lane + o < 32) m = pmap_then(t, m);
-    }
-    const double cfirst = __shfl_sync(0xffffffffu, ci, first & 31);
-    __syncthreads();  // previous round's shared values are consumed
-    if (lane == 0) {
-      sm.we[warp] = m.e; sm.wo[warp] = m.o;
-      sm.wfirst[warp] = first;
-      sm.wincl[warp] = cfirst;
-      sm.wexp[warp] = (int)(f >> 8) - 2048;  // binade of the nearest tile's map (meaningful if first > 0)
-    }
-    __syncthreads();
-    bool done = false;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      if (done) continue;
-      const int fw = sm.wfirst[w];
-      if (fw > 0) {
-        PMap win; win.e = sm.we[w]; win.o = sm.wo[w];
-        if (have_maps && sm.wexp[w] != e_maps) atomicOr(err, 4u);
-        e_maps = sm.wexp[w];
-        have_maps = true;
-        composed = pmap_then(win, composed);
-      }
-      if (fw < 32) { c_incl = sm.wincl[w]; done = true; }
-    }
-    if (done) break;
-    j0 -= kThreads;
-  }
-  if (!have_maps) return c_incl;
-  bool ok;
-  long long S = int_of(c_incl, e_maps, &ok);
-  if (!ok) atomicOr(err, 8u);
-  S = pmap_apply(composed, S);
-  return (double)S * ulp_value(e_maps - 52);
-}
-
 // ---- tile sums and their prefix ------------------------------------------------------------------
 template <bool FROM_LOG>
 __global__ void __launch_bounds__(kThreads) tile_stats_kernel(int64_t n, const double* __restrict__ in,
@@ -432,202 +355,275 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
   }
 }
 
-template <bool EXACT, bool FROM_LOG>
-__global__ void __launch_bounds__(kThreads) scan_kernel(int64_t n, const double* __restrict__ in,
-                                                        double* __restrict__ cdf, double* stats,
-                                                        TileState ts, int64_t ntiles, int64_t tpr, double margin,
-                                                        unsigned int* err) {
-  __shared__ double s_dbl[40];
+// ---- the scan proper: three kernels, no inter-CTA waiting ---------------------------------------------
+//   scan_maps_kernel   every tile, in parallel: classify (safe binade e / hard) from the approximate prefix and,
+//                      for safe tiles, reduce the tile to its composed parity map
+//   scan_chain_kernel  one CTA per run: walk the tiles in order carrying the EXACT running value; stretches of
+//                      safe tiles are an ordered scan of their maps (256 threads), hard tiles (one per binade)
+//                      are loaded and walked element-wise; leaves cstart[tile] and writes the hard tiles' CDF
+//   scan_final_kernel  every safe tile, in parallel: exact start value + in-tile map scan -> CDF
+// (A single-pass chained look-back version measured 2.2 ms at 1e8 elements: all tiles of a wave publish their
+//  maps together and the look-back has to walk a whole wave back; this pipeline reads the weights twice instead.)
+constexpr long long kHardTile = -0x7fffffffLL;  // classification value of a hard tile (otherwise: the binade e)
+
+template <bool FROM_LOG>
+__device__ __forceinline__ void load_tile(const double* __restrict__ in, int64_t n, int64_t tile, double shift,
+                                          double (&p)[kItems]) {
+  const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
+  if (base + kItems <= n) {
+    const double2* q = reinterpret_cast<const double2*>(in + base);
+#pragma unroll
+    for (int k = 0; k < kItems / 2; ++k) {
+      double2 v = __ldg(q + k);
+      p[2 * k] = v.x; p[2 * k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) p[k] = (base + k < n) ? in[base + k] : (FROM_LOG ? -INFINITY : 0.0);
+  }
+  if (FROM_LOG) {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) p[k] = exp(p[k] - shift);  // exp(-inf) = 0
+  }
+}
+
+__device__ __forceinline__ void store_tile(double* __restrict__ cdf, int64_t n, int64_t tile, const double (&c)[kItems]) {
+  const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
+  if (base + kItems <= n) {
+    double2* q = reinterpret_cast<double2*>(cdf + base);
+#pragma unroll
+    for (int k = 0; k < kItems / 2; ++k) q[k] = make_double2(c[2 * k], c[2 * k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (base + k < n) cdf[base + k] = c[k];
+  }
+}
+
+// safe (returns the binade) or hard: every running sum inside the tile lies in [a0 (1-m), (a0 + s)(1+m)]
+__device__ __forceinline__ long long classify_tile(const TileState& ts, int64_t tile, int64_t lt, double margin) {
+  if (lt == 0) return kHardTile;  // the first tile of a run starts from 0
+  const double a0 = ts.aprefix[tile];
+  const double lo = a0 * (1.0 - margin);
+  const double hi = (a0 + ts.tsum[tile]) * (1.0 + margin);
+  if (!(lo >= 2.2250738585072014e-308) || !(hi < 1.0e300)) return kHardTile;
+  const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
+  const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
+  return elo == ehi ? (long long)elo : kHardTile;
+}
+
+template <bool FROM_LOG>
+__global__ void __launch_bounds__(kThreads) scan_maps_kernel(int64_t n, const double* __restrict__ in, TileState ts,
+                                                             int64_t ntiles, int64_t tpr, double margin) {
+  __shared__ long long s_ll[72];
+  long long* cls = reinterpret_cast<long long*>(ts.flagB);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long e = classify_tile(ts, tile, tile % tpr, margin);
+    if (threadIdx.x == 0) cls[tile] = e;
+    if (e == kHardTile) continue;
+    double p[kItems];
+    load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
+    const int ue = (int)e - 52;
+    PMap f = pmap_of(p[0], ue);
+#pragma unroll
+    for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
+    PMap tot;
+    block_excl_scan_pmap(f, s_ll, &tot);
+    if (threadIdx.x == 0) { ts.aggE[tile] = tot.e; ts.aggO[tile] = tot.o; }
+    __syncthreads();
+  }
+}
+
+// walks the binades inside one (hard) tile starting from the exact value `cur`; fills c[] and returns the
+// exact value at the end of the tile (identical in every thread)
+__device__ __forceinline__ double hard_tile_walk(const double (&p)[kItems], int cnt, double cur, double (&c)[kItems],
+                                                 long long* s_ll, int* s_int, double* s_cur) {
+  const int tb = threadIdx.x * kItems;
+  int pos = 0;
+  while (true) {
+    if (cur == 0.0) {  // leading zeros: 0 + p = p exactly
+      int mine = 0x7fffffff;
+#pragma unroll
+      for (int k = kItems - 1; k >= 0; --k)
+        if (tb + k >= pos && tb + k < cnt && p[k] != 0.0) mine = tb + k;
+      const int first = block_min_int(mine, s_int);
+#pragma unroll
+      for (int k = 0; k < kItems; ++k)
+        if (tb + k >= pos && tb + k < first) c[k] = 0.0;
+      if (first >= cnt) break;
+      if (first >= tb && first < tb + kItems) {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+          if (tb + k == first) { c[k] = p[k]; *s_cur = p[k]; }
+      }
+      __syncthreads();
+      cur = *s_cur;
+      pos = first + 1;
+      __syncthreads();
+      continue;
+    }
+    int e = (int)((__double_as_longlong(cur) >> 52) & 0x7ff) - 1023;
+    if (e < -1022) e = -1022;
+    const int ue = e - 52;
+    const double u = ulp_value(ue);
+    bool ok;
+    const long long S0 = int_of(cur, e, &ok);
+    PMap f; f.e = 0; f.o = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k)
+      if (tb + k >= pos && tb + k < cnt) f = pmap_then(f, pmap_of(p[k], ue));
+    PMap tot;
+    const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+    long long S = pmap_apply(g, S0);
+    int mine = 0x7fffffff;
+    long long S_before = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      if (tb + k >= pos && tb + k < cnt) {
+        const long long Sp = S;
+        S = pmap_apply(pmap_of(p[k], ue), S);
+        if (S >= 0x0020000000000000LL) {
+          if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
+        } else {
+          c[k] = (double)S * u;
+        }
+      }
+    }
+    const int first = block_min_int(mine, s_int);
+    if (first >= cnt) {  // no crossing left: the tile ends inside this binade
+      cur = (double)pmap_apply(tot, S0) * u;
+      break;
+    }
+    if (first == mine) {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k)
+        if (tb + k == first) {
+          const double cx = __dadd_rn((double)S_before * u, p[k]);
+          c[k] = cx;
+          *s_cur = cx;
+        }
+    }
+    __syncthreads();
+    cur = *s_cur;
+    pos = first + 1;
+    __syncthreads();
+  }
+  return cur;
+}
+
+template <bool FROM_LOG>
+__global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const double* __restrict__ in,
+                                                              double* __restrict__ cdf, double* stats, TileState ts,
+                                                              int64_t n_runs, int64_t tpr, unsigned int* err) {
   __shared__ long long s_ll[72];
   __shared__ int s_int[40];
-  __shared__ int64_t s_tile;
-  __shared__ double s_cin;
-  __shared__ LookbackSmem s_lb;
-  __shared__ int s_safe, s_e;
-
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ts.ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= ntiles) break;
-    const int64_t lt = tile % tpr;           // tile index inside its run (tpr = ntiles: a single run)
-    const int64_t run_first = tile - lt;
-    const double shift = FROM_LOG ? ts.tmax[tile] : 0.0;  // left there by the tile-prefix kernel
-    const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
-
-    double p[kItems];
-    if (base + kItems <= n) {
-      const double2* q = reinterpret_cast<const double2*>(in + base);
-#pragma unroll
-      for (int k = 0; k < kItems / 2; ++k) {
-        double2 v = __ldg(q + k);
-        p[2 * k] = v.x; p[2 * k + 1] = v.y;
+  __shared__ double s_cur;
+  const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
+  double* cstart = ts.inclB;
+  for (int64_t run = blockIdx.x; run < n_runs; run += gridDim.x) {
+    const int64_t t_begin = run * tpr, t_end = t_begin + tpr;
+    double cur = 0.0;  // exact running value entering tile t
+    int64_t t = t_begin;
+    while (t < t_end) {
+      const long long e = cls[t];
+      if (e == kHardTile) {
+        double p[kItems], c[kItems];
+        load_tile<FROM_LOG>(in, n, t, FROM_LOG ? ts.tmax[t] : 0.0, p);
+        const int64_t left = n - t * kScanTile;
+        const int cnt = (int)(left < kScanTile ? left : kScanTile);
+        cur = hard_tile_walk(p, cnt, cur, c, s_ll, s_int, &s_cur);
+        store_tile(cdf, n, t, c);
+        if (t * kScanTile + cnt == n && threadIdx.x == 0) stats[PFB_STAT_TOTAL] = cur;
+        ++t;
+        __syncthreads();
+        continue;
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < kItems; ++k) p[k] = (base + k < n) ? in[base + k] : (FROM_LOG ? -INFINITY : 0.0);
-    }
-    if (FROM_LOG) {
-#pragma unroll
-      for (int k = 0; k < kItems; ++k) p[k] = exp(p[k] - shift);  // exp(-inf) = 0
-    }
-    const double a0 = ts.aprefix[tile];
-    if (threadIdx.x == 0) {
-      if (EXACT) {
-        // certain binade?  every running sum inside the tile lies in [lo, hi]
-        const double lo = a0 * (1.0 - margin);
-        const double hi = (a0 + ts.tsum[tile]) * (1.0 + margin);
-        int safe = 0, e = 0;
-        if (lt > 0 && lo >= 2.2250738585072014e-308 && hi < 1.0e300) {
-          const int elo = (int)((__double_as_longlong(lo) >> 52) & 0x7ff) - 1023;
-          const int ehi = (int)((__double_as_longlong(hi) >> 52) & 0x7ff) - 1023;
-          if (elo == ehi) { safe = 1; e = elo; }
-        }
-        s_safe = safe;
-        s_e = e;
+      // stretch of safe tiles [t, t2): all in binade e (a tile that could leave it would be hard)
+      int64_t t2 = t;
+      while (true) {  // first hard tile at or after t, kThreads tiles per probe
+        const int64_t cand = t2 + threadIdx.x;
+        const int hit = (cand >= t_end || cls[cand] == kHardTile) ? (int)threadIdx.x : 0x7fffffff;
+        const int first = block_min_int(hit, s_int);
+        if (first != 0x7fffffff) { t2 += first; break; }
+        t2 += kThreads;
       }
+      const int64_t L = t2 - t;
+      const int64_t chunk = (L + kThreads - 1) / kThreads;
+      const int64_t c0 = t + (int64_t)threadIdx.x * chunk;
+      const int64_t c1 = (c0 + chunk < t2) ? c0 + chunk : t2;
+      PMap f; f.e = 0; f.o = 0;
+      for (int64_t j = c0; j < c1; ++j) {
+        if (cls[j] != e) atomicOr(err, 4u);
+        PMap m; m.e = ts.aggE[j]; m.o = ts.aggO[j];
+        f = pmap_then(f, m);
+      }
+      PMap tot;
+      const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+      bool ok;
+      const long long S0 = int_of(cur, (int)e, &ok);
+      if (!ok) atomicOr(err, 1u);
+      const double u = ulp_value((int)e - 52);
+      long long S = pmap_apply(g, S0);
+      for (int64_t j = c0; j < c1; ++j) {
+        cstart[j] = (double)S * u;
+        PMap m; m.e = ts.aggE[j]; m.o = ts.aggO[j];
+        S = pmap_apply(m, S);
+      }
+      const long long Send = pmap_apply(tot, S0);
+      if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // a safe stretch left its binade: bound violated
+      cur = (double)Send * u;
+      t = t2;
+      __syncthreads();
     }
-    __syncthreads();
+  }
+}
 
-    double c[kItems];
+template <bool EXACT, bool FROM_LOG>
+__global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const double* __restrict__ in,
+                                                              double* __restrict__ cdf, double* stats, TileState ts,
+                                                              int64_t ntiles) {
+  __shared__ double s_dbl[40];
+  __shared__ long long s_ll[72];
+  const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e = 0;
+    if (EXACT) {
+      e = cls[tile];
+      if (e == kHardTile) continue;  // written by scan_chain_kernel
+    }
+    double p[kItems], c[kItems];
+    load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
     if constexpr (!EXACT) {
       double tsum = p[0];
 #pragma unroll
       for (int k = 1; k < kItems; ++k) tsum += p[k];
       double total;
       const double toff = block_excl_scan(tsum, s_dbl, &total);
-      double run = a0 + toff;
+      double run = ts.aprefix[tile] + toff;
 #pragma unroll
       for (int k = 0; k < kItems; ++k) { run += p[k]; c[k] = run; }
     } else {
-    if (s_safe) {
-      const int ue = s_e - 52;
+      const int ue = (int)e - 52;
       PMap f = pmap_of(p[0], ue);
 #pragma unroll
       for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
       PMap tot;
       const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
-      if (threadIdx.x == 0) {
-        st_relaxed_s64(ts.aggE + tile, tot.e);
-        st_relaxed_s64(ts.aggO + tile, tot.o);
-        st_release_u64(ts.flagB + tile, 1ULL | ((unsigned long long)(s_e + 2048) << 8));
-      }
-      const double cin = lookback_block(ts, tile, run_first, err, s_lb);
-      if (threadIdx.x == 0) {
-        bool ok0;
-        const long long S0 = int_of(cin, s_e, &ok0);
-        if (!ok0) atomicOr(err, 1u);
-        const long long Send = pmap_apply(tot, S0);
-        if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // safe tile crossed a binade: bound violated
-        st_relaxed_f64(ts.inclB + tile, (double)Send * ulp_value(ue));
-        st_release_u64(ts.flagB + tile, 2ULL | ((unsigned long long)(s_e + 2048) << 8));
-      }
       bool ok;
-      long long S = int_of(cin, s_e, &ok);
-      S = pmap_apply(g, S);
+      long long S = pmap_apply(g, int_of(ts.inclB[tile], (int)e, &ok));
       const double u = ulp_value(ue);
 #pragma unroll
       for (int k = 0; k < kItems; ++k) {
         S = pmap_apply(pmap_of(p[k], ue), S);
         c[k] = (double)S * u;
       }
-    } else {
-      // hard tile: wait for the exact incoming value, then walk the binades inside the tile.  Within
-      // one binade the tile is an integer scan (as in a safe tile); the first element whose sum
-      // reaches 2^53 is the crossing: it gets one real fp64 add, and the walk restarts behind it.
-      double cin0 = 0.0;
-      if (lt > 0) cin0 = lookback_block(ts, tile, run_first, err, s_lb);
-      const int cnt = (int)((n - tile * kScanTile) < kScanTile ? (n - tile * kScanTile) : kScanTile);
-      const int tb = threadIdx.x * kItems;
-      double cur = cin0;
-      int pos = 0;
-      while (true) {
-        if (cur == 0.0) {  // leading zeros: 0 + p = p exactly
-          int mine = 0x7fffffff;
-#pragma unroll
-          for (int k = kItems - 1; k >= 0; --k)
-            if (tb + k >= pos && tb + k < cnt && p[k] != 0.0) mine = tb + k;
-          const int first = block_min_int(mine, s_int);
-#pragma unroll
-          for (int k = 0; k < kItems; ++k)
-            if (tb + k >= pos && tb + k < first) c[k] = 0.0;
-          if (first >= cnt) break;
-          if (first >= tb && first < tb + kItems) {
-#pragma unroll
-            for (int k = 0; k < kItems; ++k)
-              if (tb + k == first) { c[k] = p[k]; s_cin = p[k]; }
-          }
-          __syncthreads();
-          cur = s_cin;
-          pos = first + 1;
-          __syncthreads();
-          continue;
-        }
-        int e = (int)((__double_as_longlong(cur) >> 52) & 0x7ff) - 1023;
-        if (e < -1022) e = -1022;
-        const int ue = e - 52;
-        const double u = ulp_value(ue);
-        bool ok;
-        const long long S0 = int_of(cur, e, &ok);
-        PMap f; f.e = 0; f.o = 0;
-#pragma unroll
-        for (int k = 0; k < kItems; ++k)
-          if (tb + k >= pos && tb + k < cnt) f = pmap_then(f, pmap_of(p[k], ue));
-        PMap tot;
-        const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
-        long long S = pmap_apply(g, S0);
-        int mine = 0x7fffffff;
-        long long S_before = 0;
-#pragma unroll
-        for (int k = 0; k < kItems; ++k) {
-          if (tb + k >= pos && tb + k < cnt) {
-            const long long Sp = S;
-            S = pmap_apply(pmap_of(p[k], ue), S);
-            if (S >= 0x0020000000000000LL) {
-              if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
-            } else {
-              c[k] = (double)S * u;
-            }
-          }
-        }
-        const int first = block_min_int(mine, s_int);
-        if (first >= cnt) break;  // no crossing left in this tile
-        if (first == mine) {
-#pragma unroll
-          for (int k = 0; k < kItems; ++k)
-            if (tb + k == first) {
-              const double cx = __dadd_rn((double)S_before * u, p[k]);
-              c[k] = cx;
-              s_cin = cx;
-            }
-        }
-        __syncthreads();
-        cur = s_cin;
-        pos = first + 1;
-        __syncthreads();
-      }
-      // publish the exact value at the end of the tile
-      if ((cnt - 1) / kItems == (int)threadIdx.x) {
-        const double cend = c[(cnt - 1) % kItems];
-        st_relaxed_f64(ts.inclB + tile, cend);
-        st_release_u64(ts.flagB + tile, 2ULL);
-      }
     }
-    }
-    if (base + kItems <= n) {
-      double2* q = reinterpret_cast<double2*>(cdf + base);
-#pragma unroll
-      for (int k = 0; k < kItems / 2; ++k) q[k] = make_double2(c[2 * k], c[2 * k + 1]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < kItems; ++k)
-        if (base + k < n) cdf[base + k] = c[k];
-    }
+    store_tile(cdf, n, tile, c);
     if (tile == ntiles - 1) {
       const int64_t last = n - 1 - tile * kScanTile;
       if ((int64_t)threadIdx.x == last / kItems) stats[PFB_STAT_TOTAL] = c[last % kItems];
     }
+    __syncthreads();
   }
 }
 
@@ -661,8 +657,6 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, d
   unsigned int* ticket = W.counters + 1;
   unsigned int* err = W.counters + 2;
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
-  PFB_CUDA_OK(cudaMemsetAsync(ts.flagB, 0, (size_t)ntiles * 8, st));
-  PFB_CUDA_OK(cudaMemsetAsync(ticket, 0, 4, st));
   // 1. per-tile sums, unless the weighting kernel already left them in the workspace
   if (!have_tile_stats) {
     const int g = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
@@ -682,24 +676,23 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, d
   }
   // 3. the scan proper
   const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
-  int rc = PFB_OK;
-  auto launch = [&](auto kern) -> int {
-    int per_sm = 0;
-    PFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    // persistent CTAs (tiles are handed out by ticket): exactly what is co-resident
-    int64_t g = (int64_t)sm_count() * per_sm;
-    if (g > ntiles) g = ntiles;
-    kern<<<(int)g, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, tpr, margin, err);
-    return PFB_OK;
-  };
+  const int tg = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
   if (mode == PFB_SCAN_SEQEXACT) {
-    rc = from_log ? launch(scan_kernel<true, true>) : launch(scan_kernel<true, false>);
+    const int rg = (int)(n_runs < (int64_t)sm_count() * 8 ? n_runs : (int64_t)sm_count() * 8);
+    if (from_log) {
+      scan_maps_kernel<true><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin);
+      scan_chain_kernel<true><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err);
+      scan_final_kernel<true, true><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
+    } else {
+      scan_maps_kernel<false><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin);
+      scan_chain_kernel<false><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err);
+      scan_final_kernel<true, false><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
+    }
   } else {
-    rc = from_log ? launch(scan_kernel<false, true>) : launch(scan_kernel<false, false>);
+    if (from_log) scan_final_kernel<false, true><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
+    else scan_final_kernel<false, false><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
   }
-  if (rc) return rc;
-  PFB_LAUNCH_OK("scan_kernel");
+  PFB_LAUNCH_OK("scan kernels");
   return PFB_OK;
 }
 }  // namespace pfb
