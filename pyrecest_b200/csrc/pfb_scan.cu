@@ -88,6 +88,24 @@ __device__ __forceinline__ PMap pmap_of(double p, int ue) {
   return r;
 }
 
+// The same addend as a plain integer increment; *tie is set when the addend sits exactly half way between two
+// representable sums (then the increment depends on the parity of the running sum and the map form is needed).
+// For weights that are not dyadic rationals of the running sum this essentially never happens.
+__device__ __forceinline__ long long inc_of(double p, int ue, bool* tie) {
+  const long long bits = __double_as_longlong(p);
+  const int ef = (int)((bits >> 52) & 0x7ff);
+  long long M = bits & 0x000fffffffffffffLL;
+  int q;
+  if (ef == 0) { q = -1074; } else { M |= 0x0010000000000000LL; q = ef - 1075; }
+  const int sh = ue - q;
+  if (M == 0 || sh >= 63) return 0;
+  if (sh <= 0) return (sh > -7) ? (M << (-sh)) : kSat;
+  const long long rem = M & ((1LL << sh) - 1LL);
+  const long long half = 1LL << (sh - 1);
+  if (rem == half) *tie = true;
+  return (M >> sh) + (rem > half ? 1LL : 0LL);
+}
+
 __device__ __forceinline__ double ulp_value(int ue) {  // 2^ue, ue >= -1074
   long long b = (ue >= -1022) ? ((long long)(ue + 1023) << 52) : (1LL << (ue + 1074));
   return __longlong_as_double(b);
@@ -196,6 +214,34 @@ __device__ __forceinline__ double block_excl_scan(double v, double* smem /*33*/,
   double exc = __shfl_up_sync(0xffffffffu, inc, 1);
   if (lane == 0) exc = 0.0;
   return smem[warp] + exc;
+}
+
+// block-wide exclusive scan of one int64 per thread
+__device__ __forceinline__ long long block_excl_scan_ll(long long v, long long* smem /*34*/, long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = (lane < (kThreads / 32)) ? smem[lane] : 0;
+    long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < (kThreads / 32)) smem[lane] = wi - w;
+    if (lane == (kThreads / 32) - 1) smem[33] = wi;
+  }
+  __syncthreads();
+  *total = smem[33];
+  return smem[warp] + (inc - v);
 }
 
 // block-wide exclusive scan of parity maps (ordered composition)
@@ -365,6 +411,9 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
 // (A single-pass chained look-back version measured 2.2 ms at 1e8 elements: all tiles of a wave publish their
 //  maps together and the look-back has to walk a whole wave back; this pipeline reads the weights twice instead.)
 constexpr long long kHardTile = -0x7fffffffLL;  // classification value of a hard tile (otherwise: the binade e)
+constexpr long long kTieBit = 1LL << 40;          // OR-ed into the binade of a safe tile that contains a tie
+__device__ __forceinline__ bool cls_has_tie(long long c) { return c > (kTieBit >> 1); }  // binades are |e| < 1100
+__device__ __forceinline__ long long cls_binade(long long c) { return cls_has_tie(c) ? c - kTieBit : c; }
 
 template <bool FROM_LOG>
 __device__ __forceinline__ void load_tile(const double* __restrict__ in, int64_t n, int64_t tile, double shift,
@@ -424,12 +473,22 @@ __global__ void __launch_bounds__(kThreads) scan_maps_kernel(int64_t n, const do
     double p[kItems];
     load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
     const int ue = (int)e - 52;
-    PMap f = pmap_of(p[0], ue);
+    bool tie = false;
+    long long inc = 0;
 #pragma unroll
-    for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
-    PMap tot;
-    block_excl_scan_pmap(f, s_ll, &tot);
-    if (threadIdx.x == 0) { ts.aggE[tile] = tot.e; ts.aggO[tile] = tot.o; }
+    for (int k = 0; k < kItems; ++k) inc += inc_of(p[k], ue, &tie);
+    if (!__syncthreads_or(tie ? 1 : 0)) {  // no tie in the whole tile: the tile is a plain integer sum
+      long long tot;
+      block_excl_scan_ll(inc, s_ll, &tot);
+      if (threadIdx.x == 0) { ts.aggE[tile] = tot; ts.aggO[tile] = tot; }
+    } else {
+      PMap f = pmap_of(p[0], ue);
+#pragma unroll
+      for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
+      PMap tot;
+      block_excl_scan_pmap(f, s_ll, &tot);
+      if (threadIdx.x == 0) { ts.aggE[tile] = tot.e; ts.aggO[tile] = tot.o; cls[tile] = e + kTieBit; }
+    }
     __syncthreads();
   }
 }
@@ -525,7 +584,7 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
     double cur = 0.0;  // exact running value entering tile t
     int64_t t = t_begin;
     while (t < t_end) {
-      const long long e = cls[t];
+      const long long e = (cls[t] == kHardTile) ? kHardTile : cls_binade(cls[t]);
       if (e == kHardTile) {
         double p[kItems], c[kItems];
         load_tile<FROM_LOG>(in, n, t, FROM_LOG ? ts.tmax[t] : 0.0, p);
@@ -553,7 +612,7 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
       const int64_t c1 = (c0 + chunk < t2) ? c0 + chunk : t2;
       PMap f; f.e = 0; f.o = 0;
       for (int64_t j = c0; j < c1; ++j) {
-        if (cls[j] != e) atomicOr(err, 4u);
+        if (cls_binade(cls[j]) != e) atomicOr(err, 4u);
         PMap m; m.e = ts.aggE[j]; m.o = ts.aggO[j];
         f = pmap_then(f, m);
       }
@@ -587,9 +646,12 @@ __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const d
   const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     long long e = 0;
+    bool has_tie = false;
     if (EXACT) {
       e = cls[tile];
       if (e == kHardTile) continue;  // written by scan_chain_kernel
+      has_tie = cls_has_tie(e);
+      e = cls_binade(e);
     }
     double p[kItems], c[kItems];
     load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
@@ -604,18 +666,31 @@ __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const d
       for (int k = 0; k < kItems; ++k) { run += p[k]; c[k] = run; }
     } else {
       const int ue = (int)e - 52;
-      PMap f = pmap_of(p[0], ue);
-#pragma unroll
-      for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
-      PMap tot;
-      const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
-      bool ok;
-      long long S = pmap_apply(g, int_of(ts.inclB[tile], (int)e, &ok));
       const double u = ulp_value(ue);
+      bool ok;
+      const long long S0 = int_of(ts.inclB[tile], (int)e, &ok);
+      if (!has_tie) {  // plain integer prefix sums (the usual case)
+        long long inc[kItems];
+        bool tie = false;
+        long long tsum = 0;
 #pragma unroll
-      for (int k = 0; k < kItems; ++k) {
-        S = pmap_apply(pmap_of(p[k], ue), S);
-        c[k] = (double)S * u;
+        for (int k = 0; k < kItems; ++k) { inc[k] = inc_of(p[k], ue, &tie); tsum += inc[k]; }
+        long long tot;
+        long long S = S0 + block_excl_scan_ll(tsum, s_ll, &tot);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) { S += inc[k]; c[k] = (double)S * u; }
+      } else {
+        PMap f = pmap_of(p[0], ue);
+#pragma unroll
+        for (int k = 1; k < kItems; ++k) f = pmap_then(f, pmap_of(p[k], ue));
+        PMap tot;
+        const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+        long long S = pmap_apply(g, S0);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+          S = pmap_apply(pmap_of(p[k], ue), S);
+          c[k] = (double)S * u;
+        }
       }
     }
     store_tile(cdf, n, tile, c);
