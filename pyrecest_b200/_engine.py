@@ -102,7 +102,7 @@ class Engine:
             self._tile_stats_key = None if logw is None else (logw.data_ptr(), n, st.data_ptr())
         L.check(self.lib.pfb_scan_cdf(mode, n, _ptr(w), _ptr(logw), _ptr(cdf), _ptr(st), ws, wsb,
                                       _stream(self.device)))
-        self.launches += (4 if exact else 2) + (0 if have else 1)  # [tile_stats] + tile_prefix + maps/chain/final
+        self.launches += (4 if exact else 2) + 1  # tile_combine | tile_stats, tile_prefix, maps + chain + final | final
 
     def resample(self, cdf, u, x_in, x_out, n_out, dim, systematic=False, idx_out=None, est_kind=L.EST_NONE,
                  est_out=None):
@@ -167,7 +167,7 @@ class Engine:
         mode = (L.SCAN_SEQEXACT if exact else L.SCAN_FAST) | L.SCAN_TILE_STATS_VALID
         L.check(self.lib.pfb_scan_cdf_batched(mode, n_runs, run_len, _ptr(logw_pad), _ptr(cdf_pad), _ptr(self.stats),
                                               ws, wsb, _stream(self.device)))
-        self.launches += 4 if exact else 2
+        self.launches += 5 if exact else 3
 
     def resample_batched(self, cdf_pad, x_in, x_out, n_runs, run_len, dim, u=None, seed=0, offset=0, systematic=False,
                          idx_out=None, n_out_run=None):

@@ -39,7 +39,7 @@ constexpr int64_t kPartialDoubles = 64;  // doubles per block partial (>= D*D + 
 constexpr int64_t kWsPartials = (int64_t)kMaxPartialBlocks * kPartialDoubles * 8;
 constexpr int kScanTile = 2048;          // elements per scan tile
 // per tile: flagA, sumA_agg, sumA_incl, flagB, agg_even, agg_odd, incl  (7 x 8 bytes) -> pad to 64
-constexpr int64_t kTileStateBytes = 64;
+constexpr int64_t kTileStateBytes = 192;  // 8 state columns + 8 warps x (max, sum) partials of the weighting kernels
 constexpr int kGuideShift = 3;           // guide table: one bucket per 2^3 = 8 cdf entries (rounded to pow2)
 
 inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
@@ -63,8 +63,9 @@ struct Workspace {
   int64_t tile_bytes;
   int32_t* guide;
   int64_t guide_buckets;
-  double* tmax;   // per scan tile: max log-weight  } written by the weighting kernels,
-  double* tsum;   // per scan tile: sum exp(l - max) } read by pfb_scan_cdf
+  double* tmax;   // per scan tile: max log-weight   } filled by tile_combine / tile_stats,
+  double* tsum;   // per scan tile: sum exp(l - max)  } read by the tile-prefix kernels
+  double* wpart;  // per scan tile: 8 warps x (max, sum exp): what the weighting kernels leave behind
 };
 // tile-state columns (ntiles entries each): 0 flag, 1 aggE, 2 aggO, 3 incl, 4 tmax, 5 tsum, 6 aprefix (+ spare)
 inline double* tile_col(unsigned char* base, int64_t ntiles, int col) {

@@ -393,18 +393,23 @@ inline Seg seg_batched(int64_t n_runs, int64_t run_len) {
   return Seg{n_runs, run_len, tpr * kScanTile, tpr};
 }
 
+// No CTA-wide barrier inside the tile loop: the likelihoods have data-dependent cost (image candidates,
+// series lengths), so every warp owns a contiguous 256-particle slice of the tile, reduces its own
+// (max, sum exp) with shuffles and stores it; pfb_scan_cdf combines the 8 partials of a tile.
 template <typename EVAL>
 __device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, double* stats, Workspace ws,
                                              double* red, EVAL eval) {
   const int64_t ntiles = sg.n_runs * sg.tpr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarpSpan = kScanTile / (kThreads / 32);  // 256 particles per warp and tile
   double gmax = -INFINITY, gnan = 0.0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t run = tile / sg.tpr;
-    const int64_t lbase = (tile - run * sg.tpr) * kScanTile + threadIdx.x;
+    const int64_t lbase = (tile - run * sg.tpr) * kScanTile + warp * kWarpSpan + lane;
     double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
 #pragma unroll 1
-    for (int k = 0; k < kTileItems; ++k) {
-      const int64_t local = lbase + (int64_t)k * kThreads;
+    for (int k = 0; k < kWarpSpan / 32; ++k) {
+      const int64_t local = lbase + k * 32;
       if (local < sg.run_len) {
         const double v = eval(run * sg.run_len + local, run);
         logw[run * sg.run_pad + local] = v;
@@ -420,11 +425,13 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, 
         logw[run * sg.run_pad + local] = -INFINITY;  // padding of a batched run: weight 0
       }
     }
-    const double bm = block_max(m, red);
-    double sv[1] = {(m > -INFINITY) ? sacc * exp(m - bm) : 0.0};
-    block_sum<1>(sv, red);
-    if (threadIdx.x == 0) { ws.tmax[tile] = bm; ws.tsum[tile] = sv[0]; }
-    gmax = fmax(gmax, bm);
+    const double wm = warp_max(m);
+    const double wsum = warp_sum((m > -INFINITY) ? sacc * exp(m - wm) : 0.0);
+    if (lane == 0) {
+      ws.wpart[tile * 16 + 2 * warp] = wm;
+      ws.wpart[tile * 16 + 2 * warp + 1] = wsum;
+    }
+    gmax = fmax(gmax, wm);
   }
   finish_max(gmax, gnan, stats, ws, red);
 }

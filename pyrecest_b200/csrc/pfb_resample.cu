@@ -62,6 +62,7 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   out->guide_buckets = guide_buckets(n);
   out->tmax = tile_col(out->tiles, scan_tiles(n), 4);
   out->tsum = tile_col(out->tiles, scan_tiles(n), 5);
+  out->wpart = tile_col(out->tiles, scan_tiles(n), 8);  // 16 doubles per tile
   return PFB_OK;
 }
 

@@ -312,6 +312,27 @@ __global__ void __launch_bounds__(kThreads) tile_stats_kernel(int64_t n, const d
   }
 }
 
+// (max, sum exp) of a tile from the 8 per-warp partials the weighting kernels left in the workspace
+__global__ void __launch_bounds__(kThreads) tile_combine_kernel(TileState ts, const double* __restrict__ wpart,
+                                                                int64_t ntiles) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
+    double m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmax(m, wpart[t * 16 + 2 * w]);
+    double sacc = 0.0;
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const double mw = wpart[t * 16 + 2 * w];
+        if (mw > -INFINITY) sacc += wpart[t * 16 + 2 * w + 1] * exp(mw - m);
+      }
+    }
+    ts.tmax[t] = m;
+    ts.tsum[t] = sacc;
+  }
+}
+
 // Segmented variant for batched runs: one warp per run.  The shift of a run is the max over its tiles.
 __global__ void __launch_bounds__(kThreads) tile_prefix_runs_kernel(TileState ts, int64_t n_runs, int tpr,
                                                                     int from_log) {
@@ -732,8 +753,11 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, d
   unsigned int* ticket = W.counters + 1;
   unsigned int* err = W.counters + 2;
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
-  // 1. per-tile sums, unless the weighting kernel already left them in the workspace
-  if (!have_tile_stats) {
+  // 1. per-tile sums: combine the partials the weighting kernel left in the workspace, or make them here
+  if (have_tile_stats) {
+    tile_combine_kernel<<<stream_grid(ntiles), kThreads, 0, st>>>(ts, W.wpart, ntiles);
+    PFB_LAUNCH_OK("tile_combine_kernel");
+  } else {
     const int g = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
     if (from_log) tile_stats_kernel<true><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
     else tile_stats_kernel<false><<<g, kThreads, 0, st>>>(n, in, stats, ts, ntiles);
