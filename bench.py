@@ -283,6 +283,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    barrier()
     launches0 = eng.launches
     t_wall0 = time.time()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -423,6 +424,7 @@ def run_mc(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    barrier()
     l0 = eng.launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
@@ -513,6 +515,8 @@ def run_sharded(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    dist.barrier()  # every rank enters the timed region together (rank 0 just slept)
+    torch.cuda.synchronize()
     l0 = eng.launches
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()

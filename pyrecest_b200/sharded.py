@@ -77,11 +77,11 @@ def exchange_plan(B, rank, world, n_loc):
 # ----------------------------------------------------------------------------------------------------
 # the distributed resampling step (backend-agnostic)
 # ----------------------------------------------------------------------------------------------------
-def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None):
+def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out=None):
     """x: (n_loc, D) local particles (already predicted), logw: (n_loc,), local_max: 1-element tensor.
     Returns the new local particles (n_loc, D).  `backend` provides
         scan(logw, shift) -> (cdf (n_loc,), total: 1-element tensor)
-        offspring(cdf, offset, total, u0, j_begin, count, n_total, x) -> (count, D) tensor
+        offspring(cdf, offset, total, u0, j_begin, count, n_total, x, out=view) -> fills (count, D) rows
     Collectives: all_reduce(MAX) of 1 double, all_gather of 1 double per rank, all_to_all_v of particles."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -98,11 +98,34 @@ def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None):
     offs = shard_offsets(tot_host)
     B = offspring_boundaries(offs, u0, n_total)
     send, recv = exchange_plan(B, rank, world, n_loc)
-    count = B[rank + 1] - B[rank]
-    mine = backend.offspring(cdf, offs[rank], offs[-1], u0, B[rank], count, n_total, x)
-    out = torch.empty((n_loc, D), dtype=x.dtype, device=x.device)
-    assert sum(send) == count and sum(recv) == n_loc
-    dist.all_to_all_single(out.view(-1), mine.reshape(-1), [r * D for r in recv], [s * D for s in send], group=group)
+    if out is None:
+        out = torch.empty((n_loc, D), dtype=x.dtype, device=x.device)
+    lo_slot = rank * n_loc
+    # the piece that stays on this rank is written straight into its output slots (no copy, no NCCL)
+    if send[rank] > 0:
+        j0 = max(B[rank], lo_slot)
+        backend.offspring(cdf, offs[rank], offs[-1], u0, j0, send[rank], n_total, x, out=out[j0 - lo_slot:j0 - lo_slot + send[rank]])
+    # remote pieces: produced contiguously in destination-rank order, exchanged with one all_to_all_v
+    send_remote = [0 if r == rank else send[r] for r in range(world)]
+    recv_remote = [0 if r == rank else recv[r] for r in range(world)]
+    if world > 1:
+        sendbuf = torch.empty((sum(send_remote), D), dtype=x.dtype, device=x.device)
+        pos = 0
+        for r in range(world):
+            if send_remote[r] > 0:
+                j0 = max(B[rank], r * n_loc)
+                backend.offspring(cdf, offs[rank], offs[-1], u0, j0, send_remote[r], n_total, x, out=sendbuf[pos:pos + send_remote[r]])
+                pos += send_remote[r]
+        recvbuf = torch.empty((sum(recv_remote), D), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(recvbuf.view(-1), sendbuf.view(-1), [r * D for r in recv_remote], [s_ * D for s_ in send_remote],
+                               group=group)
+        pos = 0
+        for s_ in range(world):
+            if recv_remote[s_] > 0:
+                j0 = max(B[s_], lo_slot)
+                out[j0 - lo_slot:j0 - lo_slot + recv_remote[s_]].copy_(recvbuf[pos:pos + recv_remote[s_]])
+                pos += recv_remote[s_]
+    assert sum(recv) == n_loc
     return out, {"offsets": offs, "boundaries": B, "send": send, "recv": recv}
 
 
@@ -132,8 +155,9 @@ class CudaShardBackend:
         eng.scan(self._cdf, logw=logw, exact=True)
         return self._cdf, eng.stats[L.STAT_TOTAL:L.STAT_TOTAL + 1].clone()
 
-    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x):
-        out = torch.empty((count, x.shape[1]), dtype=x.dtype, device=x.device)
+    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None):
+        if out is None:
+            out = torch.empty((count, x.shape[1]), dtype=x.dtype, device=x.device)
         if count > 0:
             self.eng.resample_sharded(cdf, offset, total, u0, j_begin, count, n_total, x, out, x.shape[1])
         return out
@@ -233,8 +257,9 @@ class ShardedParticleFilter:
             t = src.uniforms((1,), x.device) if not src.fused else torch.rand(1, dtype=torch.float64, device=x.device)
             dist.broadcast(t, src=0, group=self.group)
             u0 = float(t.cpu())
-        new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group)
+        new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt)
         self.last_plan = plan
+        loc._alt = x  # ping-pong
         st._d = new.reshape(st._d.shape)
         st._uniform = True
         st._est_cache = None

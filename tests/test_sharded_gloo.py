@@ -21,12 +21,16 @@ class NumpyShardBackend:
         c = np.cumsum(p)
         return torch.from_numpy(c), torch.tensor([c[-1]], dtype=torch.float64)
 
-    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x):
+    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None):
         j = np.arange(j_begin, j_begin + count, dtype=np.float64)
         u = (j + np.float64(u0)) / np.float64(n_total)
         v = (np.float64(offset) + cdf.numpy()) / np.float64(total)
         idx = np.minimum(np.searchsorted(v, u, side="right"), cdf.shape[0] - 1)
-        return torch.from_numpy(x.numpy()[idx].copy())
+        res = torch.from_numpy(x.numpy()[idx].copy())
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 def _free_port():
