@@ -205,7 +205,7 @@ __device__ __forceinline__ double whitened_sq(const pfb_lik_params& L, const dou
 
 constexpr double kPi = 3.141592653589793;
 constexpr double kImageCut = 90.0;  // screen: drop images whose maha exceeds the best one by this much (e^-45)
-constexpr float kScreenCut = 92.0f; // the same cut for the fp32 screen, plus slack for its rounding
+constexpr float kScreenCut = 78.0f; // fp32 screen: kTermCut plus slack for its rounding (terms beyond kTermCut add nothing)
 constexpr double kTermCut = 76.0;   // a term e^-38 below the best one cannot change the fp64 sum
 
 template <int D, int KIND>
@@ -229,19 +229,30 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
     double best = INFINITY, sum = 0.0;
+    // exp(-d/2) of a term relative to the best one: fp64 where it matters, fp32 once the term is below
+    // 2e-9 of the sum (relative error 1e-6 of 2e-9), nothing beyond e^-38
+    auto rel_term = [](double d) -> double {
+      if (d <= 40.0) return exp(-0.5 * d);
+      return d <= kTermCut ? (double)__expf(-0.5f * (float)d) : 0.0;
+    };
     auto accumulate = [&](const double* row) {
       double sh[D];
 #pragma unroll
       for (int c = 0; c < D; ++c) sh[c] = dev[c] + row[D + 1 + c];
       const double ma = whitened_sq<D>(L, sh);
       if (ma < best) {
-        const double d = best - ma;              // rescale what was summed so far to the new best
-        sum = (d <= kTermCut ? sum * exp(-0.5 * d) : 0.0) + 1.0;
+        sum = (best == INFINITY ? 0.0 : sum * rel_term(best - ma)) + 1.0;  // rescale to the new best
         best = ma;
       } else {
-        const double d = ma - best;
-        if (d <= kTermCut) sum += exp(-0.5 * d);
+        sum += rel_term(ma - best);
       }
+    };
+    // log(sum), sum = 1 + s with s >= 0: the series is exact to fp64 for small s
+    auto log_sum = [](double sm) -> double {
+      const double sx = sm - 1.0;
+      if (sx == 0.0) return 0.0;
+      if (sx < 1e-5) return sx * (1.0 - sx * (0.5 - sx * (1.0 / 3.0)));
+      return log(sm);
     };
     if constexpr (D <= 3) {
       if (K <= 64) {
@@ -265,7 +276,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
           const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
           if (r <= lim) accumulate(images + k * ROW);
         }
-        return L.logc - 0.5 * best + (sum == 1.0 ? 0.0 : log(sum));
+        return L.logc - 0.5 * best + log_sum(sum);
       }
     }
     // generic path (D > 3 or more than 64 images): the same screen in fp64, two passes
@@ -285,7 +296,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
       for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
       if (fma(2.0, lin, q0) + row[D] - mmin <= kImageCut) accumulate(row);
     }
-    return L.logc - 0.5 * best + (sum == 1.0 ? 0.0 : log(sum));
+    return L.logc - 0.5 * best + log_sum(sum);
   } else if constexpr (KIND == PFB_LIK_WN_1D) {
     if (L.sigma > 10.0) return -log(kTwoPi);
     double xx = np_mod_2pi(x[0]);

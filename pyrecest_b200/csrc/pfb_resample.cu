@@ -574,11 +574,13 @@ __global__ void __launch_bounds__(kThreads) resample_sharded_kernel(int64_t n, c
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
     const double uj = __ddiv_rn(__dadd_rn((double)(j_begin + k), u0), dn_total);
+    const double t = uj * total;  // division-free comparison except within 4 ulps of a tie (see cdf_le)
+    const double tl = t * (1.0 - 2.220446049250313e-16);
+    const double th = t * (1.0 + 4.440892098500626e-16);
     int64_t lo = 0, hi = n;  // neighbouring k search neighbouring entries: probes coalesce
     while (lo < hi) {
       const int64_t mid = lo + ((hi - lo) >> 1);
-      const double v = __ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + mid)), total);
-      if (v <= uj) lo = mid + 1; else hi = mid;
+      if (cdf_le(__dadd_rn(cdf_offset, __ldg(cdf + mid)), total, uj, tl, th)) lo = mid + 1; else hi = mid;
     }
     if (lo > n - 1) lo = n - 1;
     if (idx_out) idx_out[k] = lo;
