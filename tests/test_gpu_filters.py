@@ -279,3 +279,37 @@ def test_fused_rng_path_is_reproducible_and_seed_dependent():
     assert not np.array_equal(d1, d3)
     np.testing.assert_allclose(e1, [1.0, 2.0, 3.0], atol=0.1)
     np.testing.assert_allclose(e3, [1.0, 2.0, 3.0], atol=0.1)
+
+
+def test_fp32_storage_option_matches_oracle_to_1e5():
+    """dtype=float32 stores particles (and noise) in fp32, arithmetic / weights / CDF stay fp64: states and
+    estimates within 1e-5 relative of the fp64 oracle (BASELINE.json north_star)."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200.filters import EuclideanParticleFilter, LinearTransition
+
+    rng = np.random.default_rng(77)
+    N, D = 6000, 4
+    F = np.eye(4)
+    F[0, 2] = F[1, 3] = 1.0
+    Q, Rm = 0.1 * np.eye(4), 0.5 * np.eye(4)
+    d0 = rng.standard_normal((N, D))
+    Z = rng.standard_normal((N, D))
+    U = rng.random(N)
+    z = np.array([0.3, -0.2, 0.1, 0.0])
+    pf = EuclideanParticleFilter(N, D, dtype=torch.float32)
+    pf.filter_state.d = torch.as_tensor(d0, dtype=torch.float32)
+    assert pf.filter_state.d.dtype == torch.float32
+    with prandom.inject(normals=Z, uniforms=U):
+        pf.predict_nonlinear(LinearTransition(F), GaussianDistribution(np.zeros(4), Q))
+        dp = host(pf.filter_state.d).astype(np.float64)
+        pf.update_identity(GaussianDistribution(np.zeros(4), Rm), z)
+    ref_pred = O.predict_euclid(d0, O.gaussian_rows(Z, Q), F=F)
+    np.testing.assert_allclose(dp, ref_pred, rtol=1e-5, atol=1e-5)
+    # resampling of the fp32 particles: compare with the oracle run on exactly those particles
+    lik = O.pdf_gauss(dp, z, Rm)
+    dn, wn, idx, _ = O.update_resample(dp, O.uniform_w(N), lik, U)
+    got = host(pf.filter_state.d).astype(np.float64)
+    assert (np.abs(got - dn).max(axis=1) > 0).sum() <= 1
+    np.testing.assert_allclose(host(pf.get_point_estimate()), O.mean_linear(dn, wn), rtol=1e-5, atol=1e-6)
+    assert pf.filter_state.d.dtype == torch.float32 and pf.filter_state.w.dtype == torch.float64
