@@ -19,6 +19,7 @@ communication: give every rank its slice of `measurements`.
 from __future__ import annotations
 
 import copy
+import ctypes as C_
 import math
 import time
 import warnings
@@ -141,10 +142,19 @@ class BatchedParticleFilter:
         return torch.where(self.failed[:, None], torch.full_like(est, float("nan")), est)
 
 
+_ANY_MEAN_CACHE: dict = {}
+
+
 def _wn_params_any_mean(dist, dim, device):
     """wrapped-normal likelihood parameters whose image table is valid for ANY mean in [0, 2 pi)^d: the offset
     box of registry.wn_image_table is taken for mu = 0 and mu = 2 pi and the kept images are united."""
     C = np.atleast_2d(R._np(dist.C))
+    key = (C.tobytes(), dim, str(device))
+    hit = _ANY_MEAN_CACHE.get(key)
+    if hit is not None:
+        p = L.LikParams()
+        C_.memmove(C_.byref(p), C_.byref(hit[0]), C_.sizeof(L.LikParams))
+        return p, hit[1]
     W, logdet = R.gaussian_whitening(C)
     P = W @ W.T
     rows = {}
@@ -160,6 +170,11 @@ def _wn_params_any_mean(dist, dim, device):
     p.n_images = table.shape[0]
     keep = torch.as_tensor(np.ascontiguousarray(table), device=device).contiguous()
     p.images_dev = keep.data_ptr()
+    if len(_ANY_MEAN_CACHE) > 64:
+        _ANY_MEAN_CACHE.clear()
+    tmpl = L.LikParams()
+    C_.memmove(C_.byref(tmpl), C_.byref(p), C_.sizeof(L.LikParams))
+    _ANY_MEAN_CACHE[key] = (tmpl, keep)
     return p, keep
 
 
