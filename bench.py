@@ -53,6 +53,17 @@ def algorithmic_bytes(D, E):
     return {"predict_loglik": 8 * (2 * D + E + 1), "scan": 16, "resample": 8 * (2 * D + 2)}
 
 
+def ncu_traffic(name, n, resampling, exact, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this exact configuration, else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        key = f"{name}:{n}:f64:{resampling}:{'exact' if exact else 'fast'}"
+        return t[key][kernel], t[key]["source"]
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -339,6 +350,7 @@ def run_gpu(args):
         names = ["predict_loglik", "scan", "resample"]
         k = int(np.argmax(kt))
         achieved = ab[names[k]] * n / (kt[k] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(name, n, args.resampling, exact, names[k])
         step_gbs = sum(ab.values()) * n / (ms_step * 1e-3) / 1e9
         cpu_n = args.cpu_particles
         cpu_val, cpu_s = run_cpu(name, cpu_n, 2, 1) if not args.no_cpu else (None, None)
@@ -357,7 +369,8 @@ def run_gpu(args):
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": names[k], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel_ms": {nm: float(t) for nm, t in zip(names, kt)},
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
                          "bytes_per_particle": ab},
