@@ -100,8 +100,8 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
-        double s = np_mod_2pi(n[c] + mean);      // sample(): draw + mean, wrapped
-        out[c] = np_mod_2pi(s);                  // filter wraps again
+        double s = np_mod_2pi(n[c] + mean);      // sample(): draw + mean, wrapped: s in [0, 2 pi]
+        out[c] = (s == kTwoPi) ? 0.0 : s;        // filter wraps again: mod(s) = s, except mod(2 pi) = 0
       }
     } else {
 #pragma unroll
@@ -261,20 +261,31 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
 #pragma unroll
         for (int c = 0; c < 3; ++c) df[c] = (c < D) ? (float)dev[c] : 0.0f;
         float runmin = INFINITY;
-        unsigned long long mask = 0ULL;
-        for (int k = 0; k < K; ++k) {
+        uint32_t mlo = 0u, mhi = 0u;  // candidate bits of images 0..31 / 32..63 (branch-free, 32-bit ops)
+        const int K0 = K < 32 ? K : 32;
+        for (int k = 0; k < K0; ++k) {
           const float4 t = scr[k];
           const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
-          if (r <= runmin + kScreenCut) mask |= (1ULL << k);
+          mlo |= (r <= runmin + kScreenCut) ? (1u << k) : 0u;
+          runmin = fminf(runmin, r);
+        }
+        for (int k = 32; k < K; ++k) {
+          const float4 t = scr[k];
+          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
+          mhi |= (r <= runmin + kScreenCut) ? (1u << (k - 32)) : 0u;
           runmin = fminf(runmin, r);
         }
         const float lim = runmin + kScreenCut;
-        while (mask) {
-          const int k = __ffsll((long long)mask) - 1;
-          mask &= mask - 1ULL;
-          const float4 t = scr[k];
-          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
-          if (r <= lim) accumulate(images + k * ROW);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t m = half ? mhi : mlo;
+          while (m) {
+            const int k = __ffs((int)m) - 1 + 32 * half;
+            m &= m - 1u;
+            const float4 t = scr[k];
+            const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
+            if (r <= lim) accumulate(images + k * ROW);
+          }
         }
         return L.logc - 0.5 * best + log_sum(sum);
       }
