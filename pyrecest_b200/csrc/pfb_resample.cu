@@ -125,37 +125,51 @@ __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double
                                                          int32_t* __restrict__ guide, int64_t M,
                                                          int64_t run_pad) {
   // n: elements over all runs (padded); run r occupies cdf[r run_pad, (r+1) run_pad) and guide row r (M + 2 ints).
-  // run_pad is a multiple of 32 when there is more than one run, so a warp never straddles two runs.
+  // Each thread owns kG consecutive elements (loads issued together); run_pad is a multiple of 32 kG when there
+  // is more than one run, so neither a thread nor a warp straddles two runs.
+  constexpr int kG = 4;
   const double dM = (double)M;
   const int lane = threadIdx.x & 31;
-  const int64_t nround = (n + 31) & ~(int64_t)31;  // whole warps stay converged for the shuffles
+  const int64_t nquads = (n + kG - 1) / kG;
+  const int64_t nround = (nquads + 31) & ~(int64_t)31;  // whole warps stay converged for the shuffles
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-    const int64_t run = (i < n ? i : n - 1) / run_pad;
-    const int64_t k = i - run * run_pad;  // position inside the run
+  for (int64_t qd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < nround; qd += stride) {
+    const int64_t i0 = qd * kG;
+    const int64_t run = (i0 < n ? i0 : n - 1) / run_pad;
+    const int64_t k0 = i0 - run * run_pad;  // position of the first element inside the run
     const int64_t last = (run + 1) * run_pad - 1;
     const double total = __ldg(cdf + (last < n ? last : n - 1));
     int32_t* g = guide + run * (M + 2);
-    int64_t bi = M;  // past-the-end elements own nothing
-    if (i < n) bi = (int64_t)(__ddiv_rn(__ldg(cdf + i), total) * dM);
-    int64_t bprev = __shfl_up_sync(0xffffffffu, bi, 1);
-    if (lane == 0 || k == 0) bprev = (k == 0) ? -1 : (i <= n ? (int64_t)(__ddiv_rn(__ldg(cdf + i - 1), total) * dM) : M);
-    if (i >= n) bprev = bi;  // nothing to write
-    int64_t len = bi - bprev;
-    // short runs of buckets: the owner writes them; long ones: warp-cooperative
-    if (len > 0 && len <= 4) {
-      for (int64_t b = bprev + 1; b <= bi; ++b) g[b] = (int32_t)k;
+    double c[kG];
+#pragma unroll
+    for (int k = 0; k < kG; ++k) c[k] = (i0 + k < n) ? __ldg(cdf + i0 + k) : 0.0;
+    int64_t b[kG];
+#pragma unroll
+    for (int k = 0; k < kG; ++k) b[k] = (i0 + k < n) ? (int64_t)(__ddiv_rn(c[k], total) * dM) : M;  // past the end: owns nothing
+    int64_t bprev = __shfl_up_sync(0xffffffffu, b[kG - 1], 1);
+    if (lane == 0 || k0 == 0) {
+      if (k0 == 0) bprev = -1;
+      else bprev = (i0 <= n) ? (int64_t)(__ddiv_rn(__ldg(cdf + i0 - 1), total) * dM) : M;
     }
-    unsigned longmask = __ballot_sync(0xffffffffu, len > 4);
-    while (longmask) {
-      const int src = __ffs(longmask) - 1;
-      longmask &= longmask - 1;
-      const int64_t b0 = __shfl_sync(0xffffffffu, bprev, src) + 1;
-      const int64_t b1 = __shfl_sync(0xffffffffu, bi, src);
-      const int32_t val = (int32_t)__shfl_sync(0xffffffffu, k, src);
-      const int64_t grow = __shfl_sync(0xffffffffu, run, src);
-      int32_t* gs = guide + grow * (M + 2);
-      for (int64_t b = b0 + lane; b <= b1; b += 32) gs[b] = val;
+#pragma unroll
+    for (int k = 0; k < kG; ++k) {
+      const int64_t bp = (k == 0) ? bprev : b[k - 1];
+      int64_t len = (i0 + k < n) ? b[k] - bp : 0;
+      // short runs of buckets: the owner writes them; long ones: warp-cooperative
+      if (len > 0 && len <= 4) {
+        for (int64_t bb = bp + 1; bb <= b[k]; ++bb) g[bb] = (int32_t)(k0 + k);
+      }
+      unsigned longmask = __ballot_sync(0xffffffffu, len > 4);
+      while (longmask) {
+        const int src = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const int64_t b0 = __shfl_sync(0xffffffffu, bp, src) + 1;
+        const int64_t b1 = __shfl_sync(0xffffffffu, b[k], src);
+        const int32_t val = (int32_t)__shfl_sync(0xffffffffu, k0 + k, src);
+        const int64_t grow = __shfl_sync(0xffffffffu, run, src);
+        int32_t* gs = guide + grow * (M + 2);
+        for (int64_t bb = b0 + lane; bb <= b1; bb += 32) gs[bb] = val;
+      }
     }
   }
 }
@@ -556,7 +570,7 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   cudaStream_t st = (cudaStream_t)stream;
   const double* stats_total = cdf + (n - 1);
   const int64_t M = W.guide_buckets;
-  guide_kernel<<<stream_grid(n, 4), kThreads, 0, st>>>(n, cdf, W.guide, M, n);
+  guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, M, n);
   PFB_LAUNCH_OK("guide_kernel");
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n, n_out, cdf, u, systematic, stats_total, x_in, x_out, idx_out, est_kind, est_out, W, st, W.guide, M, key, n, n, n_out))));
   if (rc) return rc;
@@ -645,7 +659,7 @@ extern "C" int pfb_resample_batched(pfb_dtype dtype, int32_t dim, int64_t n_runs
   int32_t* guide = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + guide_offset(n_pad));
   const int64_t M = guide_buckets(run_len);
   cudaStream_t st = (cudaStream_t)stream;
-  guide_kernel<<<stream_grid(n_pad, 4), kThreads, 0, st>>>(n_pad, cdf_pad, guide, M, run_pad);
+  guide_kernel<<<stream_grid((n_pad + 3) / 4, 2), kThreads, 0, st>>>(n_pad, cdf_pad, guide, M, run_pad);
   PFB_LAUNCH_OK("guide_kernel");
   const int64_t n_out = n_runs * n_out_run;
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n_pad, n_out, cdf_pad, u, systematic, cdf_pad, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st, guide, M, RngKey{rng_seed, rng_offset}, run_pad, run_len, n_out_run))));
