@@ -132,50 +132,55 @@ __device__ __forceinline__ void normal_pair(const uint4& r, double* z0, double* 
 }
 // Zero-mean von Mises draws in [-pi, pi] for D dimensions at once (Best & Fisher 1979: wrapped-Cauchy
 // envelope, rejection).  rr = (1 + rho^2)/(2 rho), rho = (tau - sqrt(2 tau))/(2 kappa),
-// tau = 1 + sqrt(1 + 4 kappa^2) comes from the host.  One Philox block per attempt: 53 bits for the
-// proposal, 32 for the acceptance uniform, 1 for the sign.  The accept/reject decision is evaluated in
-// fp32 (it only shapes the acceptance probability, to ~1e-6 relative); the accepted proposal is then
-// mapped to the angle in fp64 from its 53-bit uniform.  All dimensions share one loop (a lane works on
+// tau = 1 + sqrt(1 + 4 kappa^2) comes from the host.  The accept/reject decision is evaluated in fp32 (it only
+// shapes the acceptance probability, to ~1e-6 relative); the accepted proposal (a 32-bit uniform, i.e. an
+// angle grid of 7e-10 rad) is then mapped to the angle in fp64.  All dimensions share one loop (a lane works on
 // its lowest unfinished dimension) so that a warp pays max-over-lanes of the SUM of attempts, not the sum
 // of per-dimension maxima.
 template <int D>
 __device__ __forceinline__ void vonmises_draws(const RngKey& k, uint64_t index, const double* kappa,
                                                const double* rr, double (&out)[D]) {
-  // phase 1 (divergent, fp32 + integer only): find the accepted proposal of every dimension
-  double u_acc[D];
+  // phase 1 (divergent, fp32 + integer only): find the accepted proposal of every dimension.  One Philox
+  // block carries two attempts: (32-bit proposal, 24-bit acceptance uniform, sign bit) each.
+  uint32_t u_acc[D];
   uint32_t sign_acc = 0;
-  uint32_t attempt = 0;
+  uint32_t call = 0;
   int c = 0;
   while (c < D) {
-    const float kf = (float)kappa[c], rf = (float)rr[c];
-    const uint4 r = rng_block(k, index, (uint32_t)c + (attempt << 8));
-    ++attempt;
-    const double u1 = u53(r.x, r.y);
-    bool accept = true;
-    if (kf >= 1e-8f) {
-      const float zf = cospif((float)u1);
-      const float ff = (1.0f + rf * zf) / (rf + zf);
-      const float cf = kf * (rf - ff);
-      const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f;
-      accept = (cf * (2.0f - cf) - u2 > 0.0f) || (__logf(cf / u2) + 1.0f - cf >= 0.0f) || attempt >= 64u;
-    }
-    if (accept) {
+    const uint4 r = rng_block(k, index, 16u + call);
+    ++call;
 #pragma unroll
-      for (int cc = 0; cc < D; ++cc)
-        if (cc == c) u_acc[cc] = u1;  // (static indices keep the array in registers)
-      sign_acc |= (r.w & 1u) << c;
-      ++c;
-      attempt = 0;
+    for (int half = 0; half < 2; ++half) {
+      if (c < D) {
+        const uint32_t w1 = half ? r.z : r.x, w2 = half ? r.w : r.y;
+        const float kf = (float)kappa[c], rf = (float)rr[c];
+        bool accept = true;
+        if (kf >= 1e-8f) {
+          const float zf = cospif(((float)w1 + 0.5f) * 2.3283064365386963e-10f);
+          const float ff = (1.0f + rf * zf) / (rf + zf);
+          const float cf = kf * (rf - ff);
+          const float u2 = ((float)(w2 >> 8) + 0.5f) * 5.9604644775390625e-08f;
+          accept = (cf * (2.0f - cf) - u2 > 0.0f) || (__logf(cf / u2) + 1.0f - cf >= 0.0f) || call >= 64u;
+        }
+        if (accept) {
+#pragma unroll
+          for (int cc = 0; cc < D; ++cc)
+            if (cc == c) u_acc[cc] = w1;  // (static indices keep the array in registers)
+          sign_acc |= (w2 & 1u) << c;
+          ++c;
+        }
+      }
     }
   }
   // phase 2 (uniform, fp64): proposal -> angle
 #pragma unroll
   for (int cc = 0; cc < D; ++cc) {
+    const double u1 = ((double)u_acc[cc] + 0.5) * 2.3283064365386963e-10;  // (0, 1), 32-bit grid
     double th;
     if (kappa[cc] < 1e-8) {
-      th = 3.141592653589793 * u_acc[cc];  // uniform on the circle: |theta| uniform in [0, pi), sign below
+      th = 3.141592653589793 * u1;  // uniform on the circle: |theta| uniform in (0, pi), sign below
     } else {
-      const double z = cospi(u_acc[cc]);
+      const double z = cospi(u1);
       const double f = (1.0 + rr[cc] * z) / (rr[cc] + z);
       th = acos(fmin(1.0, fmax(-1.0, f)));
     }
