@@ -60,7 +60,8 @@ typedef struct {
   int32_t has_A;             /* 1: noise rows are standard normals, n = z A + mu_noise (A is E x D, the
                                 numpy-legacy factor sqrt(s)[:,None] * Vt of svd(C)); 0: rows used as given */
   int32_t has_mu_noise;
-  int32_t renormalize;       /* SPHERE_VMF: renormalise the rotated draw */
+  int32_t renormalize;       /* sphere modes: bit 0 renormalise the rotated VMF draw; bit 1 mirror onto the upper
+                                hemisphere x_last >= 0 (hyperhemispherical filters identify antipodes) */
   double F[PFB_MAXD * PFB_MAXD];   /* row-major */
   double b[PFB_MAXD];
   double A[PFB_MAXD * PFB_MAXD];   /* row-major E x D */

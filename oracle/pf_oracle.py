@@ -442,6 +442,33 @@ def scatter(d, w):
     return (d * np.asarray(w)[:, None]).T @ d
 
 
+def mean_axis(d, w):
+    """AbstractHypersphereSubsetDistribution._compute_mean_axis_from_moment
+    (pyrecest/distributions/hypersphere_subset/abstract_hypersphere_subset_distribution.py:207-225): eigenvector
+    of the largest eigenvalue of the scatter matrix, signed so that its last component is >= 0."""
+    D, V = np.linalg.eig(scatter(d, w))
+    D, V = np.real(D), np.real(V)
+    m = V[:, np.argsort(D)][:, -1]
+    return m if m[-1] >= 0 else -m
+
+
+def predict_nonadditive(d, samples, weights, u, F, G, b=None, torus=False):
+    """AbstractParticleFilter.predict_nonlinear_nonadditive (pyrecest/filters/abstract_particle_filter.py:56-69):
+    noise_samples = choice(samples, n, p=weights / sum(weights)); d = f(d, noise) with the registry form
+    f(x, n) = x F^T + n G^T + b.  torus=True wraps like the hypertoroidal filters do (PARITY UNPINNED: the
+    reference's hypertoroidal override, hypertoroidal_particle_filter.py:58-67, does not run)."""
+    w = np.asarray(weights, dtype=np.float64)
+    w = w / np.sum(w)
+    noise = np.asarray(samples, dtype=np.float64).reshape(w.shape[0], -1)[multinomial_indices(w, u)]
+    fd = np.asarray(d, dtype=np.float64) @ np.asarray(F).T
+    if b is not None:
+        fd = fd + np.asarray(b)
+    gn = noise @ np.asarray(G).T
+    if torus:
+        return np.mod(fd + np.mod(gn, TWO_PI), TWO_PI)
+    return fd + gn
+
+
 def association_likelihood(lik, w):
     """AbstractParticleFilter.association_likelihood (abstract_particle_filter.py:127-129)."""
     return np.sum(lik * w)

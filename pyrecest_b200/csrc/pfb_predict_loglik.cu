@@ -161,10 +161,11 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
         positive = beta > 0.0;
       }
       if (!positive) { r[0] = -r[0]; r[1] = -r[1]; r[2] = -r[2]; }
-      if (p.renormalize) {
+      if (p.renormalize & 1) {
         double nn = sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
         r[0] /= nn; r[1] /= nn; r[2] /= nn;
       }
+      if ((p.renormalize & 2) && r[2] < 0.0) { r[0] = -r[0]; r[1] = -r[1]; r[2] = -r[2]; }  // upper hemisphere
 #pragma unroll
       for (int c = 0; c < D; ++c) out[c] = r[c < 3 ? c : 0];
     } else {
@@ -182,6 +183,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
 #pragma unroll
     for (int c = 1; c < D; ++c) ss += y[c] * y[c];
     double nn = sqrt(ss);
+    if ((p.renormalize & 2) && y[D - 1] < 0.0) nn = -nn;  // antipodal points are identified: keep the last coordinate >= 0
 #pragma unroll
     for (int c = 0; c < D; ++c) out[c] = y[c] / nn;
   }

@@ -676,6 +676,22 @@ class AbstractHypersphereSubsetDiracDistribution(AbstractDiracDistribution):
     def entropy(self):
         return -torch.sum(self._w * torch.log(self._w))
 
+    def mean_axis(self):
+        """abstract_hypersphere_subset_distribution.py:207-225: principal eigenvector of the scatter matrix
+        (the moment() kernel), signed so that its last component is >= 0."""
+        mom = self.moment()
+        evals, evecs = torch.linalg.eigh(0.5 * (mom + mom.T))  # ascending
+        m = evecs[:, -1]
+        return m if float(m[-1]) >= 0 else -m
+
+
+class HyperhemisphericalDiracDistribution(AbstractHypersphereSubsetDiracDistribution):
+    """hypersphere_subset/hyperhemispherical_dirac_distribution.py: Diracs on the upper hemisphere, antipodes
+    identified; mean() is the mean axis (abstract_hyperhemispherical_distribution.py:31-39)."""
+
+    def mean(self):
+        return self.mean_axis()
+
 
 class HypersphericalDiracDistribution(AbstractHypersphereSubsetDiracDistribution):
     """hypersphere_subset/hyperspherical_dirac_distribution.py:14-44."""

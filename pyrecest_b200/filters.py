@@ -26,13 +26,14 @@ from ._engine import engine
 from .distributions import (
     AbstractDiracDistribution,
     CircularDiracDistribution,
+    HyperhemisphericalDiracDistribution,
     HypersphericalDiracDistribution,
     HypertoroidalDiracDistribution,
     LinearDiracDistribution,
     _as_device_tensor,
     _default_device,
 )
-from .registry import IdentityTransition, LinearTransition  # noqa: F401  (re-export)
+from .registry import IdentityTransition, LinearNoiseTransition, LinearTransition  # noqa: F401  (re-export)
 
 TWO_PI = 2.0 * math.pi
 
@@ -137,11 +138,53 @@ class AbstractParticleFilter:
     def _noise_dim_ok(self, noise):
         return self.filter_state.dim == noise.dim
 
+    _nonadditive_mode = L.PRED_EUCLID
+
     def predict_nonlinear_nonadditive(self, f, samples, weights):
-        raise NotImplementedError(
-            "predict_nonlinear_nonadditive needs an arbitrary f(x, noise) callable; it is the next row of the "
-            "scope table (SURVEY.md 8f-1) and not on the CUDA path yet."
-        )
+        """abstract_particle_filter.py:56-69: one noise sample per particle is drawn from the weighted sample set
+        (random.choice(samples, n, p=weights)) and d <- f(d, noise).  f must be a registry
+        LinearNoiseTransition(F, G, b): d <- d F^T + noise G^T + b (an arbitrary f(x, noise) is rejected)."""
+        if not isinstance(f, LinearNoiseTransition):
+            raise NotImplementedError(
+                "predict_nonlinear_nonadditive only accepts LinearNoiseTransition(F, G, b); arbitrary Python "
+                "callables are not run on the CPU.")
+        st = self.filter_state  # materialises a deferred predict
+        x = st._records()
+        N, D = x.shape
+        smp = _as_device_tensor(samples, dtype=torch.float64, device=x.device)
+        smp = smp.reshape(smp.shape[0], -1)
+        w = _as_device_tensor(weights, dtype=torch.float64, device=x.device).reshape(-1)
+        assert smp.shape[0] == w.shape[0], "samples and weights must match in size"
+        E = smp.shape[1]
+        if f.F.shape[0] != D or f.G.shape[1] != E:
+            raise ValueError("LinearNoiseTransition shapes do not match the state / noise dimensions")
+        if E > D:
+            raise NotImplementedError("noise samples with more components than the state are not supported yet")
+        eng = self._eng()
+        # 1. resample the noise sample set (multinomial, N draws) with the same CDF + search kernels as the particles
+        cdf = torch.empty(w.shape[0], dtype=torch.float64, device=x.device)
+        eng.scan(cdf, w=(w / torch.sum(w)).contiguous(), exact=self.scan_exact)
+        pad = torch.zeros((smp.shape[0], D), dtype=x.dtype, device=x.device)
+        pad[:, :E] = smp.to(x.dtype)
+        noise = torch.empty((N, D), dtype=x.dtype, device=x.device)
+        src = prandom.source()
+        if src.fused:
+            eng.resample_rng(cdf, src.seed, src.next_offset(), pad, noise, N, D)
+        else:
+            eng.resample(cdf, src.uniforms((N,), x.device), pad, noise, N, D)
+        # 2. d <- d F^T + noise G^T + b in the predict kernel (A = G^T padded to D x D)
+        p = L.PredictParams()
+        p.mode, p.dim, p.noise_cols, p.has_F, p.has_A = self._nonadditive_mode, D, D, 1, 1
+        p.F[: D * D] = f.F.reshape(-1).tolist()
+        A = np.zeros((D, D))
+        A[:E, :] = f.G.T
+        p.A[: D * D] = A.reshape(-1).tolist()
+        if f.b is not None:
+            p.has_b = 1
+            p.b[:D] = f.b.tolist()
+        eng.predict(p, x, x, noise)
+        st._d = x.reshape(st._d.shape)
+        st._est_cache = None
 
     def _normals_or_key(self, p, src, shape):
         """standard normals: injected / torch-made array, or the in-kernel Philox key (production)"""
@@ -300,6 +343,7 @@ class HypertoroidalParticleFilter(AbstractParticleFilter):
     """hypertoroidal_particle_filter.py:27-67."""
 
     _default_shift = True
+    _nonadditive_mode = L.PRED_TORUS_ADD  # mod(f(x) + mod(noise G^T)) -- the state stays on the torus
 
     def __init__(self, n_particles, dim, dtype=torch.float64, device=None):
         device = _default_device() if device is None else torch.device(device)
@@ -440,3 +484,43 @@ class HypersphericalParticleFilter(AbstractParticleFilter):
 
     def get_point_estimate(self):
         return self.filter_state.mean_direction()
+
+
+class HyperhemisphericalParticleFilter(HypersphericalParticleFilter):
+    """hyperhemispherical_particle_filter.py:13-46: particles on the upper hemisphere of S^dim (antipodes
+    identified).  Same kernels as the hyperspherical filter; every predicted particle is mirrored onto
+    x_last >= 0, and the point estimate is the mean axis (principal eigenvector of the scatter matrix)."""
+
+    def __init__(self, n_particles, dim, dtype=torch.float64, device=None):
+        HypersphericalParticleFilter.__init__(self, n_particles, dim, dtype=dtype, device=device)
+        st = self._filter_state
+        self._filter_state = HyperhemisphericalDiracDistribution(st._d)
+
+    def set_state(self, new_state):
+        """:35-46  a non-Dirac state is sampled; hyperspherical samples are mirrored onto the hemisphere"""
+        if not isinstance(new_state, HyperhemisphericalDiracDistribution):
+            samples = new_state.sample(self._filter_state.d.shape[0])
+            samples = _as_device_tensor(samples, dtype=self._filter_state.d.dtype, device=self._filter_state.device)
+            flip = samples[:, -1] < 0
+            samples = torch.where(flip[:, None], -samples, samples)
+            new_state = HyperhemisphericalDiracDistribution(samples)
+        self.filter_state = new_state
+
+    def _set_filter_state(self, new_state):
+        if isinstance(new_state, HyperhemisphericalDiracDistribution):
+            assert self._filter_state.d.shape == new_state.d.shape
+            self._filter_state = copy.deepcopy(new_state)
+        else:
+            self.set_state(new_state)
+
+    def _predict_params(self, f, noise, shift):
+        p, draws = HypersphericalParticleFilter._predict_params(self, f, noise, shift)
+        if p.mode in (L.PRED_SPHERE_VMF, L.PRED_SPHERE_ADD):
+            p.renormalize |= 2
+        return p, draws
+
+    def _estimate_from_sums(self, est, D):
+        return None  # the mean axis needs the scatter matrix, not the resultant: no cached estimate
+
+    def get_point_estimate(self):
+        return self.filter_state.mean_axis()

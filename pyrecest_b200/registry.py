@@ -57,6 +57,18 @@ class LinearTransition:
         return y
 
 
+class LinearNoiseTransition:
+    """f(x, n) = x @ F.T + n @ G.T + b: the registry form of a non-additive system model for
+    predict_nonlinear_nonadditive (abstract_particle_filter.py:56-69 takes an arbitrary f(x, noise))."""
+
+    def __init__(self, F, G, b=None):
+        self.F = _np(F)
+        self.G = _np(G)
+        assert self.F.ndim == 2 and self.F.shape[0] == self.F.shape[1], "F must be square"
+        assert self.G.ndim == 2 and self.G.shape[0] == self.F.shape[0], "G must have one row per state component"
+        self.b = None if b is None else _np(b).reshape(-1)
+
+
 def transition_params(f, dim):
     """(has_F, F, has_b, b) for a registry transition; raises for anything else."""
     if f is None or isinstance(f, IdentityTransition):

@@ -313,3 +313,51 @@ def test_fp32_storage_option_matches_oracle_to_1e5():
     assert (np.abs(got - dn).max(axis=1) > 0).sum() <= 1
     np.testing.assert_allclose(host(pf.get_point_estimate()), O.mean_linear(dn, wn), rtol=1e-5, atol=1e-6)
     assert pf.filter_state.d.dtype == torch.float32 and pf.filter_state.w.dtype == torch.float64
+
+
+def test_nonadditive_predict_and_hemispherical_filter(golden):
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HyperhemisphericalDiracDistribution, VonMisesFisherDistribution as VMF
+    from pyrecest_b200.filters import (EuclideanParticleFilter, HyperhemisphericalParticleFilter,
+                                       HypertoroidalParticleFilter, LinearNoiseTransition)
+
+    rng = np.random.default_rng(31)
+    N = 4000
+    d0 = rng.standard_normal((N, 3))
+    samples = rng.standard_normal((50, 2))
+    weights = rng.random(50)
+    u = rng.random(N)
+    F = np.array([[1.0, 0.1, 0.0], [0.0, 1.0, 0.1], [0.0, 0.0, 1.0]])
+    G = rng.standard_normal((3, 2))
+    b = np.array([0.1, 0.2, 0.3])
+    pf = EuclideanParticleFilter(N, 3)
+    pf.filter_state.d = d0
+    with prandom.inject(uniforms=u):
+        pf.predict_nonlinear_nonadditive(LinearNoiseTransition(F, G, b), samples, weights)
+    np.testing.assert_allclose(host(pf.filter_state.d), O.predict_nonadditive(d0, samples, weights, u, F, G, b), rtol=1e-12, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        pf.predict_nonlinear_nonadditive(lambda x, n: x + n, samples, weights)
+    t0 = rng.random((N, 2)) * 2 * np.pi
+    hp = HypertoroidalParticleFilter(N, 2)
+    hp.filter_state.d = t0
+    with prandom.inject(uniforms=u):
+        hp.predict_nonlinear_nonadditive(LinearNoiseTransition(np.eye(2), np.eye(2)), samples, weights)
+    ref = O.predict_nonadditive(t0, samples, weights, u, np.eye(2), np.eye(2), torus=True)
+    diff = np.abs(host(hp.filter_state.d) - ref)
+    assert np.minimum(diff, 2 * np.pi - diff).max() < 1e-12
+    # hemispherical filter (pyrecest/tests/filters/test_hyperhemispherical_particle_filter.py:38-50 pattern)
+    prandom.seed(1)
+    hh = HyperhemisphericalParticleFilter(2000, 2)
+    assert hh.filter_state.d.shape == (2000, 3) and isinstance(hh.filter_state, HyperhemisphericalDiracDistribution)
+    mode = np.array([1.0, 0.0, 0.0])
+    hh.set_state(VMF(mode, 20.0))
+    assert float(hh.filter_state.d[:, -1].min()) >= 0.0
+    est = host(hh.get_point_estimate())
+    assert min(np.linalg.norm(est - mode), np.linalg.norm(est + mode)) < 0.1
+    for _ in range(3):
+        hh.predict_identity(VMF(np.array([0.0, 0.0, 1.0]), 100.0))
+        assert float(hh.filter_state.d[:, -1].min()) >= 0.0
+        hh.update_nonlinear_using_likelihood(VMF(np.array([0.0, 0.6, 0.8]), 30.0))
+    est = host(hh.get_point_estimate())
+    assert np.linalg.norm(est - np.array([0.0, 0.6, 0.8])) < 0.3 and est[-1] >= 0
+    np.testing.assert_allclose(est, O.mean_axis(host(hh.filter_state.d), host(hh.filter_state.w)), atol=1e-10)
