@@ -497,6 +497,147 @@ static int launch_moments_batched(int kind, int64_t n_runs, int64_t run_len, con
   return PFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// systematic resampling, source-centric: the comb u_j = fl(fl(j + u0)/n_comb) is monotone in j, so the offspring
+// of source i are the contiguous slots [J(v_{i-1}), J(v_i)), J(v) = #{j : u_j < v}, v_i = fl(C_i/total) -- the
+// same idx_j = #{i : v_i <= u_j} as the search formulation, without any search: J has a closed-form guess that is
+// corrected with exact comparisons.  One thread per source: the CDF and the particles are streamed once, every
+// offspring is one coalesced store; heavy particles (many offspring) are written by the whole warp.
+// Global CDF value of entry i: C_i = fl(cdf_offset + c_i), normalised by `total` (cdf_offset = 0, total = c_{n-1}
+// for a single filter; shard offset / global total for a sharded one, offspring restricted to
+// [j_begin, j_begin + count)).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double comb_point(int64_t j, double u0, double dn) {
+  return __ddiv_rn(__dadd_rn((double)j, u0), dn);
+}
+// #{j in [0, n_comb) : u_j < v}
+__device__ __forceinline__ int64_t comb_count_below(double v, double u0, double dn, int64_t n_comb) {
+  double g = ceil(v * dn - u0);
+  int64_t j = g <= 0.0 ? 0 : (g >= dn ? n_comb : (int64_t)g);
+  while (j > 0 && comb_point(j - 1, u0, dn) >= v) --j;
+  while (j < n_comb && comb_point(j, u0, dn) < v) ++j;
+  return j;
+}
+
+template <typename T, int D, int EST>
+__global__ void __launch_bounds__(kThreads) systematic_scatter_kernel(
+    int64_t n, const double* __restrict__ cdf, double cdf_offset, double total_imm, double u0_imm,
+    const double* __restrict__ u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count, int64_t n_comb,
+    const T* __restrict__ x_in, T* __restrict__ x_out, int64_t* __restrict__ idx_out, double* est_out, Workspace ws) {
+  constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
+  __shared__ double red[NE * 32];
+  const double total = (total_imm > 0.0) ? total_imm : __dadd_rn(cdf_offset, cdf[n - 1]);
+  double u0 = u0_imm;
+  if (u0_mode == 1) u0 = u0_ptr[0];
+  else if (u0_mode == 2) { const uint4 r = rng_block(key, 0ULL, 7u); u0 = u53(r.x, r.y); }
+  const double dn = (double)n_comb;
+  const int64_t j_end = j_begin + count;
+  const int lane = threadIdx.x & 31;
+  double acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+  const int64_t nround = (n + 31) & ~(int64_t)31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    // e = first slot that no longer belongs to source i
+    int64_t e = j_end;
+    if (i < n - 1) {
+      const double v = __ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + i)), total);
+      e = comb_count_below(v, u0, dn, n_comb);
+      e = e < j_begin ? j_begin : (e > j_end ? j_end : e);
+    }
+    int64_t sbeg = __shfl_up_sync(0xffffffffu, e, 1);
+    if (lane == 0) {
+      if (i == 0) sbeg = j_begin;
+      else if (i < n) {
+        const double vp = __ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + i - 1)), total);
+        sbeg = comb_count_below(vp, u0, dn, n_comb);
+        sbeg = sbeg < j_begin ? j_begin : (sbeg > j_end ? j_end : sbeg);
+      }
+    }
+    int64_t cnt = (i < n) ? e - sbeg : 0;
+    double r[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) r[c] = 0.0;
+    if (cnt > 0 && x_in != nullptr) load_rec<T, D>(x_in, i, r);
+    if (cnt > 0) {
+      if constexpr (EST == PFB_EST_SUM) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fma((double)cnt, r[c], acc[c]);
+      } else if constexpr (EST == PFB_EST_TRIG) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double sn, cs;
+          sincos(r[c], &sn, &cs);
+          acc[2 * c] = fma((double)cnt, cs, acc[2 * c]);
+          acc[2 * c + 1] = fma((double)cnt, sn, acc[2 * c + 1]);
+        }
+      }
+    }
+    // few offspring: the owner stores them; many: the whole warp does
+    if (cnt > 0 && cnt <= 2) {
+      for (int64_t t = 0; t < cnt; ++t) {
+        const int64_t k = sbeg - j_begin + t;
+        if (x_in != nullptr) store_rec<T, D>(x_out, k, r);
+        if (idx_out) idx_out[k] = i;
+      }
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, cnt > 2);
+    while (longmask) {
+      const int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int64_t s0 = __shfl_sync(0xffffffffu, sbeg, src) - j_begin;
+      const int64_t c0 = __shfl_sync(0xffffffffu, cnt, src);
+      const int64_t isrc = __shfl_sync(0xffffffffu, i, src);
+      double rb[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) rb[c] = __shfl_sync(0xffffffffu, r[c], src);
+      for (int64_t t = lane; t < c0; t += 32) {
+        if (x_in != nullptr) store_rec<T, D>(x_out, s0 + t, rb);
+        if (idx_out) idx_out[s0 + t] = isrc;
+      }
+    }
+  }
+  if constexpr (EST != PFB_EST_NONE) {
+    block_sum<NE>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
+    }
+    if (block_is_last(ws.counters)) {
+      double t[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) t[k] = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)b * kPartialDoubles + k];
+      }
+      block_sum<NE>(t, red);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) est_out[k] = t[k] / (double)count;
+      }
+    }
+  }
+}
+
+template <typename T, int D>
+static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, double total_imm, double u0_imm,
+                             const double* u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count,
+                             int64_t n_comb, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
+                             double* est_out, Workspace W, cudaStream_t st) {
+  const int grid = stream_grid(n);
+#define PFB_SYS_LAUNCH(E) systematic_scatter_kernel<T, D, E><<<grid, kThreads, 0, st>>>(n, cdf, cdf_offset, total_imm, u0_imm, u0_ptr, key, u0_mode, j_begin, count, n_comb, (const T*)x_in, (T*)x_out, idx_out, est_out, W)
+  switch (est_kind) {
+    case PFB_EST_NONE: PFB_SYS_LAUNCH(PFB_EST_NONE); break;
+    case PFB_EST_SUM: PFB_SYS_LAUNCH(PFB_EST_SUM); break;
+    case PFB_EST_TRIG: PFB_SYS_LAUNCH(PFB_EST_TRIG); break;
+    default: set_error("bad est_kind %d", est_kind); return PFB_ERR_INVALID;
+  }
+#undef PFB_SYS_LAUNCH
+  return PFB_OK;
+}
+
 template <typename T, int D>
 static int launch_resample(int64_t n, int64_t n_out, const double* cdf, const double* u, int systematic,
                            const double* stats, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
@@ -568,6 +709,12 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   if (rc) return rc;
   // the raw total c_{n-1} is read on the device from the CDF itself
   cudaStream_t st = (cudaStream_t)stream;
+  if (systematic) {  // monotone comb: tiled merge, no guide table
+    PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, 0.0, 0.0, 0.0, u, key, u ? 1 : 2, 0, n_out, n_out, x_in, x_out, idx_out, est_kind, est_out, W, st))));
+    if (rc) return rc;
+    PFB_LAUNCH_OK("systematic_scatter_kernel");
+    return PFB_OK;
+  }
   const double* stats_total = cdf + (n - 1);
   const int64_t M = W.guide_buckets;
   guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, M, n);
@@ -576,34 +723,6 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   if (rc) return rc;
   PFB_LAUNCH_OK("resample_kernel");
   return PFB_OK;
-}
-
-// one shard of a globally resampled filter: systematic comb, global CDF = offset + local running sums
-template <typename T, int D>
-__global__ void __launch_bounds__(kThreads) resample_sharded_kernel(int64_t n, const double* __restrict__ cdf,
-                                                                    double cdf_offset, double total, double u0,
-                                                                    int64_t j_begin, int64_t count, double dn_total,
-                                                                    const T* __restrict__ x_in, T* __restrict__ x_out,
-                                                                    int64_t* __restrict__ idx_out) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
-    const double uj = __ddiv_rn(__dadd_rn((double)(j_begin + k), u0), dn_total);
-    const double t = uj * total;  // division-free comparison except within 4 ulps of a tie (see cdf_le)
-    const double tl = t * (1.0 - 2.220446049250313e-16);
-    const double th = t * (1.0 + 4.440892098500626e-16);
-    int64_t lo = 0, hi = n;  // neighbouring k search neighbouring entries: probes coalesce
-    while (lo < hi) {
-      const int64_t mid = lo + ((hi - lo) >> 1);
-      if (cdf_le(__dadd_rn(cdf_offset, __ldg(cdf + mid)), total, uj, tl, th)) lo = mid + 1; else hi = mid;
-    }
-    if (lo > n - 1) lo = n - 1;
-    if (idx_out) idx_out[k] = lo;
-    if (x_in != nullptr) {
-      double r[D];
-      load_rec<T, D>(x_in, lo, r);
-      store_rec<T, D>(x_out, k, r);
-    }
-  }
 }
 
 __global__ void __launch_bounds__(kThreads) rng_uniform_kernel(int64_t n, RngKey key, double* __restrict__ out) {
@@ -688,10 +807,11 @@ extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, con
   if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
   if (!(total > 0.0) || n_total_out <= 0) { set_error("total weight and comb size must be positive"); return PFB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stream_grid(count);
-  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (resample_sharded_kernel<T, D><<<grid, kThreads, 0, st>>>(
-      n, cdf, cdf_offset, total, u0, j_begin, count, (double)n_total_out, (const T*)x_in, (T*)x_out, idx_out))));
-  PFB_LAUNCH_OK("resample_sharded_kernel");
+  Workspace W{};  // no estimate here: the reduction scratch is not touched
+  int rc = PFB_OK;
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, cdf_offset, total, u0, nullptr, RngKey{0, 0}, 0, j_begin, count, n_total_out, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st))));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("systematic_scatter_kernel");
   return PFB_OK;
 }
 
