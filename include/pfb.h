@@ -217,11 +217,13 @@ int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, con
  * [start, start + n) of a global CDF C_i = fl(cdf_offset + c_i), normalised by `total` (the sum over all
  * shards).  Produces the `count` systematic offspring j = j_begin .. j_begin + count - 1 of the global
  * comb u_j = (j + u0) / n_total_out:  x_out[k] = x_in[#{i : fl(C_i / total) <= u_j}]  (index local to the
- * shard, clamped to n - 1).  The caller picks [j_begin, j_begin + count) as the offspring that fall into
+ * shard, clamped to n - 1); est_kind / est_out as in pfb_resample (mean over these `count` offspring).
+ * The caller picks [j_begin, j_begin + count) as the offspring that fall into
  * this shard (pyrecest_b200/sharded.py) and exchanges the result with an all-to-all. */
 int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, double cdf_offset,
                          double total, double u0, int64_t j_begin, int64_t count, int64_t n_total_out,
-                         const void* x_in, void* x_out, int64_t* idx_out, void* stream);
+                         const void* x_in, void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out,
+                         void* ws, int64_t ws_bytes, void* stream);
 /* fill `out` (n doubles) with the uniforms pfb_resample_rng would use (tests, debugging) */
 int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream);
 

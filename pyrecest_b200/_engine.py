@@ -124,11 +124,13 @@ class Engine:
                                           _stream(self.device)))
         self.launches += 2
 
-    def resample_sharded(self, cdf, cdf_offset, total, u0, j_begin, count, n_total_out, x_in, x_out, dim, idx_out=None):
+    def resample_sharded(self, cdf, cdf_offset, total, u0, j_begin, count, n_total_out, x_in, x_out, dim, idx_out=None,
+                         est_kind=L.EST_NONE, est_out=None):
         dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        ws, wsb = self._ensure_ws(0)
         L.check(self.lib.pfb_resample_sharded(dt, dim, cdf.shape[0], _ptr(cdf), float(cdf_offset), float(total), float(u0),
                                               int(j_begin), int(count), int(n_total_out), _ptr(x_in), _ptr(x_out),
-                                              _ptr(idx_out), _stream(self.device)))
+                                              _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb, _stream(self.device)))
         self.launches += 1
 
     def rng_uniform(self, out, seed, offset):

@@ -801,15 +801,21 @@ extern "C" int pfb_moments_batched(int32_t kind, pfb_dtype dtype, int32_t dim, i
 
 extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, double cdf_offset,
                                     double total, double u0, int64_t j_begin, int64_t count, int64_t n_total_out,
-                                    const void* x_in, void* x_out, int64_t* idx_out, void* stream) {
+                                    const void* x_in, void* x_out, int64_t* idx_out, int32_t est_kind,
+                                    double* est_out, void* ws, int64_t ws_bytes, void* stream) {
   if (n <= 0 || count <= 0) return PFB_OK;
   if (!cdf) { set_error("NULL cdf"); return PFB_ERR_INVALID; }
   if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
   if (!(total > 0.0) || n_total_out <= 0) { set_error("total weight and comb size must be positive"); return PFB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  Workspace W{};  // no estimate here: the reduction scratch is not touched
+  Workspace W{};
   int rc = PFB_OK;
-  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, cdf_offset, total, u0, nullptr, RngKey{0, 0}, 0, j_begin, count, n_total_out, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st))));
+  if (est_kind != PFB_EST_NONE) {
+    if (!est_out || !x_in) { set_error("estimate requested without output / particles"); return PFB_ERR_INVALID; }
+    rc = carve_workspace(ws, ws_bytes, 0, &W);
+    if (rc) return rc;
+  }
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, cdf_offset, total, u0, nullptr, RngKey{0, 0}, 0, j_begin, count, n_total_out, x_in, x_out, idx_out, est_kind, est_out, W, st))));
   if (rc) return rc;
   PFB_LAUNCH_OK("systematic_scatter_kernel");
   return PFB_OK;

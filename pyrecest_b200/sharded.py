@@ -77,11 +77,12 @@ def exchange_plan(B, rank, world, n_loc):
 # ----------------------------------------------------------------------------------------------------
 # the distributed resampling step (backend-agnostic)
 # ----------------------------------------------------------------------------------------------------
-def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out=None):
+def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out=None, est_kind=None):
     """x: (n_loc, D) local particles (already predicted), logw: (n_loc,), local_max: 1-element tensor.
     Returns the new local particles (n_loc, D).  `backend` provides
         scan(logw, shift) -> (cdf (n_loc,), total: 1-element tensor)
-        offspring(cdf, offset, total, u0, j_begin, count, n_total, x, out=view) -> fills (count, D) rows
+        offspring(cdf, offset, total, u0, j_begin, count, n_total, x, out=view, est_kind=None|"sum"|"trig")
+            -> fills (count, D) rows; with est_kind returns the mean of those rows (or of their cos / sin)
     Collectives: all_reduce(MAX) of 1 double, all_gather of 1 double per rank, all_to_all_v of particles."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -101,10 +102,20 @@ def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out
     if out is None:
         out = torch.empty((n_loc, D), dtype=x.dtype, device=x.device)
     lo_slot = rank * n_loc
+    # sums over all offspring this rank PRODUCES (wherever they go): after an all_reduce they are the global sums
+    est_sums = None
+    if est_kind is not None:
+        est_sums = torch.zeros(2 * D if est_kind == "trig" else D, dtype=torch.float64, device=x.device)
+
+    def produce(j0, cnt, dst):
+        piece = backend.offspring(cdf, offs[rank], offs[-1], u0, j0, cnt, n_total, x, out=dst, est_kind=est_kind)
+        if est_kind is not None:
+            est_sums.add_(piece * float(cnt))
+
     # the piece that stays on this rank is written straight into its output slots (no copy, no NCCL)
     if send[rank] > 0:
         j0 = max(B[rank], lo_slot)
-        backend.offspring(cdf, offs[rank], offs[-1], u0, j0, send[rank], n_total, x, out=out[j0 - lo_slot:j0 - lo_slot + send[rank]])
+        produce(j0, send[rank], out[j0 - lo_slot:j0 - lo_slot + send[rank]])
     # remote pieces: produced contiguously in destination-rank order, exchanged with one all_to_all_v
     send_remote = [0 if r == rank else send[r] for r in range(world)]
     recv_remote = [0 if r == rank else recv[r] for r in range(world)]
@@ -114,7 +125,7 @@ def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out
         for r in range(world):
             if send_remote[r] > 0:
                 j0 = max(B[rank], r * n_loc)
-                backend.offspring(cdf, offs[rank], offs[-1], u0, j0, send_remote[r], n_total, x, out=sendbuf[pos:pos + send_remote[r]])
+                produce(j0, send_remote[r], sendbuf[pos:pos + send_remote[r]])
                 pos += send_remote[r]
         recvbuf = torch.empty((sum(recv_remote), D), dtype=x.dtype, device=x.device)
         dist.all_to_all_single(recvbuf.view(-1), sendbuf.view(-1), [r * D for r in recv_remote], [s_ * D for s_ in send_remote],
@@ -126,7 +137,7 @@ def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out
                 out[j0 - lo_slot:j0 - lo_slot + recv_remote[s_]].copy_(recvbuf[pos:pos + recv_remote[s_]])
                 pos += recv_remote[s_]
     assert sum(recv) == n_loc
-    return out, {"offsets": offs, "boundaries": B, "send": send, "recv": recv}
+    return out, {"offsets": offs, "boundaries": B, "send": send, "recv": recv, "est_sums": est_sums}
 
 
 def sharded_sum(local_sums, group=None):
@@ -155,12 +166,23 @@ class CudaShardBackend:
         eng.scan(self._cdf, logw=logw, exact=True)
         return self._cdf, eng.stats[L.STAT_TOTAL:L.STAT_TOTAL + 1].clone()
 
-    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None):
+    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None, est_kind=None):
+        """fills `out` with the offspring; returns the mean of the produced offspring (sum x, or per-dimension
+        (cos, sin)) when est_kind is "sum" / "trig", else `out`"""
+        from . import _lib as L
+
+        D = x.shape[1]
         if out is None:
-            out = torch.empty((count, x.shape[1]), dtype=x.dtype, device=x.device)
+            out = torch.empty((count, D), dtype=x.dtype, device=x.device)
+        if est_kind is None:
+            if count > 0:
+                self.eng.resample_sharded(cdf, offset, total, u0, j_begin, count, n_total, x, out, D)
+            return out
+        est = torch.zeros(2 * D if est_kind == "trig" else D, dtype=torch.float64, device=x.device)
         if count > 0:
-            self.eng.resample_sharded(cdf, offset, total, u0, j_begin, count, n_total, x, out, x.shape[1])
-        return out
+            self.eng.resample_sharded(cdf, offset, total, u0, j_begin, count, n_total, x, out, D,
+                                      est_kind=L.EST_TRIG if est_kind == "trig" else L.EST_SUM, est_out=est)
+        return est
 
 
 class ShardedParticleFilter:
@@ -200,9 +222,11 @@ class ShardedParticleFilter:
 
     @filter_state.setter
     def filter_state(self, prior):
+        self._est_sums = None
         self.local.filter_state = prior  # every shard samples its own n_loc particles (seed differs per rank)
 
     def set_local_particles(self, x):
+        self._est_sums = None
         self.local.filter_state.d = x
 
     def gather_particles(self):
@@ -213,9 +237,11 @@ class ShardedParticleFilter:
 
     # -- predict / update ----------------------------------------------------------------------------------
     def predict_identity(self, noise_distribution):
+        self._est_sums = None
         self.local.predict_identity(noise_distribution)
 
     def predict_nonlinear(self, f, noise_distribution=None, function_is_vectorized=True, shift_instead_of_add=None):
+        self._est_sums = None
         self.local.predict_nonlinear(f, noise_distribution, function_is_vectorized, shift_instead_of_add)
 
     def update_identity(self, meas_noise, measurement, shift_instead_of_add=True):
@@ -257,8 +283,10 @@ class ShardedParticleFilter:
             t = src.uniforms((1,), x.device) if not src.fused else torch.rand(1, dtype=torch.float64, device=x.device)
             dist.broadcast(t, src=0, group=self.group)
             u0 = float(t.cpu())
-        new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt)
+        new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt,
+                                                est_kind="trig" if self.manifold == "torus" else "sum")
         self.last_plan = plan
+        self._est_sums = sharded_sum(plan["est_sums"], self.group)  # global sums over all N offspring
         loc._alt = x  # ping-pong
         st._d = new.reshape(st._d.shape)
         st._uniform = True
@@ -269,6 +297,14 @@ class ShardedParticleFilter:
         from . import _lib as L
 
         loc = self.local
+        if getattr(self, "_est_sums", None) is not None and loc._pending is None:
+            s = self._est_sums  # reduced inside the resampling kernels: no extra pass over the particles
+            D = loc._filter_state._stored_dim
+            if self.manifold == "torus":
+                t = s.reshape(D, 2)
+                return torch.remainder(torch.atan2(t[:, 1], t[:, 0]), 2.0 * math.pi)
+            m = s / self.n_total
+            return m / torch.linalg.norm(m) if self.manifold == "sphere" else m
         st = loc.filter_state
         x = st._records()
         D = x.shape[1]

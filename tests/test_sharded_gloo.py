@@ -21,7 +21,7 @@ class NumpyShardBackend:
         c = np.cumsum(p)
         return torch.from_numpy(c), torch.tensor([c[-1]], dtype=torch.float64)
 
-    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None):
+    def offspring(self, cdf, offset, total, u0, j_begin, count, n_total, x, out=None, est_kind=None):
         j = np.arange(j_begin, j_begin + count, dtype=np.float64)
         u = (j + np.float64(u0)) / np.float64(n_total)
         v = (np.float64(offset) + cdf.numpy()) / np.float64(total)
@@ -29,8 +29,9 @@ class NumpyShardBackend:
         res = torch.from_numpy(x.numpy()[idx].copy())
         if out is not None:
             out.copy_(res)
-            return out
-        return res
+        if est_kind == "sum":
+            return res.mean(dim=0) if count > 0 else torch.zeros(x.shape[1], dtype=torch.float64)
+        return out if out is not None else res
 
 
 def _free_port():
@@ -50,8 +51,9 @@ def _worker(rank, world, port, case, out_dir):
     x = torch.from_numpy(data["x"][rank * n_loc:(rank + 1) * n_loc].copy())
     logw = torch.from_numpy(data["logw"][rank * n_loc:(rank + 1) * n_loc].copy())
     local_max = torch.tensor([float(logw.max())], dtype=torch.float64)
-    new, plan = sharded_systematic_resample(NumpyShardBackend(), x, logw, local_max, float(data["u0"]))
+    new, plan = sharded_systematic_resample(NumpyShardBackend(), x, logw, local_max, float(data["u0"]), est_kind="sum")
     s = sharded_sum(new.sum(dim=0))
+    assert torch.allclose(sharded_sum(plan["est_sums"]), s, rtol=1e-12)  # sums reduced where the offspring are produced
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), new=new.numpy(), sum=s.numpy(),
              boundaries=np.array(plan["boundaries"]), send=np.array(plan["send"]), recv=np.array(plan["recv"]))
     dist.destroy_process_group()
