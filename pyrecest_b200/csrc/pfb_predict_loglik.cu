@@ -591,7 +591,7 @@ static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const
   if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
   if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
+  rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = tile_grid_seg(sg);
@@ -653,7 +653,7 @@ static int predict_loglik_impl(const pfb_predict_params* p, const pfb_lik_params
   if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
   if (!x_in || !x_out || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
-  rc = carve_workspace(ws, ws_bytes, sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
+  rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   PFB_DISPATCH_DTYPE(dtype, {

@@ -525,3 +525,22 @@ def test_resample_sharded_kernel_matches_sharded_oracle(eng):
     mism = np.any(got != x[idx_ref], axis=1).sum()
     assert mism <= 3, mism
     assert B == O.offspring_boundaries(np.array(offs), u0, N)
+
+
+@pytest.mark.parametrize("n", [1, 300, 519, 2047, 2049])
+def test_fresh_engine_workspace_fits_every_call(n):
+    """A new engine's workspace (sized by pfb_workspace_bytes(n)) must satisfy every kernel of the cycle for the
+    same n -- in particular the weighting kernels, which work on whole 2048-particle tiles."""
+    from pyrecest_b200 import registry as R
+    from pyrecest_b200._engine import Engine
+
+    e = Engine("cuda:0")
+    rng = np.random.default_rng(n)
+    x = dev(rng.normal(size=(n, 2)))
+    lp, _keep = R.lik_params(_dist("GaussianDistribution", mu=np.zeros(2), C=np.eye(2)), 2, images_to_device=dev)
+    logw = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    e.loglik(lp, x, logw)
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    e.scan(cdf, logw=logw, exact=True)
+    w = np.exp(host(logw) - host(logw).max())
+    np.testing.assert_allclose(host(cdf), np.cumsum(w), rtol=1e-13)
