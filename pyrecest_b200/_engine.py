@@ -112,7 +112,7 @@ class Engine:
         L.check(self.lib.pfb_resample(dt, dim, n, n_out, _ptr(cdf), _ptr(u), 1 if systematic else 0, _ptr(x_in),
                                       _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
                                       _stream(self.device)))
-        self.launches += 2  # guide_kernel + resample_kernel
+        self.launches += 1 if systematic else 3  # scatter | guide + bucket records + resample
 
     def resample_rng(self, cdf, seed, offset, x_in, x_out, n_out, dim, systematic=False, idx_out=None,
                      est_kind=L.EST_NONE, est_out=None):
@@ -122,7 +122,7 @@ class Engine:
         L.check(self.lib.pfb_resample_rng(dt, dim, n, n_out, _ptr(cdf), seed, offset, 1 if systematic else 0,
                                           _ptr(x_in), _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
                                           _stream(self.device)))
-        self.launches += 2
+        self.launches += 1 if systematic else 3
 
     def resample_sharded(self, cdf, cdf_offset, total, u0, j_begin, count, n_total_out, x_in, x_out, dim, idx_out=None,
                          est_kind=L.EST_NONE, est_out=None):

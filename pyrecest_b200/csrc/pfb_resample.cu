@@ -174,6 +174,174 @@ __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bucket records (single-filter multinomial path).  The guide + CDF-window lookup above costs two dependent
+// random DRAM fetches (one 64-byte chunk of the guide, two of the CDF).  A bucket record folds both into ONE
+// aligned 64-byte fetch: for bucket b of Mr = 2^k >= n/16 buckets of [0, 1)
+//     word 0        : G[b]                       (int32, first CDF index of the bucket)
+//     halfword 2    : min(count, 65535)           count = G[b+1] - G[b]
+//     halfwords 3.. : q_k = floor((v_{G[b]+k} Mr - b) 2^16), k < min(count, 29)   (0xFFFF = unused)
+// v Mr, the subtraction of b and the scaling by 2^16 are all exact, so with p = floor((u Mr - b) 2^16)
+//     q_k < p  =>  v_k < u   (counted)        q_k > p  =>  v_k > u   (not counted)
+// and only q_k == p (probability ~ count / 65536) or count > 29 needs the exact search in the CDF itself.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRecShift = 4;
+constexpr int kRecEntries = 29;
+
+inline int64_t rec_buckets(int64_t n) {
+  int64_t want = n >> kRecShift;
+  int64_t M = 1;
+  while (M < want) M <<= 1;
+  return M;
+}
+inline int64_t rec_offset(int64_t n) {
+  return (guide_offset(n) + (guide_buckets(n) + 2) * (int64_t)sizeof(int32_t) + 255) & ~(int64_t)255;
+}
+inline int64_t rec_bytes(int64_t n) { return (rec_buckets(n) + 2) * 64; }
+static bool bucket_records_enabled() {
+  const char* e = getenv("PFB_BUCKET_RECORDS");  // read per call: the tests run both paths
+  return e ? atoi(e) != 0 : true;
+}
+
+__global__ void __launch_bounds__(kThreads) bucket_record_kernel(int64_t n, const double* __restrict__ cdf,
+                                                                 const int32_t* __restrict__ guide, int64_t M,
+                                                                 uint4* __restrict__ recs) {
+  const double total = __ldg(cdf + n - 1);
+  const double dM = (double)M;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= M; b += stride) {
+    const int32_t lo = __ldg(guide + b);
+    const int32_t hi = (b < M) ? __ldg(guide + b + 1) : lo;
+    const int32_t cnt = hi - lo;
+    uint32_t w[16];
+    w[0] = (uint32_t)lo;
+#pragma unroll
+    for (int k = 1; k < 16; ++k) w[k] = 0xFFFFFFFFu;
+    w[1] = 0xFFFF0000u | (uint32_t)(cnt < 65535 ? cnt : 65535);
+    const int m = cnt < kRecEntries ? cnt : kRecEntries;
+    const double db = (double)b;
+#pragma unroll
+    for (int k = 0; k < kRecEntries; ++k) {
+      if (k < m) {
+        const double v = __ddiv_rn(__ldg(cdf + lo + k), total);
+        const uint32_t q = (uint32_t)((v * dM - db) * 65536.0) & 0xFFFFu;
+        const int h = k + 3;  // halfword slot
+        if (h & 1) w[h >> 1] = (w[h >> 1] & 0x0000FFFFu) | (q << 16);
+        else w[h >> 1] = (w[h >> 1] & 0xFFFF0000u) | q;
+      }
+    }
+    uint4* r = recs + b * 4;
+    r[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    r[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    r[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    r[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  }
+}
+
+// One 32-byte sector in ONE load instruction (LDG.256, 32-byte aligned address).
+__device__ __forceinline__ void ld_sector(const void* p, uint64_t (&w)[4]) {
+  asm volatile("ld.global.nc.L2::64B.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+               : "l"(p));
+}
+
+// Random gather of one particle record.  Component-wise loads of a record send one request per component
+// to L2 for what is one (or two) 32-byte sectors, and L2 does not merge misses in flight: the 24-byte T^3
+// record cost ~150 bytes of DRAM reads.  Here every covering sector is loaded exactly once (sector-aligned,
+// so the reads stay inside the 256-byte allocation granule) and the components are selected from registers.
+template <typename T, int D>
+__device__ __forceinline__ void gather_rec(const T* __restrict__ x, int64_t i, double (&r)[D]) {
+  constexpr int R = D * (int)sizeof(T);
+  constexpr int WPS = 32 / (int)sizeof(T);                  // components per sector
+  constexpr int NS = (R - (int)sizeof(T)) / 32 + 2;         // sectors a record can touch
+  const uintptr_t a = reinterpret_cast<uintptr_t>(x + i * D);
+  const int off = (int)(a & 31) / (int)sizeof(T);
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(a & ~(uintptr_t)31);
+  uint64_t raw[NS][4];
+#pragma unroll
+  for (int sct = 0; sct < NS; ++sct) {
+    if (sct == 0 || off * (int)sizeof(T) + R > 32 * sct) ld_sector(base + 32 * sct, raw[sct]);
+    else raw[sct][0] = raw[sct][1] = raw[sct][2] = raw[sct][3] = 0ull;
+  }
+  auto word = [&](int k) -> double {  // component k of the sector-aligned span (k is a compile-time constant)
+    if constexpr (sizeof(T) == 8) {
+      return __longlong_as_double((long long)raw[k / 4][k % 4]);
+    } else {
+      const uint64_t v = raw[k / 8][(k % 8) / 2];
+      return (double)__uint_as_float((k & 1) ? (uint32_t)(v >> 32) : (uint32_t)v);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    double v = word(c);
+#pragma unroll
+    for (int o = 1; o < WPS; ++o)
+      if (c + o < NS * WPS && off == o) v = word(c + o);
+    r[c] = v;
+  }
+}
+
+// phase 4 of the resampling kernels: gather the kBatch source records, store them, accumulate the fused estimate
+template <typename T, int D, int EST, int NE>
+__device__ __forceinline__ void gather_store(const T* __restrict__ x_in, T* __restrict__ x_out,
+                                             int64_t* __restrict__ idx_out, const int64_t (&src)[kBatch],
+                                             const int64_t (&dst)[kBatch], const int64_t (&idx)[kBatch],
+                                             const bool (&live)[kBatch], double (&acc)[NE]) {
+  if (x_in != nullptr) {
+    double r[kBatch][D];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q)
+      if (live[q]) gather_rec<T, D>(x_in, src[q], r[q]);
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      if (!live[q]) continue;
+      store_rec<T, D>(x_out, dst[q], r[q]);
+      if (idx_out) idx_out[dst[q]] = idx[q];
+      if constexpr (EST == PFB_EST_SUM) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] += r[q][c];
+      } else if constexpr (EST == PFB_EST_TRIG) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double sn, cs;
+          sincos(r[q][c], &sn, &cs);
+          acc[2 * c] += cs;
+          acc[2 * c + 1] += sn;
+        }
+      }
+    }
+  } else if (idx_out) {
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q)
+      if (live[q]) idx_out[dst[q]] = idx[q];
+  }
+}
+
+// deterministic grid reduction of the fused estimate: per-CTA partials, the last CTA sums them in a fixed order
+template <int NE>
+__device__ __forceinline__ void finish_estimate(double (&acc)[NE], double* red, Workspace ws, double* est_out,
+                                                int64_t n_out) {
+  block_sum<NE>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
+  }
+  if (block_is_last(ws.counters)) {
+    double t[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) t[k] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)b * kPartialDoubles + k];
+    }
+    block_sum<NE>(t, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) est_out[k] = t[k] / (double)n_out;
+    }
+  }
+}
+
 template <typename T, int D, int EST>
 __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n_out,
                                                             const double* __restrict__ cdf,
@@ -281,57 +449,90 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
       idx[q] = r;
     }
     // phase 4: gather, store, estimate
-    if (x_in != nullptr) {
-      double r[kBatch][D];
+    int64_t src[kBatch], dst[kBatch];
 #pragma unroll
-      for (int q = 0; q < kBatch; ++q)
-        if (live[q]) load_rec<T, D>(x_in, run[q] * run_len + idx[q], r[q]);
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q) {
-        if (!live[q]) continue;
-        const int64_t j = j0 + q * stride;
-        store_rec<T, D>(x_out, j, r[q]);
-        if (idx_out) idx_out[j] = idx[q];
-        if constexpr (EST == PFB_EST_SUM) {
-#pragma unroll
-          for (int c = 0; c < D; ++c) acc[c] += r[q][c];
-        } else if constexpr (EST == PFB_EST_TRIG) {
-#pragma unroll
-          for (int c = 0; c < D; ++c) {
-            double sn, cs;
-            sincos(r[q][c], &sn, &cs);
-            acc[2 * c] += cs;
-            acc[2 * c + 1] += sn;
-          }
-        }
-      }
-    } else if (idx_out) {
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q)
-        if (live[q]) idx_out[j0 + q * stride] = idx[q];
+    for (int q = 0; q < kBatch; ++q) {
+      src[q] = run[q] * run_len + idx[q];
+      dst[q] = j0 + q * stride;
     }
+    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, src, dst, idx, live, acc);
   }
-  if constexpr (EST != PFB_EST_NONE) {
-    block_sum<NE>(acc, red);
-    if (threadIdx.x == 0) {
+  if constexpr (EST != PFB_EST_NONE) finish_estimate<NE>(acc, red, ws, est_out, n_out);
+}
+
+// multinomial resampling through the bucket records (one run, uniforms from memory or from Philox)
+template <typename T, int D, int EST>
+__global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64_t n_out,
+                                                                const double* __restrict__ cdf,
+                                                                const double* __restrict__ u,
+                                                                const T* __restrict__ x_in, T* __restrict__ x_out,
+                                                                int64_t* __restrict__ idx_out, double* est_out,
+                                                                Workspace ws, const uint4* __restrict__ recs,
+                                                                int64_t M, RngKey key) {
+  constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
+  __shared__ double red[NE * 32];
+  const bool use_rng = (u == nullptr);
+  const double dM = (double)M;
+  const double total = __ldg(cdf + n - 1);
+  double acc[NE];
 #pragma unroll
-      for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
+  for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n_out; j0 += stride * kBatch) {
+    double uj[kBatch];
+    bool live[kBatch];
+    int64_t dst[kBatch], bkt[kBatch];
+    uint32_t p2[kBatch];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      dst[q] = j0 + q * stride;
+      live[q] = dst[q] < n_out;
+      if (!live[q]) uj[q] = 0.0;
+      else if (use_rng) { const uint4 r = rng_block(key, (uint64_t)dst[q], 7u); uj[q] = u53(r.x, r.y); }
+      else uj[q] = __ldg(u + dst[q]);
+      const double ub = uj[q] * dM;  // exact (M is a power of two), u in [0, 1)
+      bkt[q] = (int64_t)ub;
+      const uint32_t p = (uint32_t)((ub - (double)bkt[q]) * 65536.0);
+      p2[q] = p | (p << 16);
     }
-    if (block_is_last(ws.counters)) {
-      double t[NE];
+    uint64_t rec[kBatch][2][4];
 #pragma unroll
-      for (int k = 0; k < NE; ++k) t[k] = 0.0;
-      for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-#pragma unroll
-        for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)b * kPartialDoubles + k];
-      }
-      block_sum<NE>(t, red);
-      if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NE; ++k) est_out[k] = t[k] / (double)n_out;
-      }
+    for (int q = 0; q < kBatch; ++q) {
+      const uint4* r = recs + bkt[q] * 4;
+      ld_sector(r, rec[q][0]);
+      ld_sector(r + 2, rec[q][1]);
     }
+    int64_t idx[kBatch];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      uint32_t w[16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        w[2 * k] = (uint32_t)rec[q][k / 4][k % 4];
+        w[2 * k + 1] = (uint32_t)(rec[q][k / 4][k % 4] >> 32);
+      }
+      const int32_t base = (int32_t)w[0];
+      const uint32_t cnt = w[1] & 0xFFFFu;
+      uint32_t below = __vcmpltu2(w[1], p2[q]) & 0xFFFF0000u;
+      uint32_t eq = __vcmpeq2(w[1], p2[q]) & 0xFFFF0000u;
+      int nb = __popc(below);
+#pragma unroll
+      for (int k = 2; k < 16; ++k) {
+        nb += __popc(__vcmpltu2(w[k], p2[q]));
+        eq |= __vcmpeq2(w[k], p2[q]);
+      }
+      int64_t r = (int64_t)base + (nb >> 4);
+      if (eq != 0u || cnt > (uint32_t)kRecEntries) {  // a tie in the 16-bit grid, or a crowded bucket: exact search
+        int64_t hi = (int64_t)base + cnt;
+        if (cnt == 65535u) hi = (int64_t)(int32_t)__ldg(&recs[(bkt[q] + 1) * 4].x);
+        r = search_range<true>(cdf, (int64_t)base, hi, total, uj[q]);
+      }
+      if (r > n - 1) r = n - 1;
+      idx[q] = r;
+    }
+    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, idx, dst, idx, live, acc);
   }
+  if constexpr (EST != PFB_EST_NONE) finish_estimate<NE>(acc, red, ws, est_out, n_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -639,6 +840,28 @@ static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, do
 }
 
 template <typename T, int D>
+static int launch_resample_rec(int64_t n, int64_t n_out, const double* cdf, const double* u, const void* x_in,
+                               void* x_out, int64_t* idx_out, int est_kind, double* est_out, Workspace W,
+                               cudaStream_t st, const uint4* recs, int64_t M, RngKey key) {
+  const int grid = stream_grid(n_out);
+  switch (est_kind) {
+    case PFB_EST_NONE:
+      resample_rec_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      break;
+    case PFB_EST_SUM:
+      resample_rec_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      break;
+    case PFB_EST_TRIG:
+      resample_rec_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      break;
+    default:
+      set_error("bad est_kind %d", est_kind);
+      return PFB_ERR_INVALID;
+  }
+  return PFB_OK;
+}
+
+template <typename T, int D>
 static int launch_resample(int64_t n, int64_t n_out, const double* cdf, const double* u, int systematic,
                            const double* stats, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
                            double* est_out, Workspace W, cudaStream_t st, const int32_t* guide, int64_t M, RngKey key,
@@ -684,7 +907,7 @@ extern "C" const char* pfb_last_error(void) { return g_err; }
 
 extern "C" int64_t pfb_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  int64_t b = guide_offset(n) + (guide_buckets(n) + 2) * (int64_t)sizeof(int32_t);
+  int64_t b = pfb::rec_offset(n) + pfb::rec_bytes(n);
   return (b + 255) & ~(int64_t)255;
 }
 
@@ -713,6 +936,18 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
     PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, 0.0, 0.0, 0.0, u, key, u ? 1 : 2, 0, n_out, n_out, x_in, x_out, idx_out, est_kind, est_out, W, st))));
     if (rc) return rc;
     PFB_LAUNCH_OK("systematic_scatter_kernel");
+    return PFB_OK;
+  }
+  if (bucket_records_enabled() && rec_buckets(n) <= W.guide_buckets) {
+    const int64_t Mr = rec_buckets(n);  // the int32 guide of the Mr buckets is scratch for the record build
+    uint4* recs = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ws) + rec_offset(n));
+    guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, n);
+    PFB_LAUNCH_OK("guide_kernel");
+    bucket_record_kernel<<<stream_grid(Mr + 1, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, recs);
+    PFB_LAUNCH_OK("bucket_record_kernel");
+    PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(n, n_out, cdf, u, x_in, x_out, idx_out, est_kind, est_out, W, st, recs, Mr, key))));
+    if (rc) return rc;
+    PFB_LAUNCH_OK("resample_rec_kernel");
     return PFB_OK;
   }
   const double* stats_total = cdf + (n - 1);

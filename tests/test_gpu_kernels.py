@@ -306,8 +306,15 @@ def test_scan_adversarial_dynamic_range(eng):
     assert eng.scan_error_flags() == 0
 
 
+@pytest.fixture(params=["1", "0"], ids=["bucket_records", "guide_window"])
+def lookup_path(request, monkeypatch):
+    """multinomial resampling has two index-lookup structures (pfb_resample.cu); PFB_BUCKET_RECORDS is read per call"""
+    monkeypatch.setenv("PFB_BUCKET_RECORDS", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_resample_gather_and_estimates(eng, golden, dtype):
+def test_resample_gather_and_estimates(eng, golden, dtype, lookup_path):
     from pyrecest_b200 import _lib as L
 
     g = golden("torus_t3")
@@ -342,7 +349,7 @@ def test_resample_gather_and_estimates(eng, golden, dtype):
     np.testing.assert_allclose(host(est), g["est"][0], rtol=RTOL64 if dtype == torch.float64 else RTOL32)
 
 
-def test_sample_n_not_equal_N_and_systematic(eng, golden):
+def test_sample_n_not_equal_N_and_systematic(eng, golden, lookup_path):
     g = golden("dirac_moments")
     w, u = g["w"], g["tor_sample_u"]
     N = w.shape[0]
@@ -544,3 +551,50 @@ def test_fresh_engine_workspace_fits_every_call(n):
     e.scan(cdf, logw=logw, exact=True)
     w = np.exp(host(logw) - host(logw).max())
     np.testing.assert_allclose(host(cdf), np.cumsum(w), rtol=1e-13)
+
+
+def test_resample_lookup_adversarial(eng, lookup_path):
+    """crowded buckets (more entries than a bucket record holds, more than its 16-bit count), heavy particles
+    spanning many buckets, and uniforms that sit exactly on / next to normalised CDF values (searchsorted ties)"""
+    rng = np.random.default_rng(11)
+    parts = [rng.random(5000) + 0.5, np.full(200, 1e-9), [800.0], np.full(70_000, 1e-13), rng.random(3000),
+             np.full(40, 2.0 ** -30), [0.0, 0.0, 0.0], rng.random(20_000) * 1e-3, [2500.0], rng.random(1000)]
+    w = np.concatenate([np.asarray(p, dtype=np.float64) for p in parts])
+    n = w.shape[0]
+    c = np.cumsum(w)
+    v = c / c[-1]
+    pick = rng.integers(0, n, 20_000)
+    u = np.concatenate([rng.random(100_000), v[pick], np.nextafter(v[pick], 0.0), np.nextafter(v[pick], 2.0),
+                        [0.0, np.nextafter(1.0, 0.0)], (np.arange(4096) + 0.0) / 4096.0])
+    u = u[u < 1.0]
+    ref = np.minimum(np.searchsorted(v, u, side="right"), n - 1)
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    assert np.array_equal(host(cdf), c)
+    idx = torch.empty(u.shape[0], dtype=torch.int64, device="cuda:0")
+    eng.resample(cdf, dev(u), None, None, u.shape[0], 1, idx_out=idx)
+    assert np.array_equal(host(idx), ref)
+    x = dev(rng.normal(size=(n, 3)))
+    out = torch.empty((u.shape[0], 3), dtype=torch.float64, device="cuda:0")
+    eng.resample(cdf, dev(u), x, out, u.shape[0], 3)
+    assert np.array_equal(host(out), host(x)[ref])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("dim", [1, 2, 3, 4, 5, 6])
+def test_resample_gather_every_record_size(eng, dtype, dim):
+    """the gather reads sector-aligned spans and picks the record out of them: every (dtype, dim) alignment"""
+    rng = np.random.default_rng(dim)
+    n = 10_007
+    w = rng.random(n)
+    u = rng.random(30_011)
+    c = np.cumsum(w)
+    ref = np.minimum(np.searchsorted(c / c[-1], u, side="right"), n - 1)
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    xs = dev(rng.normal(size=(n + 3, dim)), dtype)
+    for shift in (0, 1, 3):  # views that start at odd record offsets inside the allocation
+        x = xs[shift:shift + n]
+        out = torch.empty((u.shape[0], dim), dtype=dtype, device="cuda:0")
+        eng.resample(cdf, dev(u), x, out, u.shape[0], dim)
+        assert np.array_equal(host(out), host(x)[ref])
