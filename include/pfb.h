@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 2
+#define PFB_ABI_VERSION 3
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -76,8 +76,17 @@ typedef struct {
   uint64_t rng_seed;
   uint64_t rng_offset;
   double rng_kappa[PFB_MAXD]; /* PFB_RNG_VONMISES: concentration per dimension */
-  double rng_vm_r[PFB_MAXD];  /* PFB_RNG_VONMISES: Best-Fisher constant r(kappa) per dimension (host-computed) */
+  double rng_vm_area[PFB_MAXD];  /* PFB_RNG_VONMISES: hat area A of the dimension's strip table (pfb_vm_strip_table) */
+  const double* rng_vm_table_dev; /* device pointer: strip tables, PFB_VM_STRIPS x (start, width) doubles each */
+  int32_t rng_vm_table_idx[PFB_MAXD]; /* which table of rng_vm_table_dev each dimension uses (equal kappas share) */
 } pfb_predict_params;
+
+/* von Mises draws use vertical-strip rejection: [0, pi] is cut into PFB_VM_STRIPS strips under a piecewise-
+ * constant hat of equal areas A, so that one Philox block gives strip, position, acceptance uniform and sign, and
+ * a draw is rejected with probability ~1/2000 only.  pfb_vm_strip_table (host code, no GPU) fills
+ * table[2k] = start a_k, table[2k+1] = width w_k and *area = A for one concentration kappa >= 1e-8. */
+#define PFB_VM_STRIPS 4096
+int pfb_vm_strip_table(double kappa, double* table, double* area);
 
 typedef enum {
   PFB_RNG_NONE = 0,

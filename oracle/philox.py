@@ -61,3 +61,69 @@ def normals(seed, offset, n, D):
         if c + 1 < D:
             out[:, c + 1] = rad * np.sin(2 * np.pi * u2)
     return out
+
+
+VM_STRIPS = 4096
+
+
+def vm_strip_table(kappa, K=VM_STRIPS):
+    """numpy restatement of pfb_vm_strip_table (pfb_predict_loglik.cu): K strips [a_k, a_k + w_k) of [0, pi] whose
+    hats g(a_k) w_k, g(t) = exp(-2 kappa sin^2(t/2)), share the area A -- the smallest A whose K-th strip reaches pi"""
+
+    def end(A, table=None):
+        a = 0.0
+        for k in range(K):
+            with np.errstate(divide="ignore"):  # g underflows far in the tail of a sharp density: w = inf, clipped
+                w = A / np.exp(-2.0 * kappa * np.sin(0.5 * a) ** 2)
+            if table is not None:
+                if not a < np.pi:
+                    a, w = np.pi, 0.0
+                elif not (a + w < np.pi) or k == K - 1:
+                    w = np.pi - a
+                table[k] = (a, w)
+            elif not (a + w < np.pi):
+                return 4.0
+            a += w
+        return a
+
+    lo, hi = 0.0, float(np.pi)
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if mid <= lo or mid >= hi:
+            break
+        if end(mid) >= np.pi:
+            hi = mid
+        else:
+            lo = mid
+    table = np.zeros((K, 2))
+    end(hi, table)
+    return table, hi
+
+
+def vonmises(seed, offset, n, kappas, tables):
+    """the zero-mean von Mises draws of PFB_RNG_VONMISES, (n, D): vertical-strip rejection, one Philox block
+    (slot 16 + c + 8 attempt) per attempt.  tables: {kappa: (table, A)}.  The acceptance test is the fp64 one (the
+    kernel decides in fp32 only where fp32 cannot get it wrong)."""
+    D = len(kappas)
+    out = np.empty((n, D))
+    idx = np.arange(n, dtype=np.uint64)
+    for c, kap in enumerate(kappas):
+        pending = np.arange(n)
+        attempt = 0
+        while pending.size:
+            r = rng_block(seed, offset, idx[pending], 16 + c + 8 * attempt)
+            u = u53(r[:, 1], r[:, 2])
+            if kap < 1e-8:
+                th = np.pi * u
+                acc = np.ones(pending.size, dtype=bool)
+            else:
+                table, A = tables[kap]
+                t = table[r[:, 0] >> np.uint32(20)]
+                th = t[:, 0] + u * t[:, 1]
+                v = (r[:, 3].astype(np.float64) + 0.5) * 2.0**-32
+                acc = v * A < np.exp(-2.0 * kap * np.sin(0.5 * th) ** 2) * t[:, 1]
+            sign = (r[:, 0] & np.uint32(1)).astype(bool)
+            out[pending[acc], c] = np.where(sign[acc], th[acc], -th[acc])
+            pending = pending[~acc]
+            attempt += 1
+    return out

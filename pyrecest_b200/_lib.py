@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 2
+ABI_VERSION = 3
+VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
 # predict modes
@@ -38,20 +39,23 @@ class PredictParams(C.Structure):
         ("A", C.c_double * (PFB_MAXD * PFB_MAXD)), ("mu_noise", C.c_double * PFB_MAXD),
         ("kappa", C.c_double), ("exp_m2k", C.c_double),
         ("rng_kind", C.c_int32), ("reserved", C.c_int32), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
-        ("rng_kappa", C.c_double * PFB_MAXD), ("rng_vm_r", C.c_double * PFB_MAXD),
+        ("rng_kappa", C.c_double * PFB_MAXD), ("rng_vm_area", C.c_double * PFB_MAXD),
+        ("rng_vm_table_dev", C.c_void_p), ("rng_vm_table_idx", C.c_int32 * PFB_MAXD),
     ]
 
-    def set_von_mises_rng(self, kappas):
-        """per-dimension concentration + the Best-Fisher constant r = (1 + rho^2) / (2 rho)"""
-        import math
-
+    def set_von_mises_rng(self, kappas, device="cuda:0"):
+        """per-dimension concentration + the strip tables of the in-kernel sampler (pfb_vm_strip_table), uploaded
+        once per (set of kappas, device) and shared between dimensions of equal kappa"""
+        kappas = [float(k) for k in kappas]
+        distinct = sorted({k for k in kappas if k >= 1e-8})
+        tables = vm_tables_on_device(tuple(distinct), str(device)) if distinct else None
         for c, k in enumerate(kappas):
-            k = float(k)
             self.rng_kappa[c] = k
             if k >= 1e-8:
-                tau = 1.0 + math.sqrt(1.0 + 4.0 * k * k)
-                rho = (tau - math.sqrt(2.0 * tau)) / (2.0 * k)
-                self.rng_vm_r[c] = (1.0 + rho * rho) / (2.0 * rho)
+                self.rng_vm_table_idx[c] = distinct.index(k)
+                self.rng_vm_area[c] = vm_strip_table(k)[1]
+        self.rng_vm_table_dev = tables.data_ptr() if tables is not None else None
+        self._vm_tables = tables  # keeps the device memory alive as long as the params
 
 
 class LikParams(C.Structure):
@@ -92,6 +96,7 @@ SIGNATURES = {
     "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
+    "pfb_vm_strip_table": (C.c_int, [C.c_double, _vp, _vp]),
 }
 
 _LIB = None
@@ -131,6 +136,36 @@ def lib():
             raise PfbError("libpfb ABI version mismatch")
         _LIB = handle
     return _LIB
+
+
+_VM_HOST = {}
+_VM_DEV = {}
+
+
+def vm_strip_table(kappa: float):
+    """(table (VM_STRIPS, 2) float64 [start, width], hat area A) for one kappa >= 1e-8; host code of libpfb"""
+    import numpy as np
+
+    kappa = float(kappa)
+    if kappa not in _VM_HOST:
+        table = np.zeros((VM_STRIPS, 2), dtype=np.float64)
+        area = C.c_double()
+        check(lib().pfb_vm_strip_table(kappa, table.ctypes.data, C.addressof(area)))
+        _VM_HOST[kappa] = (table, area.value)
+    return _VM_HOST[kappa]
+
+
+def vm_tables_on_device(kappas: tuple, device: str):
+    import numpy as np
+    import torch
+
+    key = (kappas, device)
+    if key not in _VM_DEV:
+        host = np.stack([vm_strip_table(k)[0] for k in kappas])
+        _VM_DEV[key] = torch.as_tensor(host, device=device).contiguous()
+        if len(_VM_DEV) > 64:
+            _VM_DEV.pop(next(iter(_VM_DEV)))
+    return _VM_DEV[key]
 
 
 def check(rc: int):

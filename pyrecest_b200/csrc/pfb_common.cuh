@@ -130,61 +130,52 @@ __device__ __forceinline__ void normal_pair(const uint4& r, double* z0, double* 
   *z0 = rad * cs;
   *z1 = rad * sn;
 }
-// Zero-mean von Mises draws in [-pi, pi] for D dimensions at once (Best & Fisher 1979: wrapped-Cauchy
-// envelope, rejection).  rr = (1 + rho^2)/(2 rho), rho = (tau - sqrt(2 tau))/(2 kappa),
-// tau = 1 + sqrt(1 + 4 kappa^2) comes from the host.  The accept/reject decision is evaluated in fp32 (it only
-// shapes the acceptance probability, to ~1e-6 relative); the accepted proposal (a 32-bit uniform, i.e. an
-// angle grid of 7e-10 rad) is then mapped to the angle in fp64.  All dimensions share one loop (a lane works on
-// its lowest unfinished dimension) so that a warp pays max-over-lanes of the SUM of attempts, not the sum
-// of per-dimension maxima.
+// Zero-mean von Mises draws in (-pi, pi) for D dimensions at once: vertical-strip rejection.  g(t) =
+// exp(kappa (cos t - 1)) is decreasing on [0, pi]; the host cuts [0, pi] into PFB_VM_STRIPS strips [a_k, a_k + w_k)
+// whose hats g(a_k) w_k all have the same area A (pfb_vm_strip_table).  One Philox block is one attempt:
+//   word 0: strip k (top 12 bits) and the sign (bit 0);  words 1-2: 53-bit position u, t = a_k + u w_k;
+//   word 3: acceptance uniform v in (0, 1): accept iff v A < g(t) w_k.
+// ~99.95 % of the attempts are accepted, so a warp almost never loops (the wrapped-Cauchy rejection it replaces
+// accepted ~2/3 and cost three times the instructions through divergence).  The test is decided in fp32 when it
+// is clear of the fp32 error bound and in fp64 otherwise, so the decision is the fp64 one (oracle/philox.py).
 template <int D>
-__device__ __forceinline__ void vonmises_draws(const RngKey& k, uint64_t index, const double* kappa,
-                                               const double* rr, double (&out)[D]) {
-  // phase 1 (divergent, fp32 + integer only): find the accepted proposal of every dimension.  One Philox
-  // block carries two attempts: (32-bit proposal, 24-bit acceptance uniform, sign bit) each.
-  uint32_t u_acc[D];
-  uint32_t sign_acc = 0;
-  uint32_t call = 0;
-  int c = 0;
-  while (c < D) {
-    const uint4 r = rng_block(k, index, 16u + call);
-    ++call;
+__device__ __forceinline__ void vonmises_draws(const RngKey& k, uint64_t index, const pfb_predict_params& p,
+                                               double (&out)[D]) {
+  uint32_t pending = (1u << D) - 1u;
+  for (uint32_t attempt = 0; pending != 0u; ++attempt) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (c < D) {
-        const uint32_t w1 = half ? r.z : r.x, w2 = half ? r.w : r.y;
-        const float kf = (float)kappa[c], rf = (float)rr[c];
-        bool accept = true;
-        if (kf >= 1e-8f) {
-          const float zf = cospif(((float)w1 + 0.5f) * 2.3283064365386963e-10f);
-          const float ff = (1.0f + rf * zf) / (rf + zf);
-          const float cf = kf * (rf - ff);
-          const float u2 = ((float)(w2 >> 8) + 0.5f) * 5.9604644775390625e-08f;
-          accept = (cf * (2.0f - cf) - u2 > 0.0f) || (__logf(cf / u2) + 1.0f - cf >= 0.0f) || call >= 64u;
+    for (int c = 0; c < D; ++c) {
+      if (!((pending >> c) & 1u)) continue;
+      const uint4 r = rng_block(k, index, 16u + (uint32_t)c + 8u * attempt);
+      const double u = u53(r.y, r.z);
+      const double kap = p.rng_kappa[c];
+      double th;
+      bool accept = true;
+      if (kap < 1e-8) {
+        th = 3.141592653589793 * u;  // uniform on the circle
+      } else {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p.rng_vm_table_dev) +
+                                (int64_t)p.rng_vm_table_idx[c] * PFB_VM_STRIPS + (r.x >> 20));
+        th = t.x + u * t.y;
+        const float kf = (float)kap;
+        const float sh = sinf(0.5f * (float)th);
+        const float rhs = __expf(-2.0f * kf * sh * sh) * (float)t.y;
+        const float lhs = ((float)r.w + 0.5f) * 2.3283064365386963e-10f * (float)p.rng_vm_area[c];
+        const float margin = (4e-6f * kf + 8e-6f) * rhs;
+        if (lhs > rhs + margin) {
+          accept = false;
+        } else if (lhs >= rhs - margin) {  // too close for fp32
+          const double sd = sin(0.5 * th);
+          const double vd = ((double)r.w + 0.5) * 2.3283064365386963e-10;
+          accept = vd * p.rng_vm_area[c] < exp(-2.0 * kap * sd * sd) * t.y;
         }
-        if (accept) {
-#pragma unroll
-          for (int cc = 0; cc < D; ++cc)
-            if (cc == c) u_acc[cc] = w1;  // (static indices keep the array in registers)
-          sign_acc |= (w2 & 1u) << c;
-          ++c;
-        }
+        if (attempt >= 64u) accept = true;  // unreachable in practice (rejection probability ~5e-4 per attempt)
+      }
+      if (accept) {
+        out[c] = (r.x & 1u) ? th : -th;
+        pending &= ~(1u << c);
       }
     }
-  }
-  // phase 2 (uniform, fp64): proposal -> angle
-#pragma unroll
-  for (int cc = 0; cc < D; ++cc) {
-    const double u1 = ((double)u_acc[cc] + 0.5) * 2.3283064365386963e-10;  // (0, 1), 32-bit grid
-    double th;
-    if (kappa[cc] < 1e-8) {
-      th = 3.141592653589793 * u1;  // uniform on the circle: |theta| uniform in (0, pi), sign below
-    } else {
-      const double z = cospi(u1);
-      const double f = (1.0 + rr[cc] * z) / (rr[cc] + z);
-      th = acos(fmin(1.0, fmax(-1.0, f)));
-    }
-    out[cc] = ((sign_acc >> cc) & 1u) ? th : -th;
   }
 }
 

@@ -4,6 +4,9 @@
 // whatever the storage type.  Operation order follows oracle/pf_oracle.py so that the pure
 // add / numpy.mod paths are bit-exact (the library is compiled with -fmad=false; the fused
 // multiply-adds that are wanted are written explicitly).
+#include <mutex>
+#include <unordered_map>
+
 #include "pfb_common.cuh"
 
 namespace pfb {
@@ -32,12 +35,16 @@ __device__ __forceinline__ void apply_transition(const pfb_predict_params& p, co
   }
 }
 
-// noise row in state space: rows as given, or z A (+ mu) for standard-normal input
-template <typename T, int D>
+// noise row in state space: rows as given, or z A (+ mu) for standard-normal input.  RNG: the draws come from the
+// in-kernel generator (p.rng_kind); a compile-time switch, so that the array-fed kernels do not carry the
+// samplers' registers.
+template <typename T, int D, bool RNG>
 __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T* __restrict__ noise,
                                            int64_t i, double (&n)[D]) {
   double z[D];
-  if (p.rng_kind == PFB_RNG_NORMAL) {
+  if constexpr (!RNG) {
+    load_rec<T, D>(noise, i, z);
+  } else if (p.rng_kind == PFB_RNG_NORMAL) {
     const RngKey key{p.rng_seed, p.rng_offset};
 #pragma unroll
     for (int c = 0; c < D; c += 2) {
@@ -48,12 +55,10 @@ __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T*
     }
   } else if (p.rng_kind == PFB_RNG_VONMISES) {
     const RngKey key{p.rng_seed, p.rng_offset};
-    vonmises_draws<D>(key, (uint64_t)i, p.rng_kappa, p.rng_vm_r, z);
-  } else {
-    load_rec<T, D>(noise, i, z);
+    vonmises_draws<D>(key, (uint64_t)i, p, z);
   }
-  if constexpr (sizeof(T) == 4) {
-    if (p.rng_kind != PFB_RNG_NONE) {
+  if constexpr (sizeof(T) == 4 && RNG) {
+    {
 #pragma unroll
       for (int c = 0; c < D; ++c) z[c] = (double)(float)z[c];  // what an fp32 noise array would have held
     }
@@ -76,17 +81,17 @@ __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T*
   }
 }
 
-template <typename T, int D, int MODE>
+template <typename T, int D, int MODE, bool RNG>
 __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T* __restrict__ x_in,
                                             const T* __restrict__ noise, int64_t i, double (&out)[D]) {
   double x[D], y[D];
   load_rec<T, D>(x_in, i, x);
   apply_transition<D>(p, x, y);
-  const bool has_noise = (noise != nullptr || p.rng_kind != PFB_RNG_NONE) && p.noise_cols > 0;
+  const bool has_noise = (noise != nullptr || RNG) && p.noise_cols > 0;
   if constexpr (MODE == PFB_PRED_EUCLID) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D>(p, noise, i, n);
+      load_noise<T, D, RNG>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) out[c] = y[c] + n[c];
     } else {
@@ -96,7 +101,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else if constexpr (MODE == PFB_PRED_TORUS_SHIFT) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D>(p, noise, i, n);
+      load_noise<T, D, RNG>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
@@ -110,7 +115,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else if constexpr (MODE == PFB_PRED_TORUS_ADD) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D>(p, noise, i, n);          // includes the (host-wrapped) noise mean
+      load_noise<T, D, RNG>(p, noise, i, n);          // includes the (host-wrapped) noise mean
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         double s = np_mod_2pi(n[c]);
@@ -124,7 +129,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
     static_assert(D == 3 || MODE != PFB_PRED_SPHERE_VMF, "VMF noise is implemented on S^2");
     if (has_noise) {
       double t[D];
-      if (p.rng_kind == PFB_RNG_VMF) {
+      if constexpr (RNG) {
         const RngKey key{p.rng_seed, p.rng_offset};
         const uint4 r0 = rng_block(key, (uint64_t)i, 0u);
         t[0] = u53(r0.x, r0.y);
@@ -175,7 +180,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else {  // PFB_PRED_SPHERE_ADD
     double n[D];
     if (has_noise) {
-      load_noise<T, D>(p, noise, i, n);
+      load_noise<T, D, RNG>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) y[c] += n[c];
     }
@@ -337,14 +342,14 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-template <typename T, int D, int MODE>
+template <typename T, int D, int MODE, bool RNG>
 __global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p, int64_t n,
                                                            const T* __restrict__ x_in, T* x_out,
                                                            const T* __restrict__ noise) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     double out[D];
-    predict_one<T, D, MODE>(p, x_in, noise, i, out);
+    predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
   }
 }
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
   });
 }
 
-template <typename T, int D, int MODE, int KIND>
+template <typename T, int D, int MODE, int KIND, bool RNG>
 __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* __restrict__ x_in, T* x_out,
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_pa
   const double* images = stage_images<D>(L, smem_dyn);
   weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double out[D];
-    predict_one<T, D, MODE>(p, x_in, noise, i, out);
+    predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
     if constexpr (sizeof(T) == 4) {
       // weight what was stored (the fp32 particle), as a separate pfb_loglik call would
@@ -521,6 +526,59 @@ static int check_predict(const pfb_predict_params* p) {
   if (p->mode == PFB_PRED_SPHERE_VMF && p->dim != 3) { set_error("VMF noise needs dim 3 (S^2), got %d", p->dim); return PFB_ERR_UNSUPPORTED; }
   if (p->noise_cols != 0 && p->noise_cols != p->dim) { set_error("noise_cols %d must equal dim %d", p->noise_cols, p->dim); return PFB_ERR_INVALID; }
   if (p->mode == PFB_PRED_SPHERE_VMF && p->noise_cols && !(p->kappa > 0.0)) { set_error("kappa must be > 0"); return PFB_ERR_INVALID; }
+  if (p->rng_kind < PFB_RNG_NONE || p->rng_kind > PFB_RNG_VMF) { set_error("bad rng_kind %d", p->rng_kind); return PFB_ERR_INVALID; }
+  if (p->rng_kind != PFB_RNG_NONE && (p->rng_kind == PFB_RNG_VMF) != (p->mode == PFB_PRED_SPHERE_VMF)) {
+    set_error("rng_kind %d does not go with predict mode %d (VMF triples <-> PFB_PRED_SPHERE_VMF)", p->rng_kind, p->mode);
+    return PFB_ERR_INVALID;
+  }
+  if (p->rng_kind == PFB_RNG_VONMISES) {
+    for (int c = 0; c < p->dim; ++c) {
+      if (!(p->rng_kappa[c] >= 0.0)) { set_error("von Mises kappa[%d] must be >= 0", c); return PFB_ERR_INVALID; }
+      if (p->rng_kappa[c] < 1e-8) continue;
+      if (!p->rng_vm_table_dev || !(p->rng_vm_area[c] > 0.0) || p->rng_vm_table_idx[c] < 0 || p->rng_vm_table_idx[c] >= PFB_MAXD) {
+        set_error("von Mises draws need the strip table of kappa[%d] (pfb_vm_strip_table) on the device", c);
+        return PFB_ERR_INVALID;
+      }
+    }
+  }
+  return PFB_OK;
+}
+
+// Strip table of the von Mises sampler (pfb_common.cuh: vonmises_draws).  With g(t) = exp(-2 kappa sin^2(t/2)):
+// a_0 = 0, a_{k+1} = a_k + A / g(a_k); A is the smallest area for which the K-th strip reaches pi (bisection:
+// the end point is increasing in A), and the last strip is clipped to pi, which only raises its hat.
+static double vm_strip_end(double kappa, double A, int K, double* table) {
+  const double kPiH = 3.141592653589793;
+  double a = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double sh = sin(0.5 * a);
+    double w = A / exp(-2.0 * kappa * sh * sh);
+    if (table) {  // fill mode: clip at pi (a strip past pi keeps zero width: it is chosen and always rejected)
+      if (!(a < kPiH)) { a = kPiH; w = 0.0; }
+      else if (!(a + w < kPiH) || k == K - 1) w = kPiH - a;
+      table[2 * k] = a;
+      table[2 * k + 1] = w;
+    } else if (!(a + w < kPiH)) {
+      return 4.0;  // reaches pi (at the last strip: just enough; earlier: A is larger than needed)
+    }
+    a += w;
+  }
+  return a;
+}
+
+extern "C" int pfb_vm_strip_table(double kappa, double* table, double* area) {
+  if (!table || !area) { set_error("NULL table / area"); return PFB_ERR_INVALID; }
+  if (!(kappa >= 1e-8) || !(kappa < 1e300)) { set_error("strip tables exist for 1e-8 <= kappa < inf (smaller kappas draw uniformly)"); return PFB_ERR_INVALID; }
+  const double kPiH = 3.141592653589793;
+  const int K = PFB_VM_STRIPS;
+  double lo = 0.0, hi = kPiH;  // end(lo) = 0 < pi <= end(hi)
+  for (int it = 0; it < 200 && lo < hi; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    if (vm_strip_end(kappa, mid, K, nullptr) >= kPiH) hi = mid; else lo = mid;
+  }
+  vm_strip_end(kappa, hi, K, table);
+  *area = hi;
   return PFB_OK;
 }
 
@@ -569,11 +627,15 @@ extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t
   if (!x_in || !x_out) { set_error("NULL particle pointer"); return PFB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = stream_grid(n);
+  const bool rng = p->rng_kind != PFB_RNG_NONE;
   PFB_DISPATCH_DTYPE(dtype, {
     if (p->mode == PFB_PRED_SPHERE_VMF) {
-      predict_kernel<T, 3, PFB_PRED_SPHERE_VMF><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
+      if (rng) predict_kernel<T, 3, PFB_PRED_SPHERE_VMF, true><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
+      else predict_kernel<T, 3, PFB_PRED_SPHERE_VMF, false><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
+    } else if (rng) {
+      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE, true><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
     } else {
-      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
+      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE, false><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
     }
   });
   PFB_LAUNCH_OK("predict_kernel");
@@ -582,6 +644,29 @@ extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t
 
 namespace pfb {
 static int tile_grid_seg(const Seg& sg) { return tile_grid(sg.n_runs * sg.tpr * (int64_t)kScanTile); }
+
+// One wave of CTAs for the tile loops: as many as are resident at once (the kernel's own occupancy), so that no
+// CTA starts when the others are half done.  Cached per kernel.
+template <typename K>
+static int one_wave_grid(K kernel, size_t smem, const Seg& sg) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  int resident;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(reinterpret_cast<const void*>(kernel));
+    if (it == cache.end()) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ < 1) occ = 4;
+      it = cache.emplace(reinterpret_cast<const void*>(kernel), occ * sm_count()).first;
+    }
+    resident = it->second;
+  }
+  const int64_t tiles = sg.n_runs * sg.tpr;
+  int g = resident < kMaxPartialBlocks ? resident : kMaxPartialBlocks;
+  if (tiles < g) g = (int)(tiles < 1 ? 1 : tiles);
+  return g;
+}
 
 static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const void* x, const double* w_prev,
                        double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream) {
@@ -615,8 +700,14 @@ template <typename T, int D, int MODE, int KIND>
 static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* lik, Seg sg, const void* x_in,
                             void* x_out, const void* noise, double* logw, double* stats, Workspace W,
                             cudaStream_t st) {
-  predict_loglik_kernel<T, D, MODE, KIND><<<tile_grid_seg(sg), kThreads, lik_smem(lik), st>>>(
-      *p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  const size_t sm = lik_smem(lik);
+  if (p->rng_kind != PFB_RNG_NONE) {
+    auto k = predict_loglik_kernel<T, D, MODE, KIND, true>;
+    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  } else {
+    auto k = predict_loglik_kernel<T, D, MODE, KIND, false>;
+    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  }
   return PFB_OK;
 }
 

@@ -377,7 +377,7 @@ class HypertoroidalParticleFilter(AbstractParticleFilter):
             kap = np.broadcast_to(kap, (D,)) if kap.shape[0] in (1, D) else kap
             if src.fused:
                 p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VONMISES, src.seed, src.next_offset()
-                p.set_von_mises_rng(np.array(kap, dtype=np.float64).tolist())
+                p.set_von_mises_rng(np.array(kap, dtype=np.float64).tolist(), st.device)
                 z = None
             else:
                 z = src.vonmises((N, D), torch.as_tensor(np.array(kap, dtype=np.float64)), st.device, st.d.dtype)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     lib = L.lib()
-    assert lib.pfb_abi_version() == 2
+    assert lib.pfb_abi_version() == L.ABI_VERSION == 3
     assert lib.pfb_workspace_bytes(0) >= 256
     assert lib.pfb_workspace_bytes(10**8) > lib.pfb_workspace_bytes(0)
 
@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     from pyrecest_b200 import _lib as L
 
-    assert ctypes.sizeof(L.PredictParams) == 8 * 4 + 8 * (36 + 6 + 36 + 6 + 2) + 8 + 16 + 48 + 48
+    assert ctypes.sizeof(L.PredictParams) == 8 * 4 + 8 * (36 + 6 + 36 + 6 + 2) + 8 + 16 + 48 + 48 + 8 + 24
     assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8 + 8
 
 
@@ -159,3 +159,40 @@ def test_bench_reference_arm_runs_on_cpu():
     assert out.returncode == 0, out.stderr
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+@pytest.mark.parametrize("kappa", [1e-8, 0.3, 10.0, 777.0, 1e6])
+def test_vm_strip_table_is_a_valid_equal_area_hat(kappa):
+    """pfb_vm_strip_table (host code of libpfb, no GPU): contiguous strips covering [0, pi], every hat A / w_k above
+    the density on its strip, area equal to the numpy restatement's, rejection probability ~1e-3"""
+    from scipy.special import ive
+
+    from oracle import philox as P
+    from pyrecest_b200 import _lib as L
+
+    table, A = L.vm_strip_table(kappa)
+    a, w = table[:, 0], table[:, 1]
+    assert table.shape == (L.VM_STRIPS, 2) and a[0] == 0.0 and np.all(w >= 0)
+    np.testing.assert_allclose(a[1:], a[:-1] + w[:-1], rtol=0, atol=1e-15)
+    assert abs(a[-1] + w[-1] - np.pi) < 1e-15
+    g = np.exp(-2.0 * kappa * np.sin(0.5 * a) ** 2)  # density at the left (highest) end of each strip
+    assert np.all(A >= g * w * (1 - 1e-12))
+    t_ref, A_ref = P.vm_strip_table(kappa)
+    np.testing.assert_allclose(A, A_ref, rtol=1e-12)
+    np.testing.assert_allclose(table, t_ref, rtol=1e-9, atol=1e-13)
+    efficiency = np.pi * ive(0, kappa) / (L.VM_STRIPS * A)
+    assert 0.998 < efficiency <= 1.0
+
+
+def test_vm_strip_sampler_restatement_is_von_mises():
+    from scipy import stats
+
+    from oracle import philox as P
+    from pyrecest_b200 import _lib as L
+
+    kap = [0.0, 0.7, 25.0]
+    x = P.vonmises(3, 9, 100_000, kap, {k: L.vm_strip_table(k) for k in kap if k >= 1e-8})
+    assert np.abs(x).max() < np.pi
+    assert stats.kstest(x[:, 0], stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue > 1e-4
+    for c in (1, 2):
+        assert stats.kstest(x[:, c], stats.vonmises(kap[c]).cdf).pvalue > 1e-4

@@ -65,6 +65,39 @@ void run(const char* name, const unsigned char* buf, uint64_t sectors, uint64_t 
   printf("%-28s %8.3f ms  %7.1f M reads/ms  (%s)\n", name, ms, n / ms * 1e-6, cudaGetErrorString(cudaGetLastError()));
 }
 
+// footprint / memory-level-parallelism sweep with the default load flavour
+template <int ILP>
+__global__ void probe_ilp(const unsigned char* buf, uint64_t sectors, uint64_t n, uint64_t* out) {
+  uint64_t acc = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride * ILP) {
+    uint64_t v[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) {
+      const uint64_t s = mix((i + k * stride) * 0x9e3779b97f4a7c15ull) % sectors;
+      v[k] = load<0>(buf + s * 32);
+    }
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) acc ^= v[k];
+  }
+  if (acc == 0x1234567) out[0] = acc;
+}
+
+template <int ILP>
+void sweep(const unsigned char* buf, uint64_t bytes, uint64_t n, uint64_t* out, int blocks_per_sm) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  probe_ilp<ILP><<<148 * blocks_per_sm, 256>>>(buf, bytes / 32, n, out);
+  cudaEventRecord(e0);
+  probe_ilp<ILP><<<148 * blocks_per_sm, 256>>>(buf, bytes / 32, n, out);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("footprint %6llu MiB  ilp %d  blocks/SM %2d : %8.3f ms  %6.1f G reads/s\n", (unsigned long long)(bytes >> 20), ILP,
+         blocks_per_sm, ms, n / ms * 1e-6);
+}
+
 int main(int argc, char** argv) {
   if (argc > 1) {
     cudaError_t r = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1]));
@@ -86,5 +119,16 @@ int main(int argc, char** argv) {
   run<7>("2 x nc.v2.u64", buf, sectors, n, out);
   run<8>("nc.u64", buf, sectors, n, out);
   run<9>("cg.u64", buf, sectors, n, out);
+  cudaFree(buf);
+  const uint64_t big = 32ull << 30;
+  cudaMalloc(&buf, big);
+  cudaMemset(buf, 1, big);
+  for (uint64_t fp = 64ull << 20; fp <= big; fp *= 4) {
+    sweep<1>(buf, fp, n, out, 8);
+    sweep<4>(buf, fp, n, out, 8);
+    sweep<4>(buf, fp, n, out, 2);
+  }
+  sweep<1>(buf, big, n, out, 8);
+  sweep<4>(buf, big, n, out, 8);
   return 0;
 }
