@@ -444,11 +444,10 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, 
         logw[run * sg.run_pad + local] = v;
         if (v != v) {
           gnan = 1.0;
-        } else if (v > m) {
-          sacc = sacc * exp(m - v) + 1.0;  // m = -inf: 0 * 0 + 1
-          m = v;
         } else if (v > -INFINITY) {
-          sacc += exp(v - m);
+          const double e = exp(-fabs(v - m));  // one exp for both cases (m = -inf: e = 0, sacc = 0 * 0 + 1)
+          sacc = (v > m) ? sacc * e + 1.0 : sacc + e;
+          m = fmax(m, v);
         }
       } else if (local < sg.run_pad) {
         logw[run * sg.run_pad + local] = -INFINITY;  // padding of a batched run: weight 0

@@ -620,23 +620,48 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
       }
       // stretch of safe tiles [t, t2): all in binade e (a tile that could leave it would be hard)
       int64_t t2 = t;
-      while (true) {  // first hard tile at or after t, kThreads tiles per probe
-        const int64_t cand = t2 + threadIdx.x;
-        const int hit = (cand >= t_end || cls[cand] == kHardTile) ? (int)threadIdx.x : 0x7fffffff;
+      while (true) {  // first hard tile at or after t, kProbe * kThreads tiles per probe (loads issued together)
+        constexpr int kProbe = 8;
+        long long cv[kProbe];
+#pragma unroll
+        for (int q = 0; q < kProbe; ++q) {
+          const int64_t cand = t2 + q * kThreads + threadIdx.x;
+          cv[q] = (cand >= t_end) ? kHardTile : cls[cand];
+        }
+        int hit = 0x7fffffff;
+#pragma unroll
+        for (int q = kProbe - 1; q >= 0; --q)
+          if (cv[q] == kHardTile) hit = q * kThreads + (int)threadIdx.x;
         const int first = block_min_int(hit, s_int);
         if (first != 0x7fffffff) { t2 += first; break; }
-        t2 += kThreads;
+        t2 += kProbe * kThreads;
       }
       const int64_t L = t2 - t;
       const int64_t chunk = (L + kThreads - 1) / kThreads;
       const int64_t c0 = t + (int64_t)threadIdx.x * chunk;
       const int64_t c1 = (c0 + chunk < t2) ? c0 + chunk : t2;
       PMap f; f.e = 0; f.o = 0;
-      for (int64_t j = c0; j < c1; ++j) {
-        if (cls_binade(cls[j]) != e) atomicOr(err, 4u);
-        PMap m; m.e = ts.aggE[j]; m.o = ts.aggO[j];
-        f = pmap_then(f, m);
+      constexpr int kAhead = 4;  // the per-thread walk is a chain of dependent compositions: fetch ahead of it
+      bool binade_ok = true;
+      for (int64_t j = c0; j < c1; j += kAhead) {
+        long long ce[kAhead], ae[kAhead], ao[kAhead];
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q) {
+          const bool in = j + q < c1;
+          ce[q] = in ? cls[j + q] : 0;
+          ae[q] = in ? ts.aggE[j + q] : 0;
+          ao[q] = in ? ts.aggO[j + q] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q) {
+          if (j + q < c1) {
+            binade_ok = binade_ok && cls_binade(ce[q]) == e;
+            PMap m; m.e = ae[q]; m.o = ao[q];
+            f = pmap_then(f, m);
+          }
+        }
       }
+      if (!binade_ok) atomicOr(err, 4u);
       PMap tot;
       const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
       bool ok;
@@ -644,10 +669,22 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
       if (!ok) atomicOr(err, 1u);
       const double u = ulp_value((int)e - 52);
       long long S = pmap_apply(g, S0);
-      for (int64_t j = c0; j < c1; ++j) {
-        cstart[j] = (double)S * u;
-        PMap m; m.e = ts.aggE[j]; m.o = ts.aggO[j];
-        S = pmap_apply(m, S);
+      for (int64_t j = c0; j < c1; j += kAhead) {
+        long long ae[kAhead], ao[kAhead];
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q) {
+          const bool in = j + q < c1;
+          ae[q] = in ? ts.aggE[j + q] : 0;
+          ao[q] = in ? ts.aggO[j + q] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q) {
+          if (j + q < c1) {
+            cstart[j + q] = (double)S * u;
+            PMap m; m.e = ae[q]; m.o = ao[q];
+            S = pmap_apply(m, S);
+          }
+        }
       }
       const long long Send = pmap_apply(tot, S0);
       if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);  // a safe stretch left its binade: bound violated
