@@ -198,6 +198,10 @@ inline int64_t rec_offset(int64_t n) {
   return (guide_offset(n) + (guide_buckets(n) + 2) * (int64_t)sizeof(int32_t) + 255) & ~(int64_t)255;
 }
 inline int64_t rec_bytes(int64_t n) { return (rec_buckets(n) + 2) * 64; }
+static bool two_pass_record_build() {
+  const char* e = getenv("PFB_RECORD_BUILD");  // "2pass": guide_kernel + bucket_record_kernel (kept as a cross-check)
+  return e && e[0] == '2';
+}
 static bool bucket_records_enabled() {
   const char* e = getenv("PFB_BUCKET_RECORDS");  // read per call: the tests run both paths
   return e ? atoi(e) != 0 : true;
@@ -236,6 +240,217 @@ __global__ void __launch_bounds__(kThreads) bucket_record_kernel(int64_t n, cons
     r[2] = make_uint4(w[8], w[9], w[10], w[11]);
     r[3] = make_uint4(w[12], w[13], w[14], w[15]);
   }
+}
+
+// ---- one-pass record build ------------------------------------------------------------------------------
+// guide_kernel + bucket_record_kernel stream the CDF twice and divide twice per element.  This kernel builds the
+// records straight from the CDF, one 2048-element tile per CTA step:
+//   A  every element: bucket b_i = floor(v_i M) and 16-bit in-bucket position q_i into shared memory, plus 32
+//      elements of look-ahead (a record holds at most 29 entries, so the look-ahead always decides between an
+//      exact count <= 29 and "long") and the bucket of the element before the tile;
+//   B  every bucket head (b_i != b_{i-1}) writes its own record -- base i, count, the q of its entries -- and
+//      owns the empty buckets (b_{i-1}, b_i): up to 4 it writes itself, longer gaps go to a queue in shared
+//      memory that the warps drain with coalesced 16-byte stores; gaps above kBigGap buckets (one particle
+//      holding > 4096/M of the weight) are handed to record_fill_kernel, which spreads them over the grid.
+// Long buckets store count 65535: the query then takes its upper search bound from the next record's base.
+constexpr int kRecTile = 2048;
+constexpr int kRecLook = 32;
+constexpr int kBigGap = 4096;
+
+__device__ __forceinline__ void store_empty_record(uint4* __restrict__ recs, int64_t bucket, int32_t base) {
+  uint4* r = recs + bucket * 4;
+  r[0] = make_uint4((uint32_t)base, 0xFFFF0000u, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  r[1] = r[2] = r[3] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+}
+
+__global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n, const double* __restrict__ cdf, int64_t M,
+                                                                uint4* __restrict__ recs, int32_t* __restrict__ jobs,
+                                                                unsigned int* __restrict__ job_count) {
+  constexpr int kE = kRecTile / kThreads;  // elements per thread
+  __shared__ int32_t sb_raw[1 + kRecTile + kRecLook];
+  __shared__ __align__(4) uint16_t sq_raw[4 + kRecTile + kRecLook + 4];
+  __shared__ int32_t s_gap[kRecTile][3];  // (first bucket, length, base) of the medium gaps of this tile
+  __shared__ uint16_t s_head[kRecTile + kRecLook + 2];
+  __shared__ int s_wsum[kThreads / 32];
+  __shared__ int s_ngap;
+  int32_t* sb = sb_raw + 1;  // sb[-1]: bucket of the element before the tile
+  uint16_t* sq = sq_raw + 4;  // (front padding: a record is copied from 3 halfwords before its first entry)
+  const double total = __ldg(cdf + n - 1);
+  const double dM = (double)M;
+  const int64_t ntiles = (n + kRecTile - 1) / kRecTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // b = floor(v M), q = floor((v M - b) 2^16) with v = fl(c/total), i.e. the high and low bits of
+  // floor(A), A = v M 2^16 (an exact scaling of v).  T = c * fl(M 2^16 / total) differs from A by less than
+  // 2^-50 A (three roundings), so floor(T) = floor(A) unless T lies that close to an integer: only then divide.
+  const double scale = __ddiv_rn(dM * 65536.0, total);
+  auto bucket_of = [&](double c, uint32_t* q) -> int32_t {
+    double t = c * scale;
+    long long f = (long long)t;
+    const double fr = t - (double)f;
+    const double tol = t * 8.881784197001252e-16;  // 2^-50
+    if (fr <= tol || 1.0 - fr <= tol) f = (long long)(__ddiv_rn(c, total) * (dM * 65536.0));
+    *q = (uint32_t)f & 0xFFFFu;
+    return (int32_t)(f >> 16);
+  };
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t i0 = tile * kRecTile;
+    const int T = (int)((n - i0 < kRecTile) ? n - i0 : kRecTile);  // elements of this tile
+    if (threadIdx.x == 0) s_ngap = 0;
+    // phase A
+    const int e0 = threadIdx.x * kE;
+    int32_t bmine[kE];
+    {
+      double c[kE];
+      if (i0 + e0 + kE <= n) {
+        const double2* src = reinterpret_cast<const double2*>(cdf + i0 + e0);
+#pragma unroll
+        for (int k = 0; k < kE / 2; ++k) { const double2 v = __ldg(src + k); c[2 * k] = v.x; c[2 * k + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kE; ++k) c[k] = (i0 + e0 + k < n) ? __ldg(cdf + i0 + e0 + k) : total;
+      }
+#pragma unroll
+      for (int k = 0; k < kE; ++k) {
+        uint32_t q;
+        const int32_t b = bucket_of(c[k], &q);
+        bmine[k] = (e0 + k < T) ? b : 0x7fffffff;
+        sb[e0 + k] = bmine[k];
+        sq[e0 + k] = (uint16_t)q;
+      }
+      if (threadIdx.x < kRecLook) {  // look-ahead into the next tile
+        const int64_t i = i0 + kRecTile + threadIdx.x;
+        uint32_t q = 0;
+        const int32_t b = (T == kRecTile && i < n) ? bucket_of(__ldg(cdf + i), &q) : 0x7fffffff;
+        sb[kRecTile + threadIdx.x] = b;
+        sq[kRecTile + threadIdx.x] = (uint16_t)q;
+      } else if (threadIdx.x == kRecLook) {
+        uint32_t q;
+        sb[-1] = (i0 == 0) ? -1 : bucket_of(__ldg(cdf + i0 - 1), &q);
+      }
+    }
+    __syncthreads();
+    // phase B: bucket heads (b_i != b_{i-1}), ~1 in 12 elements.  They are compacted IN ORDER into a list (flags,
+    // block scan), the heads of the look-ahead and a sentinel appended, so that a head's entry count is the
+    // distance to the next head and every lane of a warp builds a record.
+    int nh = 0;
+    {
+      uint32_t flags = 0;
+      int32_t prev = sb[e0 - 1];
+#pragma unroll
+      for (int k = 0; k < kE; ++k) {
+        if (e0 + k < T && bmine[k] != prev) flags |= 1u << k;
+        prev = bmine[k];
+      }
+      int incl = __popc(flags);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int off = incl - __popc(flags);
+      int tot = 0;
+#pragma unroll
+      for (int wv = 0; wv < kThreads / 32; ++wv) {
+        const int v = s_wsum[wv];
+        if (wv < warp) off += v;
+        tot += v;
+      }
+      nh = tot;
+      while (flags) {
+        const int k = __ffs((int)flags) - 1;
+        flags &= flags - 1u;
+        s_head[off++] = (uint16_t)(e0 + k);
+      }
+      if (warp == 0) {  // heads inside the look-ahead, then the sentinel
+        const bool hd = sb[kRecTile + lane] != sb[kRecTile + lane - 1] && T == kRecTile;
+        const uint32_t bal = __ballot_sync(0xffffffffu, hd);
+        if (hd) s_head[tot + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(kRecTile + lane);
+        // sentinel: past the look-ahead (the bucket is long), or the end of the data in the last, partial tile
+        if (lane == 0) s_head[tot + __popc(bal)] = (uint16_t)(T == kRecTile ? T + kRecLook + 1 : T);
+      }
+    }
+    __syncthreads();
+    {
+      for (int hdx = threadIdx.x; hdx < nh; hdx += kThreads) {
+        const int e = s_head[hdx];
+        const int32_t b = sb[e], bp = sb[e - 1];
+        const int cnt = (int)s_head[hdx + 1] - e;  // > kRecEntries: long bucket
+        // halfword h of the record (h >= 3) is entry h - 3 = sq[e - 3 + h]: the record is a copy of the 32 halfwords
+        // from sq[e - 3], taken as aligned words (funnel-shifted when e - 3 is odd), masked to 0xFFFF past the entries
+        uint32_t w[16];
+        {
+          const int s0 = e - 3 + 4;  // halfword index into sq_raw
+          const uint32_t* sw = reinterpret_cast<const uint32_t*>(sq_raw) + (s0 >> 1);
+          const int valid = (cnt < kRecEntries ? cnt : kRecEntries) + 3;  // halfwords [3, valid) hold entries
+          uint32_t prev = sw[0];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t next = sw[j + 1];
+            uint32_t v = (s0 & 1) ? __funnelshift_r(prev, next, 16) : prev;
+            prev = next;
+            if (2 * j >= valid) v |= 0x0000FFFFu;
+            if (2 * j + 1 >= valid) v |= 0xFFFF0000u;
+            w[j] = v;
+          }
+        }
+        w[0] = (uint32_t)(i0 + e);
+        w[1] = (w[1] & 0xFFFF0000u) | (uint32_t)(cnt <= kRecEntries ? cnt : 65535);
+        uint4* r = recs + (int64_t)b * 4;
+        r[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        r[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        r[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        r[3] = make_uint4(w[12], w[13], w[14], w[15]);
+        // the empty buckets in front of it
+        const int32_t gap = b - bp - 1;
+        if (gap > 0 && gap <= 4) {
+          for (int32_t g = bp + 1; g < b; ++g) store_empty_record(recs, g, (int32_t)(i0 + e));
+        } else if (gap > 4) {
+          const int slot = atomicAdd(&s_ngap, 1);
+          s_gap[slot][0] = bp + 1;
+          s_gap[slot][1] = gap;
+          s_gap[slot][2] = (int32_t)(i0 + e);
+        }
+      }
+    }
+    __syncthreads();
+    // phase C: medium gaps, one warp per gap, coalesced 16-byte stores; big gaps to the global list
+    {
+      const int ng = s_ngap;
+      for (int j = warp; j < ng; j += kThreads / 32) {
+        const int32_t g0 = s_gap[j][0], len = s_gap[j][1], base = s_gap[j][2];
+        if (len > kBigGap) {
+          if (lane == 0) {
+            const unsigned int slot = atomicAdd(job_count, 1u);
+            jobs[3 * slot] = g0; jobs[3 * slot + 1] = len; jobs[3 * slot + 2] = base;
+          }
+          continue;
+        }
+        uint4* r = recs + (int64_t)g0 * 4;
+        for (int32_t x = lane; x < len * 4; x += 32)
+          r[x] = (x & 3) ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu)
+                         : make_uint4((uint32_t)base, 0xFFFF0000u, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// the big gaps (a few heavy particles): every job is spread over the whole grid
+__global__ void __launch_bounds__(kThreads) record_fill_kernel(uint4* __restrict__ recs, const int32_t* __restrict__ jobs,
+                                                               unsigned int* __restrict__ job_count,
+                                                               unsigned int* __restrict__ done_count) {
+  const unsigned int nj = *reinterpret_cast<volatile unsigned int*>(job_count);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (unsigned int j = 0; j < nj; ++j) {
+    const int32_t g0 = jobs[3 * j], len = jobs[3 * j + 1], base = jobs[3 * j + 2];
+    uint4* r = recs + (int64_t)g0 * 4;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < (int64_t)len * 4; x += stride)
+      r[x] = (x & 3) ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu)
+                     : make_uint4((uint32_t)base, 0xFFFF0000u, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  }
+  if (block_is_last(done_count) && threadIdx.x == 0) *job_count = 0u;  // self-cleaning
 }
 
 // One 32-byte sector in ONE load instruction (LDG.256, 32-byte aligned address).
@@ -941,10 +1156,19 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
   if (bucket_records_enabled() && rec_buckets(n) <= W.guide_buckets) {
     const int64_t Mr = rec_buckets(n);  // the int32 guide of the Mr buckets is scratch for the record build
     uint4* recs = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ws) + rec_offset(n));
-    guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, n);
-    PFB_LAUNCH_OK("guide_kernel");
-    bucket_record_kernel<<<stream_grid(Mr + 1, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, recs);
-    PFB_LAUNCH_OK("bucket_record_kernel");
+    if (two_pass_record_build()) {
+      guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, n);
+      PFB_LAUNCH_OK("guide_kernel");
+      bucket_record_kernel<<<stream_grid(Mr + 1, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, recs);
+      PFB_LAUNCH_OK("bucket_record_kernel");
+    } else {  // (the big-gap job list lives in the guide area: at most Mr / kBigGap + 1 jobs of 3 ints, and none if Mr <= kBigGap)
+      const int64_t tiles = (n + kRecTile - 1) / kRecTile;
+      const int64_t cap = (int64_t)sm_count() * 4;
+      record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(n, cdf, Mr, recs, W.guide, W.counters + 4);
+      PFB_LAUNCH_OK("record_build_kernel");
+      record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, W.guide, W.counters + 4, W.counters + 5);
+      PFB_LAUNCH_OK("record_fill_kernel");
+    }
     PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(n, n_out, cdf, u, x_in, x_out, idx_out, est_kind, est_out, W, st, recs, Mr, key))));
     if (rc) return rc;
     PFB_LAUNCH_OK("resample_rec_kernel");

@@ -306,10 +306,12 @@ def test_scan_adversarial_dynamic_range(eng):
     assert eng.scan_error_flags() == 0
 
 
-@pytest.fixture(params=["1", "0"], ids=["bucket_records", "guide_window"])
+@pytest.fixture(params=[("1", ""), ("1", "2pass"), ("0", "")], ids=["bucket_records", "bucket_records_2pass_build", "guide_window"])
 def lookup_path(request, monkeypatch):
-    """multinomial resampling has two index-lookup structures (pfb_resample.cu); PFB_BUCKET_RECORDS is read per call"""
-    monkeypatch.setenv("PFB_BUCKET_RECORDS", request.param)
+    """multinomial resampling has two index-lookup structures and two builds of the first (pfb_resample.cu);
+    PFB_BUCKET_RECORDS / PFB_RECORD_BUILD are read per call"""
+    monkeypatch.setenv("PFB_BUCKET_RECORDS", request.param[0])
+    monkeypatch.setenv("PFB_RECORD_BUILD", request.param[1])
     return request.param
 
 
@@ -607,3 +609,25 @@ def test_resample_gather_every_record_size(eng, dtype, dim):
         out = torch.empty((u.shape[0], dim), dtype=dtype, device="cuda:0")
         eng.resample(cdf, dev(u), x, out, u.shape[0], dim)
         assert np.array_equal(host(out), host(x)[ref])
+
+
+def test_resample_heavy_particles_span_many_buckets(eng, lookup_path):
+    """a few particles holding most of the weight: runs of 1e4..1e5 empty buckets (the grid-wide fill of the record
+    build), next to crowded buckets of weightless particles"""
+    rng = np.random.default_rng(5)
+    n = 2_000_003
+    w = rng.random(n) * 1e-3
+    w[[0, 777, 1_000_000, n - 1]] = [300.0, 40.0, 500.0, 90.0]
+    w[1_200_000:1_300_000] = 1e-12
+    c = np.cumsum(w)
+    v = c / c[-1]
+    u = np.concatenate([rng.random(400_000), v[[0, 776, 777, 999_999, 1_000_000, n - 2]], [0.0]])
+    u = u[u < 1.0]
+    ref = np.minimum(np.searchsorted(v, u, side="right"), n - 1)
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    assert np.array_equal(host(cdf), c)
+    idx = torch.empty(u.shape[0], dtype=torch.int64, device="cuda:0")
+    for _ in range(2):  # twice: the job counter of the fill kernel cleans itself
+        eng.resample(cdf, dev(u), None, None, u.shape[0], 1, idx_out=idx)
+        assert np.array_equal(host(idx), ref)
