@@ -280,6 +280,7 @@ def run_gpu(args):
     cls = {"torus": Fl.HypertoroidalParticleFilter, "sphere": Fl.HypersphericalParticleFilter,
            "euclid": Fl.EuclideanParticleFilter}[manifold]
     pf = cls(n, D if manifold != "sphere" else D - 1)
+    pf.resampling = args.resampling  # 'multinomial' (the reference's scheme, default) or 'systematic'
     pf.filter_state = prior
 
     def barrier():
