@@ -53,6 +53,20 @@ def algorithmic_bytes(D, E):
     return {"predict_loglik": 8 * (2 * D + E + 1), "scan": 16, "resample": 8 * (2 * D + 2)}
 
 
+def random_access_roofline(kernel, resampling, n, D, ms):
+    """Multinomial resampling is bound by DRAM random accesses, not bytes: B200 serves ~3.7e10 random reads/s from
+    footprints >= 1 GiB whatever their size up to 128 B (tools/micro/sector_fetch.cu, profiles/r01g_sector_fetch_micro.log).
+    Per particle: one 64-byte bucket record + the particle record (1 + (8 D - 8)/64 64-byte fetches)."""
+    if kernel != "resample" or resampling != "multinomial":
+        return None
+    per_particle = 1.0 + 1.0 + (8 * D - 8) / 64.0
+    peak = 3.7e10
+    achieved = per_particle * n / (ms * 1e-3)
+    return {"reads_per_particle": per_particle, "achieved_reads_per_s": achieved, "peak_reads_per_s": peak,
+            "frac": achieved / peak, "peak_source": "measured: profiles/r01g_sector_fetch_micro.log (footprint >= 1 GiB)",
+            "note": "time includes the 0.45 ms record build, which streams"}
+
+
 def ncu_traffic(name, n, resampling, exact, kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu capture of this exact configuration, else None."""
     try:
@@ -415,7 +429,8 @@ def run_gpu(args):
                          "peak_source": peak_src,
                          "kernel_ms": {nm: float(t) for nm, t in zip(names, kt)},
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
-                         "bytes_per_particle": ab},
+                         "bytes_per_particle": ab,
+                         "random_access": random_access_roofline(names[k], args.resampling, n, D, kt[k])},
             "cpu_baseline": None if args.no_cpu else {
                 "value": cpu_val, "unit": "particle-steps/s", "cores": cpu_threads(), "kind": "port",
                 "sample": f"oracle/pf_oracle.py (vectorised numpy restatement, predict + likelihood split over {cpu_threads()} host threads) "
