@@ -179,7 +179,7 @@ class Engine:
         L.check(self.lib.pfb_resample_batched(dt, dim, n_runs, run_len, n_out_run, _ptr(cdf_pad), _ptr(u), seed, offset,
                                               1 if systematic else 0, _ptr(x_in), _ptr(x_out), _ptr(idx_out), ws, wsb,
                                               _stream(self.device)))
-        self.launches += 2
+        self.launches += 2 if systematic else 3  # guide + resample | record build + fill + resample
 
     def moments_batched(self, kind, x, n_runs, run_len, dim, order=1, out=None):
         if out is None:

@@ -263,8 +263,11 @@ __device__ __forceinline__ void store_empty_record(uint4* __restrict__ recs, int
   r[1] = r[2] = r[3] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
 }
 
-__global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n, const double* __restrict__ cdf, int64_t M,
-                                                                uint4* __restrict__ recs, int32_t* __restrict__ jobs,
+// Runs: tile t belongs to run t / tpr, whose CDF is cdf[run run_pad, +run_len) and whose records start at
+// recs + run (M + 2); indices stored in the records are local to the run (a plain call is one run).
+__global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n_runs, int64_t run_len, int64_t run_pad,
+                                                                const double* __restrict__ cdf_all, int64_t M,
+                                                                uint4* __restrict__ recs_all, int32_t* __restrict__ jobs,
                                                                 unsigned int* __restrict__ job_count) {
   constexpr int kE = kRecTile / kThreads;  // elements per thread
   __shared__ int32_t sb_raw[1 + kRecTile + kRecLook];
@@ -275,14 +278,15 @@ __global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n, const
   __shared__ int s_ngap;
   int32_t* sb = sb_raw + 1;  // sb[-1]: bucket of the element before the tile
   uint16_t* sq = sq_raw + 4;  // (front padding: a record is copied from 3 halfwords before its first entry)
-  const double total = __ldg(cdf + n - 1);
   const double dM = (double)M;
-  const int64_t ntiles = (n + kRecTile - 1) / kRecTile;
+  const int64_t tpr = (run_len + kRecTile - 1) / kRecTile;
+  const int64_t ntiles = n_runs * tpr;
+  const int64_t n = run_len;  // (the body below works inside one run)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double total = 1.0, scale = 1.0;
   // b = floor(v M), q = floor((v M - b) 2^16) with v = fl(c/total), i.e. the high and low bits of
   // floor(A), A = v M 2^16 (an exact scaling of v).  T = c * fl(M 2^16 / total) differs from A by less than
   // 2^-50 A (three roundings), so floor(T) = floor(A) unless T lies that close to an integer: only then divide.
-  const double scale = __ddiv_rn(dM * 65536.0, total);
   auto bucket_of = [&](double c, uint32_t* q) -> int32_t {
     double t = c * scale;
     long long f = (long long)t;
@@ -290,10 +294,16 @@ __global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n, const
     const double tol = t * 8.881784197001252e-16;  // 2^-50
     if (fr <= tol || 1.0 - fr <= tol) f = (long long)(__ddiv_rn(c, total) * (dM * 65536.0));
     *q = (uint32_t)f & 0xFFFFu;
-    return (int32_t)(f >> 16);
+    const long long b = f >> 16;
+    return (int32_t)(b < 0 ? 0 : (b > M ? M : b));  // (only a corrupt CDF gets clamped; keeps the stores in bounds)
   };
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t i0 = tile * kRecTile;
+    const int64_t run = tile / tpr;
+    const double* __restrict__ cdf = cdf_all + run * run_pad;
+    uint4* __restrict__ recs = recs_all + run * (M + 2) * 4;
+    total = __ldg(cdf + n - 1);
+    scale = __ddiv_rn(dM * 65536.0, total);
+    const int64_t i0 = (tile - run * tpr) * kRecTile;
     const int T = (int)((n - i0 < kRecTile) ? n - i0 : kRecTile);  // elements of this tile
     if (threadIdx.x == 0) s_ngap = 0;
     // phase A
@@ -423,7 +433,7 @@ __global__ void __launch_bounds__(kThreads) record_build_kernel(int64_t n, const
         if (len > kBigGap) {
           if (lane == 0) {
             const unsigned int slot = atomicAdd(job_count, 1u);
-            jobs[3 * slot] = g0; jobs[3 * slot + 1] = len; jobs[3 * slot + 2] = base;
+            jobs[3 * slot] = (int32_t)(run * (M + 2)) + g0; jobs[3 * slot + 1] = len; jobs[3 * slot + 2] = base;
           }
           continue;
         }
@@ -683,12 +693,15 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
                                                                 const T* __restrict__ x_in, T* __restrict__ x_out,
                                                                 int64_t* __restrict__ idx_out, double* est_out,
                                                                 Workspace ws, const uint4* __restrict__ recs,
-                                                                int64_t M, RngKey key) {
+                                                                int64_t M, RngKey key, int64_t n_runs, int64_t run_pad,
+                                                                int64_t n_out_run) {
+  // runs: output j belongs to run j / n_out_run, drawn from cdf[run run_pad, +n) / x_in[run n, ..) through the
+  // records at recs + run (M + 2); a plain call is one run (run_pad = n, n_out_run = n_out)
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
   const bool use_rng = (u == nullptr);
   const double dM = (double)M;
-  const double total = __ldg(cdf + n - 1);
+  const bool multi = n_runs > 1;
   double acc[NE];
 #pragma unroll
   for (int k = 0; k < NE; ++k) acc[k] = 0.0;
@@ -696,12 +709,13 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
   for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n_out; j0 += stride * kBatch) {
     double uj[kBatch];
     bool live[kBatch];
-    int64_t dst[kBatch], bkt[kBatch];
+    int64_t dst[kBatch], bkt[kBatch], run[kBatch];
     uint32_t p2[kBatch];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       dst[q] = j0 + q * stride;
       live[q] = dst[q] < n_out;
+      run[q] = (multi && live[q]) ? dst[q] / n_out_run : 0;
       if (!live[q]) uj[q] = 0.0;
       else if (use_rng) { const uint4 r = rng_block(key, (uint64_t)dst[q], 7u); uj[q] = u53(r.x, r.y); }
       else uj[q] = __ldg(u + dst[q]);
@@ -713,7 +727,7 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
     uint64_t rec[kBatch][2][4];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
-      const uint4* r = recs + bkt[q] * 4;
+      const uint4* r = recs + (run[q] * (M + 2) + bkt[q]) * 4;
       ld_sector(r, rec[q][0]);
       ld_sector(r + 2, rec[q][1]);
     }
@@ -739,13 +753,17 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
       int64_t r = (int64_t)base + (nb >> 4);
       if (eq != 0u || cnt > (uint32_t)kRecEntries) {  // a tie in the 16-bit grid, or a crowded bucket: exact search
         int64_t hi = (int64_t)base + cnt;
-        if (cnt == 65535u) hi = (int64_t)(int32_t)__ldg(&recs[(bkt[q] + 1) * 4].x);
-        r = search_range<true>(cdf, (int64_t)base, hi, total, uj[q]);
+        if (cnt == 65535u) hi = (int64_t)(int32_t)__ldg(&recs[(run[q] * (M + 2) + bkt[q] + 1) * 4].x);
+        const double* crun = cdf + run[q] * run_pad;
+        r = search_range<true>(crun, (int64_t)base, hi, __ldg(crun + n - 1), uj[q]);
       }
       if (r > n - 1) r = n - 1;
       idx[q] = r;
     }
-    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, idx, dst, idx, live, acc);
+    int64_t src[kBatch];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) src[q] = run[q] * n + idx[q];
+    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, src, dst, idx, live, acc);
   }
   if constexpr (EST != PFB_EST_NONE) finish_estimate<NE>(acc, red, ws, est_out, n_out);
 }
@@ -1057,17 +1075,19 @@ static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, do
 template <typename T, int D>
 static int launch_resample_rec(int64_t n, int64_t n_out, const double* cdf, const double* u, const void* x_in,
                                void* x_out, int64_t* idx_out, int est_kind, double* est_out, Workspace W,
-                               cudaStream_t st, const uint4* recs, int64_t M, RngKey key) {
+                               cudaStream_t st, const uint4* recs, int64_t M, RngKey key, int64_t n_runs = 1,
+                               int64_t run_pad = 0, int64_t n_out_run = 0) {
+  if (n_runs <= 1) { n_runs = 1; run_pad = n; n_out_run = n_out; }
   const int grid = stream_grid(n_out);
   switch (est_kind) {
     case PFB_EST_NONE:
-      resample_rec_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      resample_rec_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
       break;
     case PFB_EST_SUM:
-      resample_rec_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      resample_rec_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
       break;
     case PFB_EST_TRIG:
-      resample_rec_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key);
+      resample_rec_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
       break;
     default:
       set_error("bad est_kind %d", est_kind);
@@ -1164,7 +1184,7 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
     } else {  // (the big-gap job list lives in the guide area: at most Mr / kBigGap + 1 jobs of 3 ints, and none if Mr <= kBigGap)
       const int64_t tiles = (n + kRecTile - 1) / kRecTile;
       const int64_t cap = (int64_t)sm_count() * 4;
-      record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(n, cdf, Mr, recs, W.guide, W.counters + 4);
+      record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(1, n, n, cdf, Mr, recs, W.guide, W.counters + 4);
       PFB_LAUNCH_OK("record_build_kernel");
       record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, W.guide, W.counters + 4, W.counters + 5);
       PFB_LAUNCH_OK("record_fill_kernel");
@@ -1216,6 +1236,8 @@ extern "C" int64_t pfb_workspace_bytes_batched(int64_t n_runs, int64_t run_len) 
   const int64_t n_pad = n_runs * scan_tiles(run_len) * kScanTile;
   int64_t b = guide_offset(n_pad) + n_runs * (guide_buckets(run_len) + 2) * (int64_t)sizeof(int32_t);
   b = (b + 255) & ~(int64_t)255;
+  b += n_runs * (pfb::rec_buckets(run_len) + 2) * 64;  // per-run bucket records
+  b = (b + 255) & ~(int64_t)255;
   const int64_t single = pfb_workspace_bytes(n_pad);  // the weighting / scan calls size themselves on n_pad
   return b > single ? b : single;
 }
@@ -1237,9 +1259,24 @@ extern "C" int pfb_resample_batched(pfb_dtype dtype, int32_t dim, int64_t n_runs
   int32_t* guide = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + guide_offset(n_pad));
   const int64_t M = guide_buckets(run_len);
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_out = n_runs * n_out_run;
+  if (!systematic && bucket_records_enabled()) {  // multinomial: per-run bucket records (the job list lives in the guide area)
+    const int64_t Mr = rec_buckets(run_len);
+    const int64_t goff = guide_offset(n_pad) + n_runs * (M + 2) * (int64_t)sizeof(int32_t);
+    uint4* recs = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ws) + ((goff + 255) & ~(int64_t)255));
+    const int64_t tiles = n_runs * scan_tiles(run_len);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(n_runs, run_len, run_pad, cdf_pad, Mr, recs, guide, W.counters + 4);
+    PFB_LAUNCH_OK("record_build_kernel");
+    record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, guide, W.counters + 4, W.counters + 5);
+    PFB_LAUNCH_OK("record_fill_kernel");
+    PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(run_len, n_out, cdf_pad, u, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st, recs, Mr, RngKey{rng_seed, rng_offset}, n_runs, run_pad, n_out_run))));
+    if (rc) return rc;
+    PFB_LAUNCH_OK("resample_rec_kernel");
+    return PFB_OK;
+  }
   guide_kernel<<<stream_grid((n_pad + 3) / 4, 2), kThreads, 0, st>>>(n_pad, cdf_pad, guide, M, run_pad);
   PFB_LAUNCH_OK("guide_kernel");
-  const int64_t n_out = n_runs * n_out_run;
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample<T, D>(n_pad, n_out, cdf_pad, u, systematic, cdf_pad, x_in, x_out, idx_out, PFB_EST_NONE, nullptr, W, st, guide, M, RngKey{rng_seed, rng_offset}, run_pad, run_len, n_out_run))));
   if (rc) return rc;
   PFB_LAUNCH_OK("resample_kernel");

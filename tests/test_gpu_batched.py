@@ -13,9 +13,12 @@ def host(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.mark.parametrize("records", ["1", "0"], ids=["bucket_records", "guide_window"])
 @pytest.mark.parametrize("n", [700, 2048, 5000])
-def test_batched_torus_runs_equal_single_runs(n):
+def test_batched_torus_runs_equal_single_runs(n, records, monkeypatch):
     from pyrecest_b200 import random as prandom
+
+    monkeypatch.setenv("PFB_BUCKET_RECORDS", records)  # both lookup structures of the multinomial resampling
     from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN
     from pyrecest_b200.evaluation import BatchedParticleFilter
 
