@@ -109,7 +109,10 @@ typedef struct {
   int32_t kind;
   int32_t dim;               /* stored components D */
   int32_t n_images;          /* WN_MULTI: rows of images_dev */
-  int32_t reserved;
+  int32_t cell_grid;         /* WN_MULTI, D <= 3, n_images <= 64, single measurement: G > 0 says that images_dev is
+                                followed by G^D uint64 candidate masks, one per cell of the box dev in
+                                [-pi - mu, pi - mu)^D cut into G cells per dimension (index c_0 + G c_1 + G^2 c_2):
+                                bit k set iff image k can pass the screen somewhere in the cell.  0: screen all. */
   double mu[PFB_MAXD];
   double W[PFB_MAXD * PFB_MAXD]; /* GAUSS / WN_MULTI: whitening matrix (row-major D x D), y = (x - mu) W */
   double logc;               /* log normalising constant added to every log-likelihood */

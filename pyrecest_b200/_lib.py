@@ -60,7 +60,7 @@ class PredictParams(C.Structure):
 
 class LikParams(C.Structure):
     _fields_ = [
-        ("kind", C.c_int32), ("dim", C.c_int32), ("n_images", C.c_int32), ("reserved", C.c_int32),
+        ("kind", C.c_int32), ("dim", C.c_int32), ("n_images", C.c_int32), ("cell_grid", C.c_int32),
         ("mu", C.c_double * PFB_MAXD), ("W", C.c_double * (PFB_MAXD * PFB_MAXD)),
         ("logc", C.c_double), ("kappa", C.c_double), ("sigma", C.c_double),
         ("images_dev", C.c_void_p), ("mu_batch_dev", C.c_void_p),

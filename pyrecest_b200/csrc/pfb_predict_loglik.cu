@@ -269,6 +269,34 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
         for (int c = 0; c < 3; ++c) df[c] = (c < D) ? (float)dev[c] : 0.0f;
         float runmin = INFINITY;
         uint32_t mlo = 0u, mhi = 0u;  // candidate bits of images 0..31 / 32..63 (branch-free, 32-bit ops)
+        if (L.cell_grid > 0 && L.mu_batch_dev == nullptr) {
+          // the host has listed, per cell of the dev box, the images that can pass the screen anywhere in the cell
+          // (registry.wn_cell_masks: a superset that contains the minimiser): the minimum of r over them is the
+          // minimum over all images, so the second loop below selects exactly what the full screen selects
+          const int G = L.cell_grid;
+          const double inv = (double)G * 0.15915494309189535;  // G / (2 pi)
+          int ci = 0, mul = 1;
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            int q = (int)((dev[c] + (kPi + mu[c])) * inv);
+            q = q < 0 ? 0 : (q >= G ? G - 1 : q);
+            ci += q * mul;
+            mul *= G;
+          }
+          const uint64_t cand = reinterpret_cast<const uint64_t*>(scr + K)[ci];
+          mlo = (uint32_t)cand;
+          mhi = (uint32_t)(cand >> 32);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t m = half ? mhi : mlo;
+            while (m) {
+              const int k = __ffs((int)m) - 1 + 32 * half;
+              m &= m - 1u;
+              const float4 t = scr[k];
+              runmin = fminf(runmin, fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w));
+            }
+          }
+        } else {
         const int K0 = K < 32 ? K : 32;
         for (int k = 0; k < K0; ++k) {
           const float4 t = scr[k];
@@ -281,6 +309,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
           const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
           mhi |= (r <= runmin + kScreenCut) ? (1u << (k - 32)) : 0u;
           runmin = fminf(runmin, r);
+        }
         }
         const float lim = runmin + kScreenCut;
 #pragma unroll
@@ -399,6 +428,14 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
       t.w = (float)row[D];
       scr[k] = t;
     }
+    if (L.cell_grid > 0) {  // candidate masks of the cell grid, after the screen rows
+      uint64_t* cells = reinterpret_cast<uint64_t*>(scr + K);
+      const uint64_t* src = reinterpret_cast<const uint64_t*>(L.images_dev + count);
+      int nc = L.cell_grid;
+      if (D > 1) nc *= L.cell_grid;
+      if (D > 2) nc *= L.cell_grid;
+      for (int k = threadIdx.x; k < nc; k += blockDim.x) cells[k] = src[k];
+    }
   }
   __syncthreads();
   return smem_img;
@@ -484,7 +521,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
 }
 
 template <typename T, int D, int MODE, int KIND, bool RNG>
-__global__ void __launch_bounds__(kThreads) predict_loglik_kernel(pfb_predict_params p,
+__global__ void __launch_bounds__(kThreads, RNG ? 4 : 0) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* __restrict__ x_in, T* x_out,
                                                                   const T* __restrict__ noise,
@@ -588,13 +625,23 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
     if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
-    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 16) + 8 > 48 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 16) + 8 > 40 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+    if (L->cell_grid != 0 && (L->cell_grid < 1 || L->cell_grid > 8 || dim > 3 || L->n_images > 64)) {
+      set_error("cell_grid %d: candidate masks need 1 <= G <= 8, dim <= 3 and at most 64 images", L->cell_grid);
+      return PFB_ERR_INVALID;
+    }
   }
   return PFB_OK;
 }
 
 static size_t lik_smem(const pfb_lik_params* L) {
-  return L->kind == PFB_LIK_WN_MULTI ? (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 16 : 0;
+  if (L->kind != PFB_LIK_WN_MULTI) return 0;
+  size_t cells = 0;
+  if (L->cell_grid > 0) {
+    cells = 8;
+    for (int c = 0; c < L->dim; ++c) cells *= (size_t)L->cell_grid;
+  }
+  return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 16 + cells;
 }
 
 #define PFB_DISPATCH_MODE(mode, ...)                                                       \

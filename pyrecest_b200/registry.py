@@ -198,11 +198,46 @@ def wn_image_table_cached(mu, P, device_put=None):
     hit = _IMAGE_TABLE_CACHE.get(key)
     if hit is None:
         table, n_img = wn_image_table(mu, P)
-        dev = device_put(table) if device_put is not None else None
+        cells = wn_cell_masks(mu, table)
+        flat = table.reshape(-1) if cells is None else np.concatenate([table.reshape(-1), cells.view(np.float64)])
+        dev = device_put(flat) if device_put is not None else None
         if len(_IMAGE_TABLE_CACHE) > 256:
             _IMAGE_TABLE_CACHE.clear()
-        hit = _IMAGE_TABLE_CACHE[key] = (table, n_img, dev)
+        hit = _IMAGE_TABLE_CACHE[key] = (table, n_img, dev, 0 if cells is None else WN_CELL_GRID)
     return hit
+
+
+WN_CELL_GRID = 8       # cells per dimension of the candidate grid
+WN_SCREEN_CUT = 78.0   # kScreenCut of pfb_predict_loglik.cu
+
+
+def wn_cell_masks(mu, table, G=WN_CELL_GRID):
+    """Candidate masks of the image screen.  The kernel evaluates the images k with r_k <= min_j r_j + cut,
+    r_k(dev) = 2 g_k.dev + h_k linear in dev.  Over a cell of the box dev in [-pi - mu, pi - mu) (G cells per
+    dimension, index c_0 + G c_1 + G^2 c_2) r_k is bounded by its corner values, so image k can only be evaluated
+    somewhere in the cell if min_cell r_k <= min_j max_cell r_j + cut: bit k of the cell's uint64 mask.  A superset
+    of what the full screen keeps at every point of the cell (+1 of slack for the kernel's fp32 r, cells inflated by
+    1e-6 for the rounding of the cell index), so screening only the masked images selects exactly the same images."""
+    mu = _np(mu).reshape(-1)
+    d = mu.shape[0]
+    K = table.shape[0]
+    if d > 3 or K > 64:
+        return None
+    g, h = table[:, :d], table[:, d]
+    lo = -math.pi - mu
+    wid = TWO_PI / G
+    idx = np.stack(np.meshgrid(*([np.arange(G)] * d), indexing="ij"), axis=-1).reshape(-1, d)  # (cells, d), c_0 slowest
+    a = lo + idx * wid - 1e-6
+    b = a + wid + 2e-6
+    ga, gb = 2.0 * g[None, :, :] * a[:, None, :], 2.0 * g[None, :, :] * b[:, None, :]
+    rmin = h[None, :] + np.minimum(ga, gb).sum(axis=-1)   # (cells, K)
+    rmax = h[None, :] + np.maximum(ga, gb).sum(axis=-1)
+    keep = rmin <= rmax.min(axis=1, keepdims=True) + WN_SCREEN_CUT + 1.0
+    bits = (keep.astype(np.uint64) << np.arange(K, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint64)
+    flat = (idx * (G ** np.arange(d))[None, :]).sum(axis=1)  # c_0 + G c_1 + G^2 c_2
+    out = np.zeros(G ** d, dtype=np.uint64)
+    out[flat] = bits
+    return out
 
 
 def wn_image_table(mu, P, m=3, cut=None):
@@ -276,8 +311,9 @@ def lik_params(dist, dim, images_to_device=None):
             raise AssertionError("likelihood dimension does not match the filter state")
         C = np.atleast_2d(_np(dist.C))
         W, logdet = gaussian_whitening(C)
-        table, n_img, dev_table = wn_image_table_cached(mu, W @ W.T, images_to_device)
+        table, n_img, dev_table, cell_grid = wn_image_table_cached(mu, W @ W.T, images_to_device)
         p.kind = L.LIK_WN_MULTI
+        p.cell_grid = cell_grid if dev_table is not None else 0
         p.mu[:dim] = mu.tolist()
         p.W[: dim * dim] = W.reshape(-1).tolist()
         p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)
