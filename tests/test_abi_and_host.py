@@ -196,3 +196,30 @@ def test_vm_strip_sampler_restatement_is_von_mises():
     assert stats.kstest(x[:, 0], stats.uniform(-np.pi, 2 * np.pi).cdf).pvalue > 1e-4
     for c in (1, 2):
         assert stats.kstest(x[:, c], stats.vonmises(kap[c]).cdf).pvalue > 1e-4
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_wn_cell_masks_cover_the_full_screen(d):
+    """registry.wn_cell_masks: at every point of the dev box, the images the kernel's full screen would evaluate
+    (r_k <= min r + cut) are inside the candidate mask of the point's cell, and so is the minimiser"""
+    from pyrecest_b200 import registry as R
+
+    rng = np.random.default_rng(d)
+    A = rng.normal(size=(d, d))
+    C = A @ A.T / d + 0.2 * np.eye(d)
+    mu = rng.random(d) * 2 * np.pi
+    W, _ = R.gaussian_whitening(C)
+    table, K = R.wn_image_table(mu, W @ W.T)
+    masks = R.wn_cell_masks(mu, table)
+    G = R.WN_CELL_GRID
+    assert masks.shape == (G**d,) and masks.dtype == np.uint64
+    g, h = table[:, :d], table[:, d]
+    y = rng.random((20_000, d)) * 2 * np.pi - np.pi  # wrapped particle coordinate
+    dev = y - mu
+    r = 2.0 * dev @ g.T + h
+    need = r <= r.min(axis=1, keepdims=True) + R.WN_SCREEN_CUT
+    q = np.clip(((dev + (np.pi + mu)) * (G / (2 * np.pi))).astype(int), 0, G - 1)
+    cell = (q * (G ** np.arange(d))).sum(axis=1)
+    have = ((masks[cell][:, None] >> np.arange(K, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+    assert np.all(have[need])
+    assert have.sum(axis=1).mean() < K  # and it prunes

@@ -631,3 +631,26 @@ def test_resample_heavy_particles_span_many_buckets(eng, lookup_path):
     for _ in range(2):  # twice: the job counter of the fill kernel cleans itself
         eng.resample(cdf, dev(u), None, None, u.shape[0], 1, idx_out=idx)
         assert np.array_equal(host(idx), ref)
+
+
+def test_wn_cell_masks_do_not_change_the_likelihood(eng, golden):
+    """screening only the cell's candidate images (lik.cell_grid > 0) selects exactly the images of the full
+    screen: bit-identical log-likelihoods"""
+    from pyrecest_b200 import registry as R
+
+    g = golden("likelihoods")
+    rng = np.random.default_rng(3)
+    for tag in ("wn2", "wn3", "wn3b"):
+        mu, Cc = g[f"{tag}_mu"], g[f"{tag}_C"]
+        D = mu.shape[0]
+        x = dev(rng.random((200_000, D)) * 2 * np.pi)
+        out = []
+        for grid in (None, 0):
+            lp, keep = R.lik_params(_dist("HypertoroidalWrappedNormalDistribution", mu=mu, C=Cc), D, images_to_device=dev)
+            assert lp.cell_grid == R.WN_CELL_GRID
+            if grid is not None:
+                lp.cell_grid = grid
+            logw = torch.empty(x.shape[0], dtype=torch.float64, device="cuda:0")
+            eng.loglik(lp, x, logw)
+            out.append(host(logw))
+        assert np.array_equal(out[0], out[1])
