@@ -422,6 +422,23 @@ def mean_direction_torus(d, w):
     return np.mod(np.arctan2(np.imag(a), np.real(a)), TWO_PI)
 
 
+def hybrid_moment(d, w, bound_dim):
+    """HypercylindricalDiracDistribution.hybrid_moment
+    (pyrecest/distributions/cart_prod/hypercylindrical_dirac_distribution.py:39-50): w @ [cos(periodic) | sin(periodic) | linear]."""
+    d = np.asarray(d, dtype=np.float64)
+    S = np.column_stack((np.cos(d[:, :bound_dim]), np.sin(d[:, :bound_dim]), d[:, bound_dim:]))
+    return np.asarray(w) @ S
+
+
+def hybrid_mean(d, w, bound_dim):
+    """LinBoundedCartProdDiracDistribution.hybrid_mean
+    (pyrecest/distributions/cart_prod/lin_bounded_cart_prod_dirac_distribution.py:37-41): circular mean direction of the
+    periodic part (the part is a HypertoroidalDiracDistribution, whose constructor wraps it, :41 there) and weighted mean
+    of the linear part."""
+    d = np.asarray(d, dtype=np.float64)
+    return np.concatenate((mean_direction_torus(np.mod(d[:, :bound_dim], TWO_PI), w), mean_linear(d[:, bound_dim:], w)))
+
+
 def mean_resultant(d, w):
     """HypersphericalDiracDistribution.mean_resultant_vector
     (pyrecest/distributions/hypersphere_subset/hyperspherical_dirac_distribution.py:43-44)."""

@@ -479,7 +479,14 @@ class AbstractDiracDistribution:
         """:69-80  w <- f(d) * w / sum, evaluated as max / log-sum-exp normalisation of log f + log w.
         The reference's assertions (f >= 0, sum > 0) map to the device status word."""
         dist = copy.deepcopy(self)
-        logw, keep = self._log_weights(f)
+        if isinstance(f, (torch.Tensor, np.ndarray)):
+            # likelihood VALUES f(d_i) computed by the caller (a likelihood outside the device registry): (N,) >= 0
+            vals = _as_device_tensor(f, dtype=torch.float64, device=self.device).reshape(-1)
+            assert vals.shape[0] == self._w.shape[0], "Function returned wrong number of outputs."
+            logw = torch.log(vals) + torch.log(self._w)
+            keep = None
+        else:
+            logw, keep = self._log_weights(f)
         eng = self._eng()
         w_new = torch.empty_like(logw)
         eng.normalize(logw, w_new)
@@ -653,6 +660,75 @@ class ToroidalDiracDistribution(HypertoroidalDiracDistribution):
 
     def __init__(self, d, w=None):
         HypertoroidalDiracDistribution.__init__(self, d, w, dim=2)
+
+class LinBoundedCartProdDiracDistribution(AbstractDiracDistribution):
+    """cart_prod/lin_bounded_cart_prod_dirac_distribution.py:14-52 -- bounded (periodic) dimensions first, then linear.
+    All moments are taken on the whole (N, D) record with the kernels of the torus and the linear Diracs and the wanted
+    components picked from the result: no marginal copies of the particle set are made."""
+
+    _manifold = "cart_prod"
+
+    def __init__(self, bound_dim, d, w=None):
+        if not int(bound_dim) >= 1:
+            raise ValueError("bound_dim must be a positive integer")
+        AbstractDiracDistribution.__init__(self, d, w)
+        assert self._d.ndim == 2 and self._d.shape[1] > int(bound_dim), "need at least one linear dimension"
+        self.bound_dim = int(bound_dim)
+        self.lin_dim = self._d.shape[1] - self.bound_dim
+        self.dim = self._d.shape[1]
+        self.input_dim = self.dim
+
+    def marginalize_periodic(self):
+        """:17-20"""
+        return LinearDiracDistribution(self._d[:, self.bound_dim:].contiguous(), self._w.clone())
+
+    def marginalize_linear(self):
+        raise NotImplementedError
+
+    def linear_mean(self):
+        """:22-23"""
+        return self._moment(L.MOM_MEAN)[self.bound_dim:self.dim].clone()
+
+    def linear_covariance(self, approximate_mean=False):
+        """:25-32"""
+        if approximate_mean:
+            warnings.warn("Formula for mean is trivial, so approximate_mean is ignored.")
+        D, b = self.dim, self.bound_dim
+        m = self._moment(L.MOM_MEAN)
+        c = self._moment(L.MOM_CENTRAL, center=m)[: D * D].reshape(D, D)
+        return c[b:, b:].clone()
+
+    def hybrid_mean(self):
+        """:37-41  concatenate(periodic.mean_direction(), linear.mean())"""
+        D, b = self.dim, self.bound_dim
+        t = self._moment(L.MOM_TRIG, order=1)[: 2 * D].reshape(D, 2).clone()
+        per = torch.remainder(torch.atan2(t[:b, 1], t[:b, 0]), TWO_PI)
+        return torch.cat((per, self.linear_mean()))
+
+    def mean(self):
+        """abstract_lin_bounded_cart_prod_distribution.py:35-43"""
+        return self.hybrid_mean()
+
+    @classmethod
+    def from_distribution(cls, distribution, n_particles):
+        """:43-52"""
+        return cls(distribution.bound_dim, distribution.sample(n_particles))
+
+
+class HypercylindricalDiracDistribution(LinBoundedCartProdDiracDistribution):
+    """cart_prod/hypercylindrical_dirac_distribution.py:18-49"""
+
+    _manifold = "cylinder"
+
+    def marginalize_linear(self):
+        """:33-36"""
+        return HypertoroidalDiracDistribution(self._d[:, : self.bound_dim].contiguous(), self._w.clone())
+
+    def hybrid_moment(self):
+        """:38-49  w @ [cos(periodic) | sin(periodic) | linear]"""
+        D, b = self.dim, self.bound_dim
+        t = self._moment(L.MOM_TRIG, order=1)[: 2 * D].reshape(D, 2).clone()
+        return torch.cat((t[:b, 0], t[:b, 1], self.linear_mean()))
 
 
 class AbstractHypersphereSubsetDiracDistribution(AbstractDiracDistribution):

@@ -194,7 +194,7 @@ def wn_image_table_cached(mu, P, device_put=None):
     covariance every step and often revisits measurements, and the pruning below costs milliseconds of
     host time that would otherwise sit on the critical path of every update."""
     key = (np.asarray(mu, dtype=np.float64).tobytes(), np.asarray(P, dtype=np.float64).tobytes(),
-           None if device_put is None else getattr(device_put, "cache_key", None))
+           None if device_put is None else getattr(device_put, "cache_key", id(device_put)))
     hit = _IMAGE_TABLE_CACHE.get(key)
     if hit is None:
         table, n_img = wn_image_table(mu, P)

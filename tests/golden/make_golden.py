@@ -296,7 +296,44 @@ def resample_cases(seed=8):
     save("resample_cases", **arrs)
 
 
+def hypercylindrical(seed=9):
+    """HypercylindricalDiracDistribution (periodic dims first, then linear) -- hybrid_mean,
+    hybrid_moment, linear_mean / linear_covariance, the marginals, and a reweigh + sample round trip"""
+    from pyrecest.distributions.cart_prod.hypercylindrical_dirac_distribution import HypercylindricalDiracDistribution
+
+    rng = np.random.default_rng(seed)
+    N = 900
+    arrs = {}
+    for tag, bd, ld in (("c21", 2, 1), ("c13", 1, 3), ("c22", 2, 2)):
+        d = np.column_stack([rng.random((N, bd)) * 2 * np.pi, rng.standard_normal((N, ld)) * 2.0 + np.arange(ld)])
+        w = rng.random(N)
+        w /= w.sum()
+        hd = HypercylindricalDiracDistribution(bd, d, w)
+        arrs[f"{tag}_d"], arrs[f"{tag}_w"] = d, w
+        arrs[f"{tag}_hybrid_mean"] = np.asarray(hd.hybrid_mean())
+        arrs[f"{tag}_hybrid_moment"] = np.asarray(hd.hybrid_moment())
+        arrs[f"{tag}_linear_mean"] = np.asarray(hd.linear_mean())
+        arrs[f"{tag}_linear_cov"] = np.atleast_2d(np.asarray(hd.linear_covariance()))
+        arrs[f"{tag}_per_m1"] = np.atleast_1d(hd.marginalize_linear().trigonometric_moment(1))
+        lik = np.exp(-0.5 * np.sum((d[:, bd:] - 1.0) ** 2, axis=1)) * (1.2 + np.cos(d[:, 0] - 1.0))
+        arrs[f"{tag}_lik"] = lik
+        rw = hd.reweigh(lambda x, bd=bd: np.exp(-0.5 * np.sum((x[:, bd:] - 1.0) ** 2, axis=1)) * (1.2 + np.cos(x[:, 0] - 1.0)))
+        arrs[f"{tag}_reweighed_w"] = rw.w
+        arrs[f"{tag}_reweighed_mean"] = np.asarray(rw.hybrid_mean())
+        u = rng.random(500)
+        with injected_draws(DrawQueue(uniforms=u)):
+            arrs[f"{tag}_sample"] = rw.sample(500)
+            arrs[f"{tag}_sample_idx"] = LAST["choice_idx"].copy()
+        arrs[f"{tag}_sample_u"] = u
+    save("hypercylindrical", **arrs)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # regenerate only the named fixtures
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
+    hypercylindrical()
     euclid_cv()
     torus_t3()
     torus_addmode()

@@ -361,3 +361,31 @@ def test_nonadditive_predict_and_hemispherical_filter(golden):
     est = host(hh.get_point_estimate())
     assert np.linalg.norm(est - np.array([0.0, 0.6, 0.8])) < 0.3 and est[-1] >= 0
     np.testing.assert_allclose(est, O.mean_axis(host(hh.filter_state.d), host(hh.filter_state.w)), atol=1e-10)
+
+
+@pytest.mark.parametrize("tag,bd", [("c21", 2), ("c13", 1), ("c22", 2)])
+def test_hypercylindrical_dirac_against_reference_run(golden, tag, bd):
+    """HypercylindricalDiracDistribution on the device vs the reference's own outputs"""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HypercylindricalDiracDistribution
+
+    g = golden("hypercylindrical")
+    d, w = g[f"{tag}_d"], g[f"{tag}_w"]
+    hd = HypercylindricalDiracDistribution(bd, d, w)
+    host = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    np.testing.assert_allclose(host(hd.hybrid_moment()), g[f"{tag}_hybrid_moment"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(host(hd.hybrid_mean()), g[f"{tag}_hybrid_mean"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(host(hd.mean()), g[f"{tag}_hybrid_mean"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(host(hd.linear_mean()), g[f"{tag}_linear_mean"], rtol=1e-12)
+    np.testing.assert_allclose(host(hd.linear_covariance()), g[f"{tag}_linear_cov"], rtol=1e-11)
+    np.testing.assert_allclose(host(hd.marginalize_linear().trigonometric_moment(1)), g[f"{tag}_per_m1"], rtol=1e-12)
+    np.testing.assert_allclose(host(hd.marginalize_periodic().mean()), g[f"{tag}_linear_mean"], rtol=1e-12)
+    rw = hd.reweigh(g[f"{tag}_lik"])  # likelihood values evaluated by the caller
+    np.testing.assert_allclose(host(rw.w), g[f"{tag}_reweighed_w"], rtol=1e-12)
+    np.testing.assert_allclose(host(rw.hybrid_mean()), g[f"{tag}_reweighed_mean"], rtol=1e-11)
+    rw.w = g[f"{tag}_reweighed_w"]  # the reference's weights bit for bit: the draw below must then pick the same indices
+    with prandom.inject(uniforms=g[f"{tag}_sample_u"]):
+        smp = rw.sample(500)
+    assert np.array_equal(host(smp), g[f"{tag}_sample"])
+    with pytest.raises(ValueError):
+        HypercylindricalDiracDistribution(0, d, w)

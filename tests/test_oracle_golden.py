@@ -162,3 +162,20 @@ def test_systematic_definition():
     assert np.all(np.diff(idx) >= 0) and idx.min() >= 0 and idx.max() <= 999
     counts = np.bincount(idx, minlength=1000)
     assert np.all(np.abs(counts - 1000 * w) < 1.0 + 1e-9)
+
+
+@pytest.mark.parametrize("tag,bd", [("c21", 2), ("c13", 1), ("c22", 2)])
+def test_hypercylindrical_moments_against_reference_run(golden, tag, bd):
+    """hybrid_mean / hybrid_moment / linear moments of HypercylindricalDiracDistribution,
+    reweigh and the sample round trip, all from a run of the real reference (tests/golden/make_golden.py)"""
+    g = golden("hypercylindrical")
+    d, w = g[f"{tag}_d"], g[f"{tag}_w"]
+    np.testing.assert_allclose(O.hybrid_moment(d, w, bd), g[f"{tag}_hybrid_moment"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(O.hybrid_mean(d, w, bd), g[f"{tag}_hybrid_mean"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(O.mean_linear(d[:, bd:], w), g[f"{tag}_linear_mean"], rtol=1e-13)
+    np.testing.assert_allclose(O.covariance_linear(d[:, bd:], w), g[f"{tag}_linear_cov"], rtol=1e-12)
+    w2 = O.reweigh(w, g[f"{tag}_lik"])
+    np.testing.assert_allclose(w2, g[f"{tag}_reweighed_w"], rtol=1e-13)
+    idx = O.multinomial_indices(g[f"{tag}_reweighed_w"], g[f"{tag}_sample_u"])
+    assert np.array_equal(idx, g[f"{tag}_sample_idx"])
+    assert np.array_equal(d[idx], g[f"{tag}_sample"])
