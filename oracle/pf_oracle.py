@@ -439,6 +439,32 @@ def hybrid_mean(d, w, bound_dim):
     return np.concatenate((mean_direction_torus(np.mod(d[:, :bound_dim], TWO_PI), w), mean_linear(d[:, bound_dim:], w)))
 
 
+def angular_error(alpha, beta):
+    """AbstractHypertoroidalDistribution.angular_error
+    (pyrecest/distributions/hypertorus/abstract_hypertoroidal_distribution.py:146-167)."""
+    diff = np.abs(np.mod(alpha, TWO_PI) - np.mod(beta, TWO_PI))
+    return np.minimum(diff, TWO_PI - diff)
+
+
+def distance(manifold_name, est, true):
+    """pyrecest/evaluation/get_distance_function.py:14-56 for one (estimate, groundtruth) pair."""
+    if "circle" in manifold_name or "hypertorus" in manifold_name:
+        return np.linalg.norm(angular_error(est, true))
+    if "hypersphere" in manifold_name:
+        return np.arccos(np.dot(est, true))
+    if "uclidean" in manifold_name:
+        return np.linalg.norm(est - true)
+    raise NotImplementedError(manifold_name)
+
+
+def summarize(manifold_name, last_estimates, groundtruths, runtimes, run_failed):
+    """determine_all_deviations (pyrecest/evaluation/determine_all_deviations.py:9-52) + summarize_filter_results
+    (pyrecest/evaluation/summarize_filter_results.py:40-58): rows (error_mean, error_std, time_mean, failure_rate)."""
+    dev = np.array([[distance(manifold_name, e, g[-1]) for e, g in zip(est_c, groundtruths)] for est_c in last_estimates])
+    return dev, np.column_stack([dev.mean(axis=1), dev.std(axis=1), np.mean(runtimes, axis=1),
+                                 np.sum(run_failed, axis=1) / run_failed.shape[1]])
+
+
 def mean_resultant(d, w):
     """HypersphericalDiracDistribution.mean_resultant_vector
     (pyrecest/distributions/hypersphere_subset/hyperspherical_dirac_distribution.py:43-44)."""

@@ -84,7 +84,10 @@ class BatchedParticleFilter:
     def update_identity(self, meas_noise, measurements):
         """measurements: (n_runs, d) -- run r is weighted with meas_noise.set_mode(measurements[r]).pdf
         (abstract_particle_filter.py:95-125 per run), then resampled n of n."""
-        z = R._np(measurements).reshape(self.n_runs, -1)
+        if isinstance(measurements, torch.Tensor):  # already on the device (evaluation.generate_measurements): stays there
+            z = measurements.reshape(self.n_runs, -1)
+        else:
+            z = R._np(measurements).reshape(self.n_runs, -1)
         if z.shape[1] != self.D:
             raise AssertionError("measurement dimension does not match the filter state")
         flat = self.flat
@@ -199,7 +202,7 @@ def iterate_configs_and_runs(groundtruths, measurements, scenario_config, filter
     evaluation_config = evaluation_config or {}
     if evaluation_config.get("extract_all_point_estimates", False) or evaluation_config.get("convert_to_point_estimate_during_runtime", False):
         raise NotImplementedError("This is not implemented yet.")
-    meas = R._np(measurements)
+    meas = measurements if isinstance(measurements, torch.Tensor) else R._np(measurements)
     n_runs, T = meas.shape[0], scenario_config["n_timesteps"]
     apply = scenario_config.get("apply_sys_noise_times", [True] * (T - 1) + [False])
     manifold = _manifold_name(scenario_config["manifold"])
@@ -239,3 +242,127 @@ def iterate_configs_and_runs(groundtruths, measurements, scenario_config, filter
         last_estimates.append(est.cpu().numpy())
     iterate_configs_and_runs.last_estimates = np.stack(last_estimates)
     return last_filter_states, run_times, run_failed, groundtruths, measurements
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Either side of the runner: scenario generation and the error summary for all runs at once,
+# on the device, so that a Monte-Carlo study never moves per-run data through the host.  These are (n_runs, d)
+# tensor operations -- plumbing, not kernels; the draws come from the same sources as the filters' (pyrecest_b200.random).
+# ---------------------------------------------------------------------------------------------------------------
+def _sample_on_device(dist, n):
+    s = R.as_distribution(dist).sample(n)
+    if not isinstance(s, torch.Tensor):  # a reference (numpy-backend) distribution object: its draws come from the host
+        dev = torch.device("cuda", torch.cuda.current_device())
+        s = torch.as_tensor(np.asarray(s, dtype=np.float64), device=dev)
+    return s.reshape(n, -1)
+
+
+def generate_groundtruths(scenario_config, n_runs):
+    """pyrecest/evaluation/generate_groundtruth.py:7-94 for every run at once (n_targets = 1, identity system model
+    with additive `sys_noise`, the case the particle-filter scenarios use): x_0 ~ initial_prior,
+    x_t = x_{t-1} + sys_noise.sample().  Like the reference, the walk is NOT wrapped on periodic manifolds.
+    Returns a device tensor (n_runs, n_timesteps, d)."""
+    if "gen_next_state_with_noise" in scenario_config or "gen_next_state_without_noise" in scenario_config:
+        raise NotImplementedError("only the identity system model with additive sys_noise is generated on the device")
+    if scenario_config.get("n_targets", 1) != 1:
+        raise NotImplementedError("multi-target scenarios are outside the particle-filter path")
+    if "sys_noise" not in scenario_config:
+        raise ValueError("Cannot generate groundtruth.")
+    T = int(scenario_config["n_timesteps"])
+    x = _sample_on_device(scenario_config["initial_prior"], n_runs)
+    out = [x]
+    for _ in range(1, T):
+        x = x + _sample_on_device(scenario_config["sys_noise"], n_runs)
+        out.append(x)
+    return torch.stack(out, dim=1)
+
+
+def generate_measurements(groundtruths, scenario_config, reference_indexing=True):
+    """pyrecest/evaluation/generate_measurements.py:147-184 for every run at once, one measurement per time step:
+    hypertoroidal noise -> mod(x + noise, 2 pi); Gaussian -> x + noise; von Mises-Fisher -> a draw around x.
+    reference_indexing: the reference reads groundtruth[t - 1] for the measurement of step t (so step 0 sees the LAST
+    state); kept by default for identical behaviour, False pairs step t with groundtruth[t].
+    Returns a device tensor (n_runs, n_timesteps, d)."""
+    gt = groundtruths
+    n_runs, T = gt.shape[0], gt.shape[1]
+    noise = R.as_distribution(scenario_config["meas_noise"])
+    kind = R.kind_of(noise)
+    out = []
+    for t in range(T):
+        x = gt[:, (t - 1) % T if reference_indexing else t]
+        if kind in ("wn_multi", "wn_1d", "vm"):
+            z = x + _sample_on_device(noise, n_runs)
+            zw = torch.empty_like(z)
+            engine(z.device).wrap_2pi(z.contiguous(), zw)
+            out.append(zw)
+        elif kind == "gauss":
+            out.append(x + _sample_on_device(noise, n_runs))
+        elif kind == "vmf":
+            p = L.PredictParams()
+            p.mode, p.dim, p.noise_cols = L.PRED_SPHERE_VMF, 3, 3
+            p.kappa = float(R._np(noise.kappa))
+            p.exp_m2k = math.exp(-2.0 * p.kappa)
+            src = prandom.source()
+            modes = x.contiguous()
+            z = torch.empty_like(modes)
+            if src.fused:
+                p.rng_kind, p.rng_seed, p.rng_offset = L.RNG_VMF, src.seed, src.next_offset()
+                engine(modes.device).predict(p, modes, z, None)
+            else:
+                engine(modes.device).predict(p, modes, z, src.vmf_triples(n_runs, modes.device, modes.dtype))
+            out.append(z)
+        else:
+            raise NotImplementedError(f"measurement noise {type(noise).__name__} is not generated on the device")
+    return torch.stack(out, dim=1)
+
+
+def get_distance_function(manifold_name):
+    """pyrecest/evaluation/get_distance_function.py:14-56, vectorised over runs: (n_runs, d) x (n_runs, d) -> (n_runs,)"""
+    if "Symm" in manifold_name:
+        raise NotImplementedError("Not implemented yet")
+    if "circle" in manifold_name or "hypertorus" in manifold_name:
+
+        def distance_function(xest, xtrue):  # norm of AbstractHypertoroidalDistribution.angular_error (:146-167)
+            diff = torch.abs(torch.remainder(xest, TWO_PI) - torch.remainder(xtrue, TWO_PI))
+            return torch.linalg.norm(torch.minimum(diff, TWO_PI - diff), dim=-1)
+
+    elif "hypersphere" in manifold_name:
+
+        def distance_function(x1, x2):
+            return torch.arccos(torch.sum(x1 * x2, dim=-1))
+
+    elif ("euclidean" in manifold_name or "Euclidean" in manifold_name) and "MTT" not in manifold_name:
+
+        def distance_function(x1, x2):
+            return torch.linalg.norm(x1 - x2, dim=-1)
+
+    else:
+        raise NotImplementedError(f"distance on {manifold_name} is outside the particle-filter path")
+    return distance_function
+
+
+def determine_all_deviations(last_estimates, groundtruths, manifold_name):
+    """pyrecest/evaluation/determine_all_deviations.py:9-52: distance between the final estimate of every
+    (configuration, run) and the last groundtruth state.  last_estimates: (n_configs, n_runs, d)."""
+    gt = groundtruths
+    est = torch.as_tensor(last_estimates, device=gt.device, dtype=gt.dtype) if not isinstance(last_estimates, torch.Tensor) else last_estimates
+    dist = get_distance_function(manifold_name)
+    dev = torch.stack([dist(est[c].reshape(gt.shape[0], -1), gt[:, -1]) for c in range(est.shape[0])])
+    if bool(torch.any(torch.isinf(dev))):
+        warnings.warn("Some of the errors are infinite.")
+    return dev
+
+
+def summarize_filter_results(scenario_config, filter_configs, runtimes, groundtruths, run_failed, last_estimates):
+    """pyrecest/evaluation/summarize_filter_results.py:11-58: error_mean / error_std / time_mean / failure_rate per
+    configuration (population std, like numpy's)."""
+    dev = determine_all_deviations(last_estimates, groundtruths, scenario_config["manifold"])
+    err_mean = dev.mean(dim=1).cpu().numpy()
+    err_std = dev.std(dim=1, unbiased=False).cpu().numpy()
+    times = np.mean(R._np(runtimes), axis=1)
+    failed = R._np(run_failed)
+    rates = failed.sum(axis=1) / failed.shape[1]
+    results = copy.deepcopy(list(filter_configs))
+    for d, e, s, tm, fr in zip(results, err_mean, err_std, times, rates):
+        d["error_mean"], d["error_std"], d["time_mean"], d["failure_rate"] = float(e), float(s), float(tm), float(fr)
+    return results

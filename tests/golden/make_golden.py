@@ -328,6 +328,45 @@ def hypercylindrical(seed=9):
     save("hypercylindrical", **arrs)
 
 
+def evaluation_summary(seed=10):
+    """the error summary either side of the batched Monte-Carlo runner -- the reference's
+    get_distance_function / determine_all_deviations / summarize_filter_results on given final estimates"""
+    from pyrecest.evaluation.determine_all_deviations import determine_all_deviations
+    from pyrecest.evaluation.get_distance_function import get_distance_function
+    from pyrecest.evaluation.summarize_filter_results import summarize_filter_results
+
+    rng = np.random.default_rng(seed)
+    R, T, C = 1200, 4, 2
+    arrs = {}
+    for tag, manifold, d in (("torus", "hypertorus", 3), ("circle", "circle", 1), ("sphere", "hypersphere", 3), ("euclid", "Euclidean", 4)):
+        if tag == "sphere":
+            gt = rng.standard_normal((R, T, d))
+            gt /= np.linalg.norm(gt, axis=-1, keepdims=True)
+            est = gt[None, :, -1, :] + 0.2 * rng.standard_normal((C, R, d))
+            est /= np.linalg.norm(est, axis=-1, keepdims=True)
+        elif tag == "euclid":
+            gt = rng.standard_normal((R, T, d)) * 3
+            est = gt[None, :, -1, :] + rng.standard_normal((C, R, d))
+        else:
+            gt = rng.random((R, T, d)) * 4 * np.pi - 2 * np.pi          # groundtruth walks are not wrapped
+            est = np.mod(gt[None, :, -1, :] + 0.3 * rng.standard_normal((C, R, d)), 2 * np.pi)
+        gts = np.empty((R, T), dtype=object)
+        for r in range(R):
+            for t in range(T):
+                gts[r, t] = gt[r, t]
+        results = [[est[c, r] for r in range(R)] for c in range(C)]
+        dist = get_distance_function(manifold)
+        dev = determine_all_deviations(results, None, dist, gts)
+        runtimes = rng.random((C, R)) * 1e-3
+        failed = rng.random((C, R)) < 0.01
+        summ = summarize_filter_results({"manifold": manifold, "mtt": False}, [{"name": "pf", "parameter": 10}, {"name": "pf", "parameter": 20}],
+                                        runtimes, gts, failed, last_filter_states=results)  # (last_estimates alone raises in the reference)
+        arrs[f"{tag}_gt"], arrs[f"{tag}_est"], arrs[f"{tag}_dev"] = gt, est, dev
+        arrs[f"{tag}_runtimes"], arrs[f"{tag}_failed"] = runtimes, failed
+        arrs[f"{tag}_summary"] = np.array([[s_["error_mean"], s_["error_std"], s_["time_mean"], s_["failure_rate"]] for s_ in summ])
+    save("evaluation_summary", **arrs)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # regenerate only the named fixtures
         for name in sys.argv[1:]:

@@ -106,3 +106,69 @@ def test_iterate_configs_and_runs_like_reference_evaluation():
     err = np.linalg.norm(est - gt[None, :, -1, :], axis=2).mean(axis=1)
     assert err[1] < 1.0 and err[0] < 1.2, err
     assert states[1].d.shape == (n_runs, 2000, 2)
+
+
+@pytest.mark.parametrize("tag,manifold", [("torus", "hypertorus"), ("circle", "circle"), ("sphere", "hypersphere"), ("euclid", "Euclidean")])
+def test_device_error_summary_against_reference_run(tag, manifold):
+    """evaluation.determine_all_deviations / summarize_filter_results on the device == the reference's (golden)"""
+    from conftest import load_golden
+    from pyrecest_b200 import evaluation as E
+
+    g = load_golden("evaluation_summary")
+    gt = torch.as_tensor(g[f"{tag}_gt"], device="cuda:0")
+    est = torch.as_tensor(g[f"{tag}_est"], device="cuda:0")
+    dev = E.determine_all_deviations(est, gt, manifold)
+    np.testing.assert_allclose(host(dev), g[f"{tag}_dev"], rtol=1e-12, atol=1e-14)
+    cfgs = [{"name": "pf", "parameter": 10}, {"name": "pf", "parameter": 20}]
+    rows = E.summarize_filter_results({"manifold": manifold}, cfgs, g[f"{tag}_runtimes"], gt, g[f"{tag}_failed"], est)
+    got = np.array([[r["error_mean"], r["error_std"], r["time_mean"], r["failure_rate"]] for r in rows])
+    np.testing.assert_allclose(got, g[f"{tag}_summary"], rtol=1e-11)
+    assert "error_mean" not in cfgs[0]  # the caller's configs are not modified
+
+
+def test_device_scenario_generation_statistics():
+    """generate_groundtruths / generate_measurements: random walk increments and measurement residuals have the
+    moments of the configured noises; the reference's t-1 indexing is reproduced; a full study runs end to end"""
+    from pyrecest_b200 import evaluation as E
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution, HypertoroidalWrappedNormalDistribution as HWN
+    from pyrecest_b200.distributions import VonMisesFisherDistribution
+
+    prandom.seed(77)
+    R_, T = 20_000, 4
+    C = np.array([[0.05, 0.01], [0.01, 0.03]])
+    sc = {"n_timesteps": T, "manifold": "hypertorus", "initial_prior": HWN(np.array([1.0, 2.0]), 4 * C),
+          "sys_noise": HWN(np.zeros(2), C), "meas_noise": HWN(np.zeros(2), 0.5 * C)}
+    gt = E.generate_groundtruths(sc, R_)
+    assert gt.shape == (R_, T, 2)
+    inc = host(gt[:, 1:] - gt[:, :-1]).reshape(-1, 2)
+    inc = np.mod(inc + np.pi, 2 * np.pi) - np.pi
+    np.testing.assert_allclose(np.cov(inc.T), C, atol=2e-3)
+    z = E.generate_measurements(gt, sc)
+    assert float(z.min()) >= 0 and float(z.max()) < 2 * np.pi
+    res = host(z[:, 2] - gt[:, 1])  # reference indexing: the measurement of step t belongs to groundtruth[t - 1]
+    res = np.mod(res + np.pi, 2 * np.pi) - np.pi
+    np.testing.assert_allclose(np.cov(res.T), 0.5 * C, atol=2e-3)
+    z2 = E.generate_measurements(gt, sc, reference_indexing=False)
+    res2 = np.mod(host(z2[:, 2] - gt[:, 2]) + np.pi, 2 * np.pi) - np.pi
+    np.testing.assert_allclose(np.cov(res2.T), 0.5 * C, atol=2e-3)
+    # Euclidean + sphere measurement models
+    sce = {"n_timesteps": 3, "manifold": "Euclidean", "initial_prior": GaussianDistribution(np.zeros(2), np.eye(2)),
+           "sys_noise": GaussianDistribution(np.zeros(2), C), "meas_noise": GaussianDistribution(np.zeros(2), C)}
+    ge = E.generate_groundtruths(sce, 5000)
+    ze = E.generate_measurements(ge, sce, reference_indexing=False)
+    np.testing.assert_allclose(np.cov(host(ze - ge).reshape(-1, 2).T), C, atol=3e-3)
+    modes = torch.zeros((5000, 1, 3), dtype=torch.float64, device="cuda:0")
+    modes[..., 2] = 1.0
+    zs = E.generate_measurements(modes, {"meas_noise": VonMisesFisherDistribution(np.array([0.0, 0.0, 1.0]), 20.0)})
+    np.testing.assert_allclose(host(torch.linalg.norm(zs, dim=-1)), 1.0, atol=1e-12)
+    assert abs(float(zs[:, 0, 2].mean()) - (1 / np.tanh(20.0) - 1 / 20.0)) < 5e-3
+    # the whole study on the device: scenario -> batched filters -> summary
+    small = dict(sc, n_timesteps=3)
+    gts = E.generate_groundtruths(small, 64)
+    meas = E.generate_measurements(gts, small, reference_indexing=False)
+    cfgs = [{"name": "pf", "parameter": [500, 2000]}]
+    states, times, failed, _, _ = E.iterate_configs_and_runs(gts, meas, small, cfgs, {"tolerate_failure": True})
+    rows = E.summarize_filter_results(small, [{"name": "pf", "parameter": 500}, {"name": "pf", "parameter": 2000}], times,
+                                      gts, failed, E.iterate_configs_and_runs.last_estimates)
+    assert all(0 < r["error_mean"] < 0.5 for r in rows)

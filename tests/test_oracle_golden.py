@@ -179,3 +179,13 @@ def test_hypercylindrical_moments_against_reference_run(golden, tag, bd):
     idx = O.multinomial_indices(g[f"{tag}_reweighed_w"], g[f"{tag}_sample_u"])
     assert np.array_equal(idx, g[f"{tag}_sample_idx"])
     assert np.array_equal(d[idx], g[f"{tag}_sample"])
+
+
+@pytest.mark.parametrize("tag,manifold", [("torus", "hypertorus"), ("circle", "circle"), ("sphere", "hypersphere"), ("euclid", "Euclidean")])
+def test_evaluation_summary_against_reference_run(golden, tag, manifold):
+    """deviations and summary rows equal the reference's determine_all_deviations /
+    summarize_filter_results on the same estimates"""
+    g = golden("evaluation_summary")
+    dev, rows = O.summarize(manifold, g[f"{tag}_est"], g[f"{tag}_gt"], g[f"{tag}_runtimes"], g[f"{tag}_failed"])
+    np.testing.assert_allclose(dev, g[f"{tag}_dev"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(rows, g[f"{tag}_summary"], rtol=1e-12)
