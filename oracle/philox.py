@@ -100,29 +100,47 @@ def vm_strip_table(kappa, K=VM_STRIPS):
     return table, hi
 
 
+def _stream_bits(words, start, length):
+    """bits [start, start + length) of the little-endian bit stream made of the uint32 columns of `words` (length <= 32)"""
+    i, o = start >> 5, start & 31
+    lo = words[:, i].astype(np.uint64)
+    hi = words[:, i + 1].astype(np.uint64) if i + 1 < words.shape[1] else np.zeros_like(lo)
+    return ((lo | (hi << np.uint64(32))) >> np.uint64(o)) & np.uint64((1 << length) - 1)
+
+
+def _vm_attempt(words, s0, kap, tables):
+    """one attempt per row from the 85 bits at s0: (theta >= 0, sign bit, accepted) -- pfb_common.cuh vonmises_attempt"""
+    v32 = _stream_bits(words, s0, 32)
+    strip = _stream_bits(words, s0 + 32, 12)
+    sign = _stream_bits(words, s0 + 44, 1).astype(bool)
+    u = ((_stream_bits(words, s0 + 45, 20) << np.uint64(20)) | _stream_bits(words, s0 + 65, 20)).astype(np.float64) * 2.0**-40
+    if kap < 1e-8:
+        return np.pi * u, sign, np.ones(u.shape, dtype=bool)
+    table, A = tables[kap]
+    t = table[strip.astype(np.int64)]
+    th = t[:, 0] + u * t[:, 1]
+    v = (v32.astype(np.float64) + 0.5) * 2.0**-32
+    return th, sign, v * A < np.exp(-2.0 * kap * np.sin(0.5 * th) ** 2) * t[:, 1]
+
+
 def vonmises(seed, offset, n, kappas, tables):
-    """the zero-mean von Mises draws of PFB_RNG_VONMISES, (n, D): vertical-strip rejection, one Philox block
-    (slot 16 + c + 8 attempt) per attempt.  tables: {kappa: (table, A)}.  The acceptance test is the fp64 one (the
-    kernel decides in fp32 only where fp32 cannot get it wrong)."""
+    """the zero-mean von Mises draws of PFB_RNG_VONMISES, (n, D): vertical-strip rejection.  The first attempts of
+    all dimensions are cut from one bit stream of ceil(85 D / 128) Philox blocks (slots 16, 17, ...), 85 bits each;
+    a rejected dimension c retries with a block of its own (slot 48 + 8 attempt + c).  tables: {kappa: (table, A)}.
+    The acceptance test is the fp64 one (the kernel decides in fp32 only where fp32 cannot get it wrong)."""
     D = len(kappas)
     out = np.empty((n, D))
     idx = np.arange(n, dtype=np.uint64)
+    nb = (85 * D + 127) // 128
+    words = np.concatenate([rng_block(seed, offset, idx, 16 + b) for b in range(nb)], axis=1)
     for c, kap in enumerate(kappas):
-        pending = np.arange(n)
-        attempt = 0
+        th, sign, acc = _vm_attempt(words, 85 * c, kap, tables)
+        out[:, c] = np.where(sign, th, -th)
+        pending = np.nonzero(~acc)[0]
+        attempt = 1
         while pending.size:
-            r = rng_block(seed, offset, idx[pending], 16 + c + 8 * attempt)
-            u = u53(r[:, 1], r[:, 2])
-            if kap < 1e-8:
-                th = np.pi * u
-                acc = np.ones(pending.size, dtype=bool)
-            else:
-                table, A = tables[kap]
-                t = table[r[:, 0] >> np.uint32(20)]
-                th = t[:, 0] + u * t[:, 1]
-                v = (r[:, 3].astype(np.float64) + 0.5) * 2.0**-32
-                acc = v * A < np.exp(-2.0 * kap * np.sin(0.5 * th) ** 2) * t[:, 1]
-            sign = (r[:, 0] & np.uint32(1)).astype(bool)
+            w = rng_block(seed, offset, idx[pending], 48 + 8 * attempt + c)
+            th, sign, acc = _vm_attempt(w, 0, kap, tables)
             out[pending[acc], c] = np.where(sign[acc], th[acc], -th[acc])
             pending = pending[~acc]
             attempt += 1

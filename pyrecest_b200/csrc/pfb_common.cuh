@@ -132,47 +132,79 @@ __device__ __forceinline__ void normal_pair(const uint4& r, double* z0, double* 
 }
 // Zero-mean von Mises draws in (-pi, pi) for D dimensions at once: vertical-strip rejection.  g(t) =
 // exp(kappa (cos t - 1)) is decreasing on [0, pi]; the host cuts [0, pi] into PFB_VM_STRIPS strips [a_k, a_k + w_k)
-// whose hats g(a_k) w_k all have the same area A (pfb_vm_strip_table).  One Philox block is one attempt:
-//   word 0: strip k (top 12 bits) and the sign (bit 0);  words 1-2: 53-bit position u, t = a_k + u w_k;
-//   word 3: acceptance uniform v in (0, 1): accept iff v A < g(t) w_k.
-// ~99.95 % of the attempts are accepted, so a warp almost never loops (the wrapped-Cauchy rejection it replaces
+// whose hats g(a_k) w_k all have the same area A (pfb_vm_strip_table).  An attempt: strip k, position u in [0, 1),
+// t = a_k + u w_k, sign, acceptance uniform v in (0, 1): accept iff v A < g(t) w_k.
+// ~99.9 % of the attempts are accepted, so a warp almost never loops (the wrapped-Cauchy rejection it replaces
 // accepted ~2/3 and cost three times the instructions through divergence).  The test is decided in fp32 when it
 // is clear of the fp32 error bound and in fp64 otherwise, so the decision is the fp64 one (oracle/philox.py).
+// Bit budget: an attempt needs 85 random bits -- acceptance uniform 32, strip 12, sign 1, position 2 x 20 (a 40-bit
+// position inside a strip of width ~1e-3 rad resolves 1e-15 rad, the spacing of doubles near 1) -- so the first
+// attempts of all D dimensions are cut from ONE bit stream of ceil(85 D / 128) Philox blocks (slots 16, 17, ..:
+// 2 blocks instead of 3 for D = 3); the rare retry of dimension c takes a block of its own (slot 48 + 8 attempt + c).
+template <int NW>
+__device__ __forceinline__ uint32_t stream_bits(const uint32_t (&w)[NW], int start, int len) {
+  const int i = start >> 5, o = start & 31;
+  const uint64_t lo = w[i], hi = (i + 1 < NW) ? w[i + 1] : 0u;
+  return (uint32_t)((lo | (hi << 32)) >> o) & (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u));
+}
+
+__device__ __forceinline__ bool vonmises_attempt(const pfb_predict_params& p, int c, uint32_t v32, uint32_t strip,
+                                                 uint32_t uhi, uint32_t ulo, double* th_out) {
+  const double u = (double)(((uint64_t)uhi << 20) | ulo) * 9.094947017729282e-13;  // 2^-40
+  const double kap = p.rng_kappa[c];
+  if (kap < 1e-8) {
+    *th_out = 3.141592653589793 * u;  // uniform on the circle
+    return true;
+  }
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p.rng_vm_table_dev) +
+                          (int64_t)p.rng_vm_table_idx[c] * PFB_VM_STRIPS + strip);
+  const double th = t.x + u * t.y;
+  *th_out = th;
+  const float kf = (float)kap;
+  const float sh = __sinf(0.5f * (float)th);  // |error| < 5e-7 on [0, pi/2]: inside the margin below
+  const float rhs = __expf(-2.0f * kf * sh * sh) * (float)t.y;
+  const float lhs = ((float)v32 + 0.5f) * 2.3283064365386963e-10f * (float)p.rng_vm_area[c];
+  const float margin = (4e-6f * kf + 8e-6f) * rhs;
+  if (lhs > rhs + margin) return false;
+  if (lhs >= rhs - margin) {  // too close for fp32
+    const double sd = sinpi(th * 0.15915494309189535);  // sin(th / 2) without the large-argument path
+    const double vd = ((double)v32 + 0.5) * 2.3283064365386963e-10;
+    return vd * p.rng_vm_area[c] < exp(-2.0 * kap * sd * sd) * t.y;
+  }
+  return true;
+}
+
 template <int D>
 __device__ __forceinline__ void vonmises_draws(const RngKey& k, uint64_t index, const pfb_predict_params& p,
                                                double (&out)[D]) {
-  uint32_t pending = (1u << D) - 1u;
-  for (uint32_t attempt = 0; pending != 0u; ++attempt) {
+  constexpr int NB = (85 * D + 127) / 128;
+  uint32_t w[4 * NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const uint4 r = rng_block(k, index, 16u + (uint32_t)b);
+    w[4 * b] = r.x; w[4 * b + 1] = r.y; w[4 * b + 2] = r.z; w[4 * b + 3] = r.w;
+  }
+  uint32_t pending = 0u;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const int s0 = 85 * c;
+    double th;
+    const bool ok = vonmises_attempt(p, c, stream_bits(w, s0, 32), stream_bits(w, s0 + 32, 12),
+                                     stream_bits(w, s0 + 45, 20), stream_bits(w, s0 + 65, 20), &th);
+    out[c] = stream_bits(w, s0 + 44, 1) ? th : -th;
+    if (!ok) pending |= 1u << c;
+  }
+  for (uint32_t attempt = 1; pending != 0u; ++attempt) {  // ~1.3e-3 of the draws get here
 #pragma unroll
     for (int c = 0; c < D; ++c) {
       if (!((pending >> c) & 1u)) continue;
-      const uint4 r = rng_block(k, index, 16u + (uint32_t)c + 8u * attempt);
-      const double u = u53(r.y, r.z);
-      const double kap = p.rng_kappa[c];
+      const uint4 r = rng_block(k, index, 48u + 8u * attempt + (uint32_t)c);
+      const uint32_t ww[4] = {r.x, r.y, r.z, r.w};
       double th;
-      bool accept = true;
-      if (kap < 1e-8) {
-        th = 3.141592653589793 * u;  // uniform on the circle
-      } else {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(p.rng_vm_table_dev) +
-                                (int64_t)p.rng_vm_table_idx[c] * PFB_VM_STRIPS + (r.x >> 20));
-        th = t.x + u * t.y;
-        const float kf = (float)kap;
-        const float sh = __sinf(0.5f * (float)th);  // |error| < 5e-7 on [0, pi/2]: inside the margin below
-        const float rhs = __expf(-2.0f * kf * sh * sh) * (float)t.y;
-        const float lhs = ((float)r.w + 0.5f) * 2.3283064365386963e-10f * (float)p.rng_vm_area[c];
-        const float margin = (4e-6f * kf + 8e-6f) * rhs;
-        if (lhs > rhs + margin) {
-          accept = false;
-        } else if (lhs >= rhs - margin) {  // too close for fp32
-          const double sd = sinpi(th * 0.15915494309189535);  // sin(th / 2) without the large-argument path
-          const double vd = ((double)r.w + 0.5) * 2.3283064365386963e-10;
-          accept = vd * p.rng_vm_area[c] < exp(-2.0 * kap * sd * sd) * t.y;
-        }
-        if (attempt >= 64u) accept = true;  // unreachable in practice (rejection probability ~5e-4 per attempt)
-      }
-      if (accept) {
-        out[c] = (r.x & 1u) ? th : -th;
+      const bool ok = vonmises_attempt(p, c, stream_bits(ww, 0, 32), stream_bits(ww, 32, 12), stream_bits(ww, 45, 20),
+                                       stream_bits(ww, 65, 20), &th) || attempt >= 64u;
+      if (ok) {
+        out[c] = stream_bits(ww, 44, 1) ? th : -th;
         pending &= ~(1u << c);
       }
     }
