@@ -970,9 +970,29 @@ __global__ void __launch_bounds__(kThreads) systematic_scatter_kernel(
   double acc[NE];
 #pragma unroll
   for (int k = 0; k < NE; ++k) acc[k] = 0.0;
-  const int64_t nround = (n + 31) & ~(int64_t)31;
+  // A piece [j_begin, j_end) of the comb (sharded filter: the offspring that go to one rank) comes from a contiguous
+  // range of sources: J(v_i) is monotone, so the first source with J(v_i) > j_begin and the first with
+  // J(v_i) >= j_end are found by bisection and only the sources in between are visited -- a small piece costs
+  // ~50 dependent probes instead of a pass over the whole shard.
+  __shared__ int64_t s_src[2];
+  int64_t i_first = 0, i_last = n - 1;
+  if (j_begin > 0 || j_end < n_comb) {
+    if (threadIdx.x == 0) {
+      auto J = [&](int64_t i) { return comb_count_below(__ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + i)), total), u0, dn, n_comb); };
+      int64_t lo = 0, hi = n - 1;  // first i in [0, n-1) with J(v_i) > j_begin, else n-1
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (J(mid) > j_begin) hi = mid; else lo = mid + 1; }
+      s_src[0] = lo;
+      hi = n - 1;                  // first i >= that with J(v_i) >= j_end, else n-1
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (J(mid) >= j_end) hi = mid; else lo = mid + 1; }
+      s_src[1] = lo;
+    }
+    __syncthreads();
+    i_first = s_src[0] & ~(int64_t)31;  // warps stay aligned to 32 consecutive sources
+    i_last = s_src[1];
+  }
+  const int64_t nround = (i_last + 1 + 31) & ~(int64_t)31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+  for (int64_t i = i_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
     // e = first slot that no longer belongs to source i
     int64_t e = j_end;
     if (i < n - 1) {

@@ -30,7 +30,9 @@ for it in range(4):
     pf.update_nonlinear_using_likelihood(lik.set_mode(P["z"]), u0=0.37)
     est = pf.get_point_estimate()
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    if rank == 0: print(f"iter {it}: total {1e3*(t1-t0):.1f} ms  " + "  ".join(f"{k} {1e3*v:.1f}" for k, v in acc.items()), pf.last_plan["send"])
+    for r in range(world):
+        if rank == r: print(f"rank {r} iter {it}: total {1e3*(t1-t0):.1f} ms  " + "  ".join(f"{k} {1e3*v:.1f}" for k, v in acc.items()), pf.last_plan["send"], flush=True)
+        dist.barrier()
 # and the same loop without any instrumentation
 for k, f in orig.items(): setattr(dist, k, f)
 pf.backend = S.CudaShardBackend(pf.local._filter_state.device)
