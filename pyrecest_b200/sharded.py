@@ -77,13 +77,17 @@ def exchange_plan(B, rank, world, n_loc):
 # ----------------------------------------------------------------------------------------------------
 # the distributed resampling step (backend-agnostic)
 # ----------------------------------------------------------------------------------------------------
-def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out=None, est_kind=None):
+def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out=None, est_kind=None, peer_out=None):
     """x: (n_loc, D) local particles (already predicted), logw: (n_loc,), local_max: 1-element tensor.
     Returns the new local particles (n_loc, D).  `backend` provides
         scan(logw, shift) -> (cdf (n_loc,), total: 1-element tensor)
         offspring(cdf, offset, total, u0, j_begin, count, n_total, x, out=view, est_kind=None|"sum"|"trig")
             -> fills (count, D) rows; with est_kind returns the mean of those rows (or of their cos / sin)
-    Collectives: all_reduce(MAX) of 1 double, all_gather of 1 double per rank, all_to_all_v of particles."""
+    Collectives: all_reduce(MAX) of 1 double, all_gather of 1 double per rank, all_to_all_v of particles.
+    peer_out(r) -> (n_loc, D) tensor aliasing rank r's `out` buffer (symmetric memory over NVLink): when given, the
+    offspring kernels store the remote pieces straight into the peer's output slots -- no staging buffers, no
+    all_to_all -- and the caller must run a collective on the same stream before any rank reads `out` (the
+    estimate's all_reduce does)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n_loc, D = x.shape
@@ -119,7 +123,15 @@ def sharded_systematic_resample(backend, x, logw, local_max, u0, group=None, out
     # remote pieces: produced contiguously in destination-rank order, exchanged with one all_to_all_v
     send_remote = [0 if r == rank else send[r] for r in range(world)]
     recv_remote = [0 if r == rank else recv[r] for r in range(world)]
-    if world > 1:
+    if world > 1 and peer_out is not None:
+        for r in range(world):
+            if send_remote[r] > 0:
+                j0 = max(B[rank], r * n_loc)
+                produce(j0, send_remote[r], peer_out(r)[j0 - r * n_loc:j0 - r * n_loc + send_remote[r]])
+        if est_kind is None:  # (with an estimate, the caller's all_reduce of the sums is the barrier)
+            flag = torch.zeros(1, dtype=torch.float64, device=x.device)
+            dist.all_reduce(flag, group=group)
+    elif world > 1:
         sendbuf = torch.empty((sum(send_remote), D), dtype=x.dtype, device=x.device)
         pos = 0
         for r in range(world):
@@ -213,6 +225,45 @@ class ShardedParticleFilter:
         self.local.lazy_predict = True
         self.backend = CudaShardBackend(self.local._filter_state.device)
         self.last_plan = None
+        self._sym = None        # [(tensor, handle)] x 2: the two particle buffers in symmetric memory (peer stores)
+        self.peer_stores = True  # write remote offspring straight into the peer's buffer when symmetric memory works
+
+    def _symmetric_buffers(self, x):
+        """Both particle buffers of the ping-pong in torch symmetric memory, so that every rank holds peer pointers
+        to every other rank's output buffer.  Returns (x, peer_out) with x the current particles inside one of the
+        two buffers, or (x, None) when symmetric memory is not available (CPU / gloo, one rank, unsupported box)."""
+        loc = self.local
+        if not self.peer_stores or self.world == 1 or x.device.type != "cuda":
+            return x, None
+        if self._sym is None:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                grp = self.group if self.group is not None else dist.group.WORLD
+                bufs = []
+                for _ in range(2):
+                    t = symm_mem.empty(x.shape, dtype=x.dtype, device=x.device)
+                    bufs.append((t, symm_mem.rendezvous(t, grp.group_name)))
+                self._sym = bufs
+            except Exception as exc:  # noqa: BLE001 -- fall back to the all_to_all exchange, once, loudly
+                import warnings
+
+                warnings.warn(f"symmetric memory unavailable ({exc!r}): sharded resampling exchanges through all_to_all")
+                self.peer_stores = False
+                return x, None
+        (a, ha), (b, hb) = self._sym
+        if x.data_ptr() == a.data_ptr():
+            cur, nxt, hn = a, b, hb
+        elif x.data_ptr() == b.data_ptr():
+            cur, nxt, hn = b, a, ha
+        else:  # particles were (re)set from outside: move them into the symmetric pair
+            a.copy_(x)
+            cur, nxt, hn = a, b, hb
+            st = loc._filter_state
+            st._d = cur.reshape(st._d.shape)
+        loc._alt = nxt
+        shape, dtype = tuple(x.shape), x.dtype
+        return cur, (lambda r: hn.get_buffer(r, shape, dtype))
 
     # -- state -------------------------------------------------------------------------------------------
     @property
@@ -264,6 +315,7 @@ class ShardedParticleFilter:
             dist_obj = copy.deepcopy(dist_obj).set_mode(R._np(measurement))
         st = loc._filter_state
         x = loc._scratch()
+        x, peer_out = self._symmetric_buffers(x)
         eng = loc._eng()
         lp, keep = R.lik_params(dist_obj, x.shape[1], images_to_device=R.device_put(x.device))
         if loc._pending is not None:
@@ -284,7 +336,8 @@ class ShardedParticleFilter:
             dist.broadcast(t, src=0, group=self.group)
             u0 = float(t.cpu())
         new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt,
-                                                est_kind="trig" if self.manifold == "torus" else "sum")
+                                                est_kind="trig" if self.manifold == "torus" else "sum",
+                                                peer_out=peer_out)
         self.last_plan = plan
         self._est_sums = sharded_sum(plan["est_sums"], self.group)  # global sums over all N offspring
         loc._alt = x  # ping-pong
