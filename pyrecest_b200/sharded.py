@@ -225,6 +225,7 @@ class ShardedParticleFilter:
         self.local.lazy_predict = True
         self.backend = CudaShardBackend(self.local._filter_state.device)
         self.last_plan = None
+        self._u0_rng = None
         self._sym = None        # [(tensor, handle)] x 2: the two particle buffers in symmetric memory (peer stores)
         self.peer_stores = True  # write remote offspring straight into the peer's buffer when symmetric memory works
 
@@ -330,11 +331,18 @@ class ShardedParticleFilter:
             eng.loglik(lp, x, loc._logw)
         del keep
         local_max = eng.stats[L.STAT_MAX:L.STAT_MAX + 1].clone()
-        if u0 is None:  # one comb offset for the whole filter: drawn on rank 0, broadcast
+        if u0 is None:  # one comb offset for the whole filter, the same on every rank
             src = prandom.source()
-            t = src.uniforms((1,), x.device) if not src.fused else torch.rand(1, dtype=torch.float64, device=x.device)
-            dist.broadcast(t, src=0, group=self.group)
-            u0 = float(t.cpu())
+            if src.fused:  # host generator seeded once from rank 0: no per-step broadcast / device sync
+                if self._u0_rng is None:
+                    t = torch.randint(0, 2**62, (1,), dtype=torch.int64, device=x.device)
+                    dist.broadcast(t, src=0, group=self.group)
+                    self._u0_rng = np.random.default_rng(int(t.cpu()))
+                u0 = float(self._u0_rng.random())
+            else:  # injected draws (parity tests): rank 0's uniform, broadcast
+                t = src.uniforms((1,), x.device)
+                dist.broadcast(t, src=0, group=self.group)
+                u0 = float(t.cpu())
         new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt,
                                                 est_kind="trig" if self.manifold == "torus" else "sum",
                                                 peer_out=peer_out)
