@@ -43,7 +43,9 @@ constexpr int64_t kTileStateBytes = 192;  // 8 state columns + 8 warps x (max, s
 constexpr int kGuideShift = 3;           // guide table: one bucket per 2^3 = 8 cdf entries (rounded to pow2)
 
 inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
-inline int64_t ws_header() { return kWsCounters + kWsPartials; }
+constexpr int kWsJobCap = 16384;                          // (source, first slot, count) triples of heavy particles
+constexpr int64_t kWsJobs = (int64_t)kWsJobCap * 3 * 8;
+inline int64_t ws_header() { return kWsCounters + kWsPartials + kWsJobs; }
 // guide table of the resampling search: M = 2^k buckets, M >= n / 2^kGuideShift (PFB_GUIDE_SHIFT overrides)
 int guide_shift();
 inline int64_t guide_buckets(int64_t n) {
@@ -59,6 +61,7 @@ inline int64_t guide_offset(int64_t n) {
 struct Workspace {
   unsigned int* counters;
   double* partials;
+  long long* jobs;  // kWsJobCap triples (systematic resampling: offspring runs that are spread over the grid)
   unsigned char* tiles;
   int64_t tile_bytes;
   int32_t* guide;

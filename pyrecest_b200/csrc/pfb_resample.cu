@@ -56,6 +56,7 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   unsigned char* b = static_cast<unsigned char*>(ws);
   out->counters = reinterpret_cast<unsigned int*>(b);
   out->partials = reinterpret_cast<double*>(b + kWsCounters);
+  out->jobs = reinterpret_cast<long long*>(b + kWsCounters + kWsPartials);
   out->tiles = b + ws_header();
   out->tile_bytes = ws_bytes - ws_header();
   out->guide = reinterpret_cast<int32_t*>(b + guide_offset(n));
@@ -944,12 +945,21 @@ static int launch_moments_batched(int kind, int64_t n_runs, int64_t run_len, con
 __device__ __forceinline__ double comb_point(int64_t j, double u0, double dn) {
   return __ddiv_rn(__dadd_rn((double)j, u0), dn);
 }
+// u_j < v, i.e. fl(fl(j + u0) / dn) < v, decided without the division unless t = fl(j + u0) lies within 2^-51
+// (relative) of p = fl(v dn):  t <= p (1 - 2^-51)  =>  t / dn < v (1 - 2^-52)  =>  fl(t / dn) < v, and symmetrically.
+__device__ __forceinline__ bool comb_lt(int64_t j, double v, double p, double u0, double dn) {
+  const double t = __dadd_rn((double)j, u0);
+  if (t <= p * (1.0 - 4.440892098500626e-16)) return true;
+  if (t >= p * (1.0 + 4.440892098500626e-16)) return false;
+  return __ddiv_rn(t, dn) < v;
+}
 // #{j in [0, n_comb) : u_j < v}
 __device__ __forceinline__ int64_t comb_count_below(double v, double u0, double dn, int64_t n_comb) {
-  double g = ceil(v * dn - u0);
+  const double p = v * dn;
+  double g = ceil(p - u0);
   int64_t j = g <= 0.0 ? 0 : (g >= dn ? n_comb : (int64_t)g);
-  while (j > 0 && comb_point(j - 1, u0, dn) >= v) --j;
-  while (j < n_comb && comb_point(j, u0, dn) < v) ++j;
+  while (j > 0 && !comb_lt(j - 1, v, p, u0, dn)) --j;
+  while (j < n_comb && comb_lt(j, v, p, u0, dn)) ++j;
   return j;
 }
 
@@ -957,7 +967,8 @@ template <typename T, int D, int EST>
 __global__ void __launch_bounds__(kThreads) systematic_scatter_kernel(
     int64_t n, const double* __restrict__ cdf, double cdf_offset, double total_imm, double u0_imm,
     const double* __restrict__ u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count, int64_t n_comb,
-    const T* __restrict__ x_in, T* __restrict__ x_out, int64_t* __restrict__ idx_out, double* est_out, Workspace ws) {
+    const T* __restrict__ x_in, T* __restrict__ x_out, int64_t* __restrict__ idx_out, double* est_out, Workspace ws,
+    int64_t big_cnt) {
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
   __shared__ double red[NE * 32];
   const double total = (total_imm > 0.0) ? total_imm : __dadd_rn(cdf_offset, cdf[n - 1]);
@@ -1036,7 +1047,12 @@ __global__ void __launch_bounds__(kThreads) systematic_scatter_kernel(
         if (idx_out) idx_out[k] = i;
       }
     }
-    unsigned longmask = __ballot_sync(0xffffffffu, cnt > 2);
+    // a degenerate weight distribution (one particle holding > 1e-4 of the weight): queued, copied by the whole grid
+    if (cnt > big_cnt) {
+      const unsigned int slot = atomicAdd(ws.counters + 6, 1u);
+      if (slot < (unsigned int)kWsJobCap) { ws.jobs[3 * slot] = i; ws.jobs[3 * slot + 1] = sbeg - j_begin; ws.jobs[3 * slot + 2] = cnt; }
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, cnt > 2 && cnt <= big_cnt);
     while (longmask) {
       const int src = __ffs(longmask) - 1;
       longmask &= longmask - 1;
@@ -1075,13 +1091,38 @@ __global__ void __launch_bounds__(kThreads) systematic_scatter_kernel(
   }
 }
 
+// heavy particles: every queued run of offspring is copied by the whole grid
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) systematic_fill_kernel(const T* __restrict__ x_in, T* __restrict__ x_out,
+                                                                   int64_t* __restrict__ idx_out, Workspace ws) {
+  const unsigned int nj_raw = *reinterpret_cast<volatile unsigned int*>(ws.counters + 6);
+  const unsigned int nj = nj_raw < (unsigned int)kWsJobCap ? nj_raw : (unsigned int)kWsJobCap;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (unsigned int j = 0; j < nj; ++j) {
+    const int64_t src = ws.jobs[3 * j], s0 = ws.jobs[3 * j + 1], cnt = ws.jobs[3 * j + 2];
+    double r[D];
+    if (x_in != nullptr) load_rec<T, D>(x_in, src, r);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += stride) {
+      if (x_in != nullptr) store_rec<T, D>(x_out, s0 + t, r);
+      if (idx_out) idx_out[s0 + t] = src;
+    }
+  }
+  if (block_is_last(ws.counters + 7) && threadIdx.x == 0) ws.counters[6] = 0u;  // self-cleaning
+}
+
 template <typename T, int D>
 static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, double total_imm, double u0_imm,
                              const double* u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count,
                              int64_t n_comb, const void* x_in, void* x_out, int64_t* idx_out, int est_kind,
                              double* est_out, Workspace W, cudaStream_t st) {
   const int grid = stream_grid(n);
-#define PFB_SYS_LAUNCH(E) systematic_scatter_kernel<T, D, E><<<grid, kThreads, 0, st>>>(n, cdf, cdf_offset, total_imm, u0_imm, u0_ptr, key, u0_mode, j_begin, count, n_comb, (const T*)x_in, (T*)x_out, idx_out, est_out, W)
+  // heavy sources go through the job list of the workspace (at most n_comb / big_cnt <= 8192 of them); without a
+  // workspace their warp writes them
+  const bool have_jobs = W.jobs != nullptr && W.counters != nullptr;
+  int64_t big_cnt = n_comb >> 13;
+  if (big_cnt < 8192) big_cnt = 8192;
+  if (!have_jobs) big_cnt = (int64_t)1 << 30;
+#define PFB_SYS_LAUNCH(E) systematic_scatter_kernel<T, D, E><<<grid, kThreads, 0, st>>>(n, cdf, cdf_offset, total_imm, u0_imm, u0_ptr, key, u0_mode, j_begin, count, n_comb, (const T*)x_in, (T*)x_out, idx_out, est_out, W, big_cnt)
   switch (est_kind) {
     case PFB_EST_NONE: PFB_SYS_LAUNCH(PFB_EST_NONE); break;
     case PFB_EST_SUM: PFB_SYS_LAUNCH(PFB_EST_SUM); break;
@@ -1089,6 +1130,7 @@ static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, do
     default: set_error("bad est_kind %d", est_kind); return PFB_ERR_INVALID;
   }
 #undef PFB_SYS_LAUNCH
+  if (have_jobs) systematic_fill_kernel<T, D><<<sm_count() * 4, kThreads, 0, st>>>((const T*)x_in, (T*)x_out, idx_out, W);
   return PFB_OK;
 }
 
@@ -1326,8 +1368,8 @@ extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, con
   cudaStream_t st = (cudaStream_t)stream;
   Workspace W{};
   int rc = PFB_OK;
-  if (est_kind != PFB_EST_NONE) {
-    if (!est_out || !x_in) { set_error("estimate requested without output / particles"); return PFB_ERR_INVALID; }
+  if (est_kind != PFB_EST_NONE && (!est_out || !x_in)) { set_error("estimate requested without output / particles"); return PFB_ERR_INVALID; }
+  if (est_kind != PFB_EST_NONE || ws != nullptr) {  // (the workspace also carries the job list of heavy particles)
     rc = carve_workspace(ws, ws_bytes, 0, &W);
     if (rc) return rc;
   }

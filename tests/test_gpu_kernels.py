@@ -654,3 +654,23 @@ def test_wn_cell_masks_do_not_change_the_likelihood(eng, golden):
             eng.loglik(lp, x, logw)
             out.append(host(logw))
         assert np.array_equal(out[0], out[1])
+
+
+def test_systematic_with_degenerate_weights(eng):
+    """one or two particles hold almost all the weight: their runs of offspring (> 8192) go through the job list and
+    are copied by the whole grid; indices and particles equal the oracle's comb"""
+    rng = np.random.default_rng(21)
+    n, n_out = 200_000, 1_500_001
+    w = rng.random(n) * 1e-4
+    w[1234] = 30.0
+    w[150_000] = 12.0
+    x = dev(rng.normal(size=(n, 3)))
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, w=dev(w), exact=True)
+    ref = O.systematic_indices(w, 0.3141, n_out)
+    for _ in range(2):  # twice: the job counter cleans itself
+        idx = torch.empty(n_out, dtype=torch.int64, device="cuda:0")
+        out = torch.empty((n_out, 3), dtype=torch.float64, device="cuda:0")
+        eng.resample(cdf, dev(np.array([0.3141])), x, out, n_out, 3, systematic=True, idx_out=idx)
+        assert np.array_equal(host(idx), ref)
+        assert np.array_equal(host(out), host(x)[ref])
