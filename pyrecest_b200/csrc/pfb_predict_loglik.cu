@@ -445,7 +445,6 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
 // per CTA step, thread t takes particles t, t+256, ... of the tile: coalesced) and leave, per tile,
 // (max log-weight, sum exp(logw - max)) in the workspace: pfb_scan_cdf turns those into the approximate
 // prefix its sequential-exact scan needs, without another pass over the log-weights.
-constexpr int kTileItems = kScanTile / kThreads;
 
 // runs of a batched launch: n_runs independent filters of run_len particles each; their log-weights
 // live at logw[run * run_pad + k] (run_pad = tpr * kScanTile, padded with -inf, so that no scan tile
