@@ -223,3 +223,10 @@ def test_wn_cell_masks_cover_the_full_screen(d):
     have = ((masks[cell][:, None] >> np.arange(K, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
     assert np.all(have[need])
     assert have.sum(axis=1).mean() < K  # and it prunes
+
+
+def test_graft_entry_build_runs():
+    """the driver's build check: compiles (make is a no-op when up to date), loads and imports"""
+    import __graft_entry__ as g
+
+    g.build()
