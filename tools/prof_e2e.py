@@ -7,6 +7,8 @@ prior, trans, noise, lik = bench.make_dists("t3", P)
 n = 10**8
 pf = Fl.HypertoroidalParticleFilter(n, 3)
 pf.filter_state = prior
+import os
+if os.environ.get('LAZY') == '0': pf.lazy_predict = False
 z = P["z"]
 def step():
     pf.predict_nonlinear(trans, noise)
