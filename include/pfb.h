@@ -143,7 +143,9 @@ typedef enum { PFB_MOM_MEAN = 0, PFB_MOM_TRIG = 1, PFB_MOM_SCATTER = 2, PFB_MOM_
 int pfb_abi_version(void);
 const char* pfb_last_error(void);
 
-/* scratch needed by any entry point for up to n particles (flags, tile states, partials).
+/* scratch needed by any entry point for up to n particles: counters, reduction partials, the job list of heavy
+ * particles (systematic resampling), scan tile states, and the lookup structure of multinomial resampling (one
+ * 64-byte bucket record per ~16 particles: ~4 bytes per particle).  The library never allocates.
  * The first pfb_workspace_bytes(0) bytes must be zeroed once (pfb_workspace_init). */
 int64_t pfb_workspace_bytes(int64_t n);
 int64_t pfb_workspace_bytes_batched(int64_t n_runs, int64_t run_len);  /* for the *_batched entry points */
@@ -230,8 +232,13 @@ int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, con
  * shards).  Produces the `count` systematic offspring j = j_begin .. j_begin + count - 1 of the global
  * comb u_j = (j + u0) / n_total_out:  x_out[k] = x_in[#{i : fl(C_i / total) <= u_j}]  (index local to the
  * shard, clamped to n - 1); est_kind / est_out as in pfb_resample (mean over these `count` offspring).
- * The caller picks [j_begin, j_begin + count) as the offspring that fall into
- * this shard (pyrecest_b200/sharded.py) and exchanges the result with an all-to-all. */
+ * The caller picks [j_begin, j_begin + count) as the offspring that fall into this shard
+ * (pyrecest_b200/sharded.py).  x_out may be PEER memory (a pointer into another GPU's buffer, mapped through CUDA
+ * IPC / torch symmetric memory): the kernel then stores the offspring that belong to that rank straight into its
+ * output slots over NVLink -- compute and exchange in one kernel; otherwise the pieces are exchanged with an
+ * all-to-all.  Only the sources of the piece are visited (bisection on the monotone offspring count).
+ * ws may be NULL when est_kind == PFB_EST_NONE (runs of > 8192 offspring of one particle are then written by one
+ * warp instead of the whole grid). */
 int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, double cdf_offset,
                          double total, double u0, int64_t j_begin, int64_t count, int64_t n_total_out,
                          const void* x_in, void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out,
