@@ -227,13 +227,15 @@ class AbstractParticleFilter:
         if self._pending is not None and st._uniform:
             p, noise = self._pending
             self._pending = None
-            try:
-                if p.rng_kind == L.RNG_VONMISES:
-                    # measured (T^3, 1e8): the von Mises sampler inside the fused kernel costs occupancy and
-                    # instruction-cache misses -- 5.7 ms fused against 1.9 (predict) + 2.8 (weight) as two kernels
-                    raise NotImplementedError
-                eng.predict_loglik(p, lp, x, x, noise, self._logw)  # fused K(1)+K(2), in place
-            except NotImplementedError:  # (mode, likelihood) pair without a fused instantiation
+            # measured (T^3, 1e8): the von Mises sampler inside the fused kernel costs occupancy and
+            # instruction-cache misses -- 5.7 ms fused against 1.9 (predict) + 2.8 (weight) as two kernels
+            fuse = p.rng_kind != L.RNG_VONMISES
+            if fuse:
+                try:
+                    eng.predict_loglik(p, lp, x, x, noise, self._logw)  # fused K(1)+K(2), in place
+                except NotImplementedError:  # (mode, likelihood) pair without a fused instantiation
+                    fuse = False
+            if not fuse:
                 eng.predict(p, x, x, noise)
                 eng.loglik(lp, x, self._logw)
         else:
