@@ -507,6 +507,7 @@ def run_mc(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     gpu_launches = eng.launches - l0
     ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+    barrier()  # rank 0 has just spent ~0.2 s collecting the clock samples: start the e2e clocks together
     t0 = time.perf_counter()
     for _ in range(max(1, args.e2e_steps)):
         est_host = step().cpu()
