@@ -674,3 +674,33 @@ def test_systematic_with_degenerate_weights(eng):
         eng.resample(cdf, dev(np.array([0.3141])), x, out, n_out, 3, systematic=True, idx_out=idx)
         assert np.array_equal(host(idx), ref)
         assert np.array_equal(host(out), host(x)[ref])
+
+
+def test_resample_small_and_odd_sizes(eng, lookup_path):
+    """n from 1 to a few thousand, n_out unrelated to n, zero weights at both ends: every size takes the same
+    kernels as 1e8 particles (one bucket, partial tiles, look-ahead past the end of the data)"""
+    rng = np.random.default_rng(99)
+    for n in list(range(1, 40)) + [63, 64, 65, 255, 256, 257, 2047, 2048, 2049, 2080, 4095, 4097, 6143]:
+        w = rng.random(n) ** 3
+        if n > 4:
+            w[0] = 0.0
+            w[-1] = 0.0
+            w[n // 2] = 0.0
+        if w.sum() == 0:
+            w[0] = 1.0
+        n_out = int(rng.integers(1, 3 * n + 50))
+        u = rng.random(n_out)
+        c = np.cumsum(w)
+        ref = np.minimum(np.searchsorted(c / c[-1], u, side="right"), n - 1)
+        cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+        eng.scan(cdf, w=dev(w), exact=True)
+        assert np.array_equal(host(cdf), c), n
+        x = dev(rng.normal(size=(n, 2)))
+        out = torch.empty((n_out, 2), dtype=torch.float64, device="cuda:0")
+        idx = torch.empty(n_out, dtype=torch.int64, device="cuda:0")
+        eng.resample(cdf, dev(u), x, out, n_out, 2, idx_out=idx)
+        assert np.array_equal(host(idx), ref), n
+        assert np.array_equal(host(out), host(x)[ref]), n
+        u0 = float(rng.random())
+        eng.resample(cdf, dev(np.array([u0])), x, out, n_out, 2, systematic=True, idx_out=idx)
+        assert np.array_equal(host(idx), O.systematic_indices(w, u0, n_out)), n
