@@ -123,17 +123,40 @@ def as_distribution(likelihood):
     )
 
 
+_FACTOR_CACHE: dict = {}
+
+
+def _memo(tag, C, make):
+    """a filter passes the same covariance every step: the svd / eigh of a d x d matrix (tens of microseconds of
+    LAPACK wrapper each) would otherwise sit on the critical path of small filters.  Values are treated as read-only."""
+    key = (tag, C.shape, C.tobytes())
+    hit = _FACTOR_CACHE.get(key)
+    if hit is None:
+        if len(_FACTOR_CACHE) > 512:
+            _FACTOR_CACHE.clear()
+        hit = _FACTOR_CACHE[key] = make(C)
+    return hit
+
+
 def gaussian_noise_factor(C):
     """numpy legacy multivariate_normal factor: draws are z @ A + mean with
     (u, s, v) = svd(C); A = sqrt(s)[:, None] * v  (gaussian_distribution.py:122-123)."""
-    C = np.atleast_2d(_np(C))
-    (_, s, v) = np.linalg.svd(C)
-    return np.sqrt(s)[:, None] * v
+    C = np.ascontiguousarray(np.atleast_2d(_np(C)), dtype=np.float64)
+
+    def make(C):
+        (_, s, v) = np.linalg.svd(C)
+        return np.sqrt(s)[:, None] * v
+
+    return _memo("svd", C, make)
 
 
 def gaussian_whitening(C):
     """(W, log|C|) the way scipy.stats.multivariate_normal factorises (eigh; W = V / sqrt(lambda))."""
-    C = np.atleast_2d(_np(C))
+    C = np.ascontiguousarray(np.atleast_2d(_np(C)), dtype=np.float64)
+    return _memo("eigh", C, _gaussian_whitening)
+
+
+def _gaussian_whitening(C):
     try:
         import scipy.linalg
 
