@@ -98,6 +98,38 @@ void sweep(const unsigned char* buf, uint64_t bytes, uint64_t n, uint64_t* out, 
          blocks_per_sm, ms, n / ms * 1e-6);
 }
 
+// random WRITES: one aligned 32-byte store (a full sector), or three 8-byte stores at a random 8-byte offset (a 24-byte
+// particle record: partial sectors, read-modify-write in L2 / DRAM)
+template <int MODE>
+__global__ void probe_write(unsigned char* buf, uint64_t units, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t s = mix(i * 0x9e3779b97f4a7c15ull + 77 + MODE) % units;
+    if (MODE == 0) {
+      uint64_t* p = reinterpret_cast<uint64_t*>(buf + s * 32);
+      asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(i), "l"(i + 1), "l"(i + 2), "l"(i + 3) : "memory");
+    } else {
+      uint64_t* p = reinterpret_cast<uint64_t*>(buf + s * 24);
+      p[0] = i; p[1] = i + 1; p[2] = i + 2;
+    }
+  }
+}
+
+template <int MODE>
+void run_write(const char* name, unsigned char* buf, uint64_t bytes, uint64_t n) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const uint64_t units = MODE == 0 ? bytes / 32 : bytes / 24 - 1;
+  probe_write<MODE><<<148 * 8, 256>>>(buf, units, n);
+  cudaEventRecord(e0);
+  probe_write<MODE><<<148 * 8, 256>>>(buf, units, n);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("%-40s footprint %6llu MiB : %8.3f ms  %6.1f G writes/s\n", name, (unsigned long long)(bytes >> 20), ms, n / ms * 1e-6);
+}
+
 int main(int argc, char** argv) {
   if (argc > 1) {
     cudaError_t r = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1]));
@@ -130,5 +162,9 @@ int main(int argc, char** argv) {
   }
   sweep<1>(buf, big, n, out, 8);
   sweep<4>(buf, big, n, out, 8);
+  for (uint64_t fp = 64ull << 20; fp <= (16ull << 30); fp *= 16) {
+    run_write<0>("random 32-byte sector stores", buf, fp, n);
+    run_write<1>("random 24-byte records (3 x 8-byte stores)", buf, fp, n);
+  }
   return 0;
 }
