@@ -53,13 +53,16 @@ def algorithmic_bytes(D, E):
     return {"predict_loglik": 8 * (2 * D + E + 1), "scan": 16, "resample": 8 * (2 * D + 2)}
 
 
-def random_access_roofline(kernel, resampling, n, D, ms):
+def random_access_roofline(kernel, resampling, n, D, ms, padded=False):
     """Multinomial resampling is bound by DRAM random accesses, not bytes: B200 serves ~3.7e10 random reads/s from
     footprints >= 1 GiB whatever their size up to 128 B (tools/micro/sector_fetch.cu, profiles/r01g_sector_fetch_micro.log).
-    Per particle: one 64-byte bucket record + the particle record (1 + (8 D - 8)/64 64-byte fetches)."""
+    Per particle: one 64-byte bucket record + the particle record (1 + (8 D - 8)/64 64-byte fetches; exactly 1
+    when the gather reads the padded copy the predict kernel left behind)."""
     if kernel != "resample" or resampling != "multinomial":
         return None
-    per_particle = 1.0 + 1.0 + (8 * D - 8) / 64.0
+    R_ = 8 * D  # bytes per record; it straddles a 64-byte fetch when (i R mod 64) + R > 64
+    straddle = 0.0 if padded else sum(((i * R_) % 64) + R_ > 64 for i in range(64)) / 64.0
+    per_particle = 2.0 + straddle  # (the padded gather copy never straddles)
     peak = 3.7e10
     achieved = per_particle * n / (ms * 1e-3)
     return {"reads_per_particle": per_particle, "achieved_reads_per_s": achieved, "peak_reads_per_s": peak,
@@ -324,6 +327,9 @@ def run_gpu(args):
     est = torch.empty(2 * L.PFB_MAXD, dtype=torch.float64, device=dev)
     est_kind = L.EST_TRIG if manifold == "torus" else L.EST_SUM
     exact = not args.fast_scan
+    # the filters' padded gather copy (pfb_predict_params.x_pad_out), as the public API uses it
+    gather = pf._padded_gather_target(pp, x)
+    xg_stride = gather[1] if gather is not None else 0
 
     def step(i, ev=None):
         nonlocal x, alt
@@ -337,7 +343,8 @@ def run_gpu(args):
         eng.scan(cdf, logw=logw, exact=exact)
         if ev:
             ev[2].record()
-        eng.resample(cdf, ub, x, alt, n, D, systematic=args.resampling == "systematic", est_kind=est_kind, est_out=est)
+        eng.resample(cdf, ub, gather[0] if gather is not None else x, alt, n, D, systematic=args.resampling == "systematic",
+                     est_kind=est_kind, est_out=est, x_in_stride=xg_stride)
         if ev:
             ev[3].record()
         x, alt = alt, x
@@ -430,7 +437,7 @@ def run_gpu(args):
                          "kernel_ms": {nm: float(t) for nm, t in zip(names, kt)},
                          "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak,
                          "bytes_per_particle": ab,
-                         "random_access": random_access_roofline(names[k], args.resampling, n, D, kt[k])},
+                         "random_access": random_access_roofline(names[k], args.resampling, n, D, kt[k], padded=gather is not None)},
             "cpu_baseline": None if args.no_cpu else {
                 "value": cpu_val, "unit": "particle-steps/s", "cores": cpu_threads(), "kind": "port",
                 "sample": f"oracle/pf_oracle.py (vectorised numpy restatement, predict + likelihood split over {cpu_threads()} host threads) "

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 3
+#define PFB_ABI_VERSION 4
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -79,6 +79,12 @@ typedef struct {
   double rng_vm_area[PFB_MAXD];  /* PFB_RNG_VONMISES: hat area A of the dimension's strip table (pfb_vm_strip_table) */
   const double* rng_vm_table_dev; /* device pointer: strip tables, PFB_VM_STRIPS x (start, width) doubles each */
   int32_t rng_vm_table_idx[PFB_MAXD]; /* which table of rng_vm_table_dev each dimension uses (equal kappas share) */
+  /* optional second output of the predict kernels: the predicted particles once more as records of x_pad_stride
+   * components (zero padded) so that a record never straddles a 64-byte fetch -- the source of the random gather
+   * of pfb_resample*_strided (a 24-byte T^3 record straddles 25 % of the time, a 32-byte one never) */
+  void* x_pad_out;
+  int32_t x_pad_stride;      /* components per padded record: 4 for D = 3, 8 for D = 5, 6; 0 = no padded copy */
+  int32_t reserved2;
 } pfb_predict_params;
 
 /* von Mises draws use vertical-strip rejection: [0, pi] is cut into PFB_VM_STRIPS strips under a piecewise-
@@ -227,6 +233,16 @@ int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, con
                      uint64_t rng_seed, uint64_t rng_offset, int32_t systematic, const void* x_in,
                      void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
                      int64_t ws_bytes, void* stream);
+/* pfb_resample / pfb_resample_rng with the gather source given as records of x_in_stride components (the padded
+ * copy a predict kernel left behind through pfb_predict_params.x_pad_out; x_in_stride = dim is the plain call).
+ * Multinomial only. */
+int pfb_resample_strided(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                         const double* u, const void* x_in, int32_t x_in_stride, void* x_out, int64_t* idx_out,
+                         int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream);
+int pfb_resample_rng_strided(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                             uint64_t rng_seed, uint64_t rng_offset, const void* x_in, int32_t x_in_stride,
+                             void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
+                             int64_t ws_bytes, void* stream);
 /* Sharded filter (one filter split over several GPUs): this rank owns particles
  * [start, start + n) of a global CDF C_i = fl(cdf_offset + c_i), normalised by `total` (the sum over all
  * shards).  Produces the `count` systematic offspring j = j_begin .. j_begin + count - 1 of the global

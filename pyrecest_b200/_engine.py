@@ -105,20 +105,31 @@ class Engine:
         self.launches += (4 if exact else 2) + 1  # tile_combine | tile_stats, tile_prefix, maps + chain + final | final
 
     def resample(self, cdf, u, x_in, x_out, n_out, dim, systematic=False, idx_out=None, est_kind=L.EST_NONE,
-                 est_out=None):
+                 est_out=None, x_in_stride=0):
         n = cdf.shape[0]
         ws, wsb = self._ensure_ws(n)
         dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        if x_in_stride and x_in_stride != dim:  # padded gather source (pfb_predict_params.x_pad_out)
+            L.check(self.lib.pfb_resample_strided(dt, dim, n, n_out, _ptr(cdf), _ptr(u), _ptr(x_in), x_in_stride, _ptr(x_out),
+                                                  _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb, _stream(self.device)))
+            self.launches += 3
+            return
         L.check(self.lib.pfb_resample(dt, dim, n, n_out, _ptr(cdf), _ptr(u), 1 if systematic else 0, _ptr(x_in),
                                       _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
                                       _stream(self.device)))
         self.launches += 1 if systematic else 3  # scatter | guide + bucket records + resample
 
     def resample_rng(self, cdf, seed, offset, x_in, x_out, n_out, dim, systematic=False, idx_out=None,
-                     est_kind=L.EST_NONE, est_out=None):
+                     est_kind=L.EST_NONE, est_out=None, x_in_stride=0):
         n = cdf.shape[0]
         ws, wsb = self._ensure_ws(n)
         dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        if x_in_stride and x_in_stride != dim:
+            L.check(self.lib.pfb_resample_rng_strided(dt, dim, n, n_out, _ptr(cdf), seed, offset, _ptr(x_in), x_in_stride,
+                                                      _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
+                                                      _stream(self.device)))
+            self.launches += 3
+            return
         L.check(self.lib.pfb_resample_rng(dt, dim, n, n_out, _ptr(cdf), seed, offset, 1 if systematic else 0,
                                           _ptr(x_in), _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
                                           _stream(self.device)))

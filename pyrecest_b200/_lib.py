@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 3
+ABI_VERSION = 4
 VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
@@ -41,6 +41,7 @@ class PredictParams(C.Structure):
         ("rng_kind", C.c_int32), ("reserved", C.c_int32), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
         ("rng_kappa", C.c_double * PFB_MAXD), ("rng_vm_area", C.c_double * PFB_MAXD),
         ("rng_vm_table_dev", C.c_void_p), ("rng_vm_table_idx", C.c_int32 * PFB_MAXD),
+        ("x_pad_out", C.c_void_p), ("x_pad_stride", C.c_int32), ("reserved2", C.c_int32),
     ]
 
     def set_von_mises_rng(self, kappas, device="cuda:0"):
@@ -91,6 +92,9 @@ SIGNATURES = {
     "pfb_resample": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "pfb_resample_rng": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, C.c_uint64, C.c_uint64, _i32, _vp, _vp, _vp, _i32, _vp,
                                    _vp, _i64, _vp]),
+    "pfb_resample_strided": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "pfb_resample_rng_strided": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, C.c_uint64, C.c_uint64, _vp, _i32, _vp, _vp, _i32,
+                                           _vp, _vp, _i64, _vp]),
     "pfb_resample_sharded": (C.c_int, [C.c_int, _i32, _i64, _vp, C.c_double, C.c_double, C.c_double, _i64, _i64, _i64,
                                        _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),

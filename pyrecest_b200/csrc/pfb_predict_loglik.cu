@@ -371,6 +371,17 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
+// second, padded copy of a predicted particle (pfb_predict_params.x_pad_out): whole sectors, vector stores
+template <typename T, int D>
+__device__ __forceinline__ void store_padded(const pfb_predict_params& p, int64_t i, const double (&out)[D]) {
+  constexpr int DP = (D <= 4) ? 4 : 8;
+  if (p.x_pad_out == nullptr || p.x_pad_stride != DP) return;
+  double q[DP];
+#pragma unroll
+  for (int c = 0; c < DP; ++c) q[c] = (c < D) ? out[c] : 0.0;
+  store_rec<T, DP>(static_cast<T*>(p.x_pad_out), i, q);
+}
+
 template <typename T, int D, int MODE, bool RNG>
 __global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p, int64_t n,
                                                            const T* __restrict__ x_in, T* x_out,
@@ -380,6 +391,7 @@ __global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p,
     double out[D];
     predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
+    store_padded<T, D>(p, i, out);
   }
 }
 
@@ -533,6 +545,7 @@ __global__ void __launch_bounds__(kThreads, RNG ? 4 : 0) predict_loglik_kernel(p
     double out[D];
     predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
+    store_padded<T, D>(p, i, out);
     if constexpr (sizeof(T) == 4) {
       // weight what was stored (the fp32 particle), as a separate pfb_loglik call would
 #pragma unroll
@@ -561,6 +574,10 @@ static int check_predict(const pfb_predict_params* p) {
   if (p->mode == PFB_PRED_SPHERE_VMF && p->dim != 3) { set_error("VMF noise needs dim 3 (S^2), got %d", p->dim); return PFB_ERR_UNSUPPORTED; }
   if (p->noise_cols != 0 && p->noise_cols != p->dim) { set_error("noise_cols %d must equal dim %d", p->noise_cols, p->dim); return PFB_ERR_INVALID; }
   if (p->mode == PFB_PRED_SPHERE_VMF && p->noise_cols && !(p->kappa > 0.0)) { set_error("kappa must be > 0"); return PFB_ERR_INVALID; }
+  if (p->x_pad_out != nullptr && p->x_pad_stride != (p->dim <= 4 ? 4 : 8)) {
+    set_error("x_pad_stride %d: the padded copy has 4 components per record for dim <= 4, else 8", p->x_pad_stride);
+    return PFB_ERR_INVALID;
+  }
   if (p->rng_kind < PFB_RNG_NONE || p->rng_kind > PFB_RNG_VMF) { set_error("bad rng_kind %d", p->rng_kind); return PFB_ERR_INVALID; }
   if (p->rng_kind != PFB_RNG_NONE && (p->rng_kind == PFB_RNG_VMF) != (p->mode == PFB_PRED_SPHERE_VMF)) {
     set_error("rng_kind %d does not go with predict mode %d (VMF triples <-> PFB_PRED_SPHERE_VMF)", p->rng_kind, p->mode);

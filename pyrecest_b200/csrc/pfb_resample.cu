@@ -476,11 +476,11 @@ __device__ __forceinline__ void ld_sector(const void* p, uint64_t (&w)[4]) {
 // record cost ~150 bytes of DRAM reads.  Here every covering sector is loaded exactly once (sector-aligned,
 // so the reads stay inside the 256-byte allocation granule) and the components are selected from registers.
 template <typename T, int D>
-__device__ __forceinline__ void gather_rec(const T* __restrict__ x, int64_t i, double (&r)[D]) {
+__device__ __forceinline__ void gather_rec(const T* __restrict__ x, int64_t i, double (&r)[D], int64_t stride = D) {
   constexpr int R = D * (int)sizeof(T);
   constexpr int WPS = 32 / (int)sizeof(T);                  // components per sector
   constexpr int NS = (R - (int)sizeof(T)) / 32 + 2;         // sectors a record can touch
-  const uintptr_t a = reinterpret_cast<uintptr_t>(x + i * D);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(x + i * stride);
   const int off = (int)(a & 31) / (int)sizeof(T);
   const unsigned char* base = reinterpret_cast<const unsigned char*>(a & ~(uintptr_t)31);
   uint64_t raw[NS][4];
@@ -512,12 +512,12 @@ template <typename T, int D, int EST, int NE>
 __device__ __forceinline__ void gather_store(const T* __restrict__ x_in, T* __restrict__ x_out,
                                              int64_t* __restrict__ idx_out, const int64_t (&src)[kBatch],
                                              const int64_t (&dst)[kBatch], const int64_t (&idx)[kBatch],
-                                             const bool (&live)[kBatch], double (&acc)[NE]) {
+                                             const bool (&live)[kBatch], double (&acc)[NE], int64_t x_in_stride = D) {
   if (x_in != nullptr) {
     double r[kBatch][D];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q)
-      if (live[q]) gather_rec<T, D>(x_in, src[q], r[q]);
+      if (live[q]) gather_rec<T, D>(x_in, src[q], r[q], x_in_stride);
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       if (!live[q]) continue;
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
                                                                 int64_t* __restrict__ idx_out, double* est_out,
                                                                 Workspace ws, const uint4* __restrict__ recs,
                                                                 int64_t M, RngKey key, int64_t n_runs, int64_t run_pad,
-                                                                int64_t n_out_run) {
+                                                                int64_t n_out_run, int64_t x_in_stride) {
   // runs: output j belongs to run j / n_out_run, drawn from cdf[run run_pad, +n) / x_in[run n, ..) through the
   // records at recs + run (M + 2); a plain call is one run (run_pad = n, n_out_run = n_out)
   constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
     int64_t src[kBatch];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) src[q] = run[q] * n + idx[q];
-    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, src, dst, idx, live, acc);
+    gather_store<T, D, EST, NE>(x_in, x_out, idx_out, src, dst, idx, live, acc, x_in_stride);
   }
   if constexpr (EST != PFB_EST_NONE) finish_estimate<NE>(acc, red, ws, est_out, n_out);
 }
@@ -1138,18 +1138,19 @@ template <typename T, int D>
 static int launch_resample_rec(int64_t n, int64_t n_out, const double* cdf, const double* u, const void* x_in,
                                void* x_out, int64_t* idx_out, int est_kind, double* est_out, Workspace W,
                                cudaStream_t st, const uint4* recs, int64_t M, RngKey key, int64_t n_runs = 1,
-                               int64_t run_pad = 0, int64_t n_out_run = 0) {
+                               int64_t run_pad = 0, int64_t n_out_run = 0, int64_t x_in_stride = 0) {
   if (n_runs <= 1) { n_runs = 1; run_pad = n; n_out_run = n_out; }
+  if (x_in_stride <= 0) x_in_stride = D;
   const int grid = stream_grid(n_out);
   switch (est_kind) {
     case PFB_EST_NONE:
-      resample_rec_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
+      resample_rec_kernel<T, D, PFB_EST_NONE><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run, x_in_stride);
       break;
     case PFB_EST_SUM:
-      resample_rec_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
+      resample_rec_kernel<T, D, PFB_EST_SUM><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run, x_in_stride);
       break;
     case PFB_EST_TRIG:
-      resample_rec_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run);
+      resample_rec_kernel<T, D, PFB_EST_TRIG><<<grid, kThreads, 0, st>>>(n, n_out, cdf, u, (const T*)x_in, (T*)x_out, idx_out, est_out, W, recs, M, key, n_runs, run_pad, n_out_run, x_in_stride);
       break;
     default:
       set_error("bad est_kind %d", est_kind);
@@ -1217,7 +1218,12 @@ extern "C" int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream) {
 namespace pfb {
 static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf, const double* u,
                          RngKey key, int32_t systematic, const void* x_in, void* x_out, int64_t* idx_out,
-                         int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream) {
+                         int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream,
+                         int32_t x_in_stride = 0) {
+  if (x_in_stride != 0 && x_in_stride != dim) {
+    if (x_in_stride < dim || systematic) { set_error("x_in_stride %d: must be >= dim, multinomial resampling only", x_in_stride); return PFB_ERR_INVALID; }
+    if (!bucket_records_enabled()) { set_error("strided gather sources need the bucket-record path"); return PFB_ERR_UNSUPPORTED; }
+  }
   if (n <= 0 || n_out <= 0) return PFB_OK;
   if (!cdf) { set_error("NULL cdf"); return PFB_ERR_INVALID; }
   if ((x_in == nullptr) != (x_out == nullptr)) { set_error("x_in and x_out must both be given or both NULL"); return PFB_ERR_INVALID; }
@@ -1251,7 +1257,7 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
       record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, W.guide, W.counters + 4, W.counters + 5);
       PFB_LAUNCH_OK("record_fill_kernel");
     }
-    PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(n, n_out, cdf, u, x_in, x_out, idx_out, est_kind, est_out, W, st, recs, Mr, key))));
+    PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(n, n_out, cdf, u, x_in, x_out, idx_out, est_kind, est_out, W, st, recs, Mr, key, 1, 0, 0, x_in_stride))));
     if (rc) return rc;
     PFB_LAUNCH_OK("resample_rec_kernel");
     return PFB_OK;
@@ -1290,6 +1296,23 @@ extern "C" int pfb_resample_rng(pfb_dtype dtype, int32_t dim, int64_t n, int64_t
                                 int64_t ws_bytes, void* stream) {
   return resample_impl(dtype, dim, n, n_out, cdf, nullptr, RngKey{rng_seed, rng_offset}, systematic, x_in, x_out,
                        idx_out, est_kind, est_out, ws, ws_bytes, stream);
+}
+
+extern "C" int pfb_resample_strided(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                                    const double* u, const void* x_in, int32_t x_in_stride, void* x_out,
+                                    int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes,
+                                    void* stream) {
+  if (n > 0 && n_out > 0 && !u) { set_error("NULL uniforms (use pfb_resample_rng_strided for in-kernel draws)"); return PFB_ERR_INVALID; }
+  return resample_impl(dtype, dim, n, n_out, cdf, u, RngKey{0, 0}, 0, x_in, x_out, idx_out, est_kind, est_out, ws,
+                       ws_bytes, stream, x_in_stride);
+}
+
+extern "C" int pfb_resample_rng_strided(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                                        uint64_t rng_seed, uint64_t rng_offset, const void* x_in, int32_t x_in_stride,
+                                        void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
+                                        int64_t ws_bytes, void* stream) {
+  return resample_impl(dtype, dim, n, n_out, cdf, nullptr, RngKey{rng_seed, rng_offset}, 0, x_in, x_out, idx_out,
+                       est_kind, est_out, ws, ws_bytes, stream, x_in_stride);
 }
 
 extern "C" int64_t pfb_workspace_bytes_batched(int64_t n_runs, int64_t run_len) {

@@ -389,3 +389,32 @@ def test_hypercylindrical_dirac_against_reference_run(golden, tag, bd):
     assert np.array_equal(host(smp), g[f"{tag}_sample"])
     with pytest.raises(ValueError):
         HypercylindricalDiracDistribution(0, d, w)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("D", [3, 5, 6])
+def test_padded_gather_copy_gives_identical_particles(D, dtype):
+    """the gather of the multinomial resampling may read the padded copy the predict kernel left behind
+    (pfb_predict_params.x_pad_out): same particles, same estimate, bit for bit"""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200.filters import EuclideanParticleFilter, LinearTransition
+
+    rng = np.random.default_rng(D)
+    A = rng.normal(size=(D, D))
+    Q = A @ A.T / D + 0.1 * np.eye(D)
+    F = np.eye(D) + 0.05 * rng.normal(size=(D, D))
+    outs = []
+    for padded in (True, False):
+        prandom.seed(2024)
+        pf = EuclideanParticleFilter(60_000, D, dtype=dtype)
+        pf.padded_gather, pf.padded_gather_min = padded, 0
+        pf.filter_state = GaussianDistribution(np.zeros(D), np.eye(D))
+        for t in range(3):
+            pf.predict_nonlinear(LinearTransition(F), GaussianDistribution(np.zeros(D), 0.2 * Q))
+            pf.update_identity(GaussianDistribution(np.zeros(D), Q), 0.3 * np.ones(D))
+            est = pf.get_point_estimate()
+        assert (pf._pad is not None) == padded
+        outs.append((pf.filter_state.d.cpu().numpy().copy(), est.cpu().numpy().copy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])

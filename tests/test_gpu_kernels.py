@@ -59,7 +59,7 @@ def pparams(mode, dim, noise_cols=None, F=None, b=None, A=None, mu=None, kappa=0
 def test_abi_version():
     from pyrecest_b200 import _lib as L
 
-    assert L.lib().pfb_abi_version() == 3
+    assert L.lib().pfb_abi_version() == L.ABI_VERSION
 
 
 def test_wrap_bitexact(eng, golden):
