@@ -337,7 +337,8 @@ def run_gpu(args):
         ub = u_ring[i % nbuf]
         if ev:
             ev[0].record()
-        eng.predict_loglik(pp, lp, x, x, nb, logw)
+        # (with the padded gather copy the compact predicted particles are dead: not stored, as in filters.py)
+        eng.predict_loglik(pp, lp, x, None if gather is not None else x, nb, logw)
         if ev:
             ev[1].record()
         eng.scan(cdf, logw=logw, exact=exact)

@@ -171,7 +171,8 @@ int pfb_loglik(const pfb_lik_params* lik, pfb_dtype dtype, int64_t n, const void
                const double* w_prev, double* logw, double* stats, void* ws, int64_t ws_bytes,
                void* stream);
 
-/* K(1)+K(2) fused: predict, write x_out, weight the predicted particle. */
+/* K(1)+K(2) fused: predict, write x_out, weight the predicted particle.  x_out may be NULL when p->x_pad_out is
+ * given: a caller that resamples next reads only the padded copy, so the compact predicted particles are dead. */
 int pfb_predict_loglik(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype,
                        int64_t n, const void* x_in, void* x_out, const void* noise,
                        double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream);

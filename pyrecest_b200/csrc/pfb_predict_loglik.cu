@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, RNG ? 4 : 0) predict_loglik_kernel(p
   weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double out[D];
     predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
-    store_rec<T, D>(x_out, i, out);
+    if (x_out != nullptr) store_rec<T, D>(x_out, i, out);  // (NULL: only the padded copy is wanted, see pfb.h)
     store_padded<T, D>(p, i, out);
     if constexpr (sizeof(T) == 4) {
       // weight what was stored (the fp32 particle), as a separate pfb_loglik call would
@@ -804,7 +804,7 @@ static int predict_loglik_impl(const pfb_predict_params* p, const pfb_lik_params
   rc = check_lik(lik, p->dim);
   if (rc) return rc;
   if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
-  if (!x_in || !x_out || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  if (!x_in || !logw || !stats || (!x_out && !p->x_pad_out)) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   Workspace W;
   rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;

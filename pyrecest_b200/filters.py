@@ -239,7 +239,11 @@ class AbstractParticleFilter:
             fuse = p.rng_kind != L.RNG_VONMISES
             if fuse:
                 try:
-                    eng.predict_loglik(p, lp, x, x, noise, self._logw)  # fused K(1)+K(2), in place
+                    # with a padded gather copy the compact predicted particles are dead (the resampling reads the
+                    # copy and replaces the particle set): not stored, unless a failed weight check has to leave them
+                    dead = gather is not None
+                    eng.predict_loglik(p, lp, x, None if dead else x, noise, self._logw)  # fused K(1)+K(2), in place
+                    self._predicted_only_in_pad = dead
                 except NotImplementedError:  # (mode, likelihood) pair without a fused instantiation
                     fuse = False
             if not fuse:
@@ -275,8 +279,12 @@ class AbstractParticleFilter:
             stats = eng.stats.cpu()
             flags = int(stats[L.STAT_FLAGS])
             self.last_log_max = float(stats[L.STAT_MAX])
+            if flags & 3 and getattr(self, "_predicted_only_in_pad", False) and gather is not None:
+                x.copy_(gather[0][:, :D])  # the update fails: leave the predicted particles behind, like the reference
+            self._predicted_only_in_pad = False
             assert not flags & 1, "All weights should be greater than or equal to 0."
             assert not flags & 2, "The sum of all weights should be greater than 0."
+        self._predicted_only_in_pad = False
         eng.scan(self._cdf, logw=self._logw, exact=self.scan_exact)
         systematic = self.resampling == "systematic"
         if not systematic and self.resampling != "multinomial":
