@@ -418,3 +418,24 @@ def test_padded_gather_copy_gives_identical_particles(D, dtype):
         outs.append((pf.filter_state.d.cpu().numpy().copy(), est.cpu().numpy().copy()))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_failed_update_leaves_predicted_particles_with_padded_gather():
+    """when the weight check fails (here: a NaN measurement) the reference has already applied the predict; with the
+    padded gather copy the compact predicted particles are not stored by the fused kernel, so they are restored"""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200.filters import EuclideanParticleFilter, IdentityTransition
+
+    states = []
+    for padded in (True, False):
+        prandom.seed(5)
+        pf = EuclideanParticleFilter(50_000, 3)
+        pf.padded_gather, pf.padded_gather_min = padded, 0
+        pf.filter_state = GaussianDistribution(np.zeros(3), np.eye(3))
+        pf.predict_nonlinear(IdentityTransition(), GaussianDistribution(np.zeros(3), 0.1 * np.eye(3)))
+        with pytest.raises(AssertionError):
+            pf.update_identity(GaussianDistribution(np.zeros(3), np.eye(3)), np.array([np.nan, 0.0, 0.0]))
+        states.append(pf.filter_state.d.cpu().numpy().copy())
+    assert np.isfinite(states[0]).all()
+    assert np.array_equal(states[0], states[1])
