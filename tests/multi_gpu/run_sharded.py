@@ -33,6 +33,10 @@ def main():
     N = n_loc * world
     rng = np.random.default_rng(5)
     x0 = rng.standard_normal((N, D))
+    if os.environ.get("SKEW", "1") == "1":
+        # very unequal shards: the particles of shard g sit g standard deviations away from the measurements, so almost
+        # all offspring come from shard 0 and large pieces cross to every other rank
+        x0[:, 0] += 1.5 * (np.arange(N) // n_loc)
     Z = rng.standard_normal((T, N, D))
     u0s = rng.random(T)
     zs = rng.standard_normal((T, D)) * 0.3
