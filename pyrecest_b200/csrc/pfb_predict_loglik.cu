@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
 }
 
 template <typename T, int D, int MODE, int KIND, bool RNG>
-__global__ void __launch_bounds__(kThreads, RNG ? 4 : 0) predict_loglik_kernel(pfb_predict_params p,
+__global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 0) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* __restrict__ x_in, T* x_out,
                                                                   const T* __restrict__ noise,
