@@ -754,7 +754,9 @@ __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const d
     store_tile(cdf, n, tile, c);
     if (tile == ntiles - 1) {
       const int64_t last = n - 1 - tile * kScanTile;
-      if ((int64_t)threadIdx.x == last / kItems) stats[PFB_STAT_TOTAL] = c[last % kItems];
+      // the elements past the end of the data are zeros (load_tile), so the thread's last entry equals the entry of
+      // element n - 1; a dynamic c[last % kItems] would move the whole array to local memory
+      if ((int64_t)threadIdx.x == last / kItems) stats[PFB_STAT_TOTAL] = c[kItems - 1];
     }
     __syncthreads();
   }
