@@ -686,6 +686,8 @@ def main():
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
     args = ap.parse_args()
+    if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        args.no_cpu = True  # the CPU baseline is reported at N = 1 only
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
