@@ -230,3 +230,23 @@ def test_graft_entry_build_runs():
     import __graft_entry__ as g
 
     g.build()
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) needs no GPU: one JSON line with the
+    same metric / config keys, impl = reference, a cpu_baseline describing the run and an e2e that repeats the value"""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-particles", "20000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
