@@ -344,8 +344,11 @@ def run_gpu(args):
         eng.scan(cdf, logw=logw, exact=exact)
         if ev:
             ev[2].record()
-        eng.resample(cdf, ub, gather[0] if gather is not None else x, alt, n, D, systematic=args.resampling == "systematic",
-                     est_kind=est_kind, est_out=est, x_in_stride=xg_stride)
+        if args.resampling == "multinomial_sorted":  # in-kernel draws (no uniform array exists for this mode)
+            eng.resample_msort(cdf, 1234 + rank, i + 1, x, alt, n, D, est_kind=est_kind, est_out=est)
+        else:
+            eng.resample(cdf, ub, gather[0] if gather is not None else x, alt, n, D, systematic=args.resampling == "systematic",
+                         est_kind=est_kind, est_out=est, x_in_stride=xg_stride)
         if ev:
             ev[3].record()
         x, alt = alt, x
@@ -684,7 +687,7 @@ def main():
     ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
-    ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "systematic"])
+    ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "multinomial_sorted", "systematic"])
     args = ap.parse_args()
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         args.no_cpu = True  # the CPU baseline is reported at N = 1 only

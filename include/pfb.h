@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 4
+#define PFB_ABI_VERSION 5
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -244,6 +244,22 @@ int pfb_resample_rng_strided(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_
                              uint64_t rng_seed, uint64_t rng_offset, const void* x_in, int32_t x_in_stride,
                              void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out, void* ws,
                              int64_t ws_bytes, void* stream);
+/* "multinomial_sorted": exact multinomial resampling with in-kernel draws whose offspring are emitted in CDF
+ * order instead of the order of the reference's uniform stream (abstract_dirac_distribution.py:82-84 draws n_out
+ * i.i.d. uniforms; here the SAME joint distribution is generated leaf by leaf: [0, 1) is cut into K = 2^k equal
+ * leaves, the leaf occupancies -- multinomial(n_out; 1/K, ..) -- come from exact binomial splitting with p = 1/2
+ * (popcounts of Philox bit streams) and each leaf's uniforms from fresh (53 - k)-bit draws).  The output is a
+ * permutation of what pfb_resample_rng would give for the same multiset of uniforms; idx_out (optional) receives the
+ * source index of every output slot, non-decreasing up to the order inside a leaf.  Lookups hit neighbouring cache
+ * lines and the stores stream, which removes the two DRAM misses per particle of the reference-order gather.
+ * x_in_stride: components per source record (0 = dim).  est_kind / est_out as in pfb_resample. */
+int pfb_resample_msort(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf,
+                       uint64_t rng_seed, uint64_t rng_offset, const void* x_in, int32_t x_in_stride, void* x_out,
+                       int64_t* idx_out, int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream);
+/* fill `out` (n_out doubles, slot order) with the uniforms pfb_resample_msort uses (tests, debugging) */
+int pfb_msort_uniforms(int64_t n_out, uint64_t rng_seed, uint64_t rng_offset, double* out, void* ws, int64_t ws_bytes,
+                       void* stream);
+
 /* Sharded filter (one filter split over several GPUs): this rank owns particles
  * [start, start + n) of a global CDF C_i = fl(cdf_offset + c_i), normalised by `total` (the sum over all
  * shards).  Produces the `count` systematic offspring j = j_begin .. j_begin + count - 1 of the global

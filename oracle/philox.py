@@ -145,3 +145,79 @@ def vonmises(seed, offset, n, kappas, tables):
             pending = pending[~acc]
             attempt += 1
     return out
+
+
+# ---- "multinomial_sorted" draws (pfb_msort.cu) --------------------------------------------------------------
+# n_out i.i.d. uniforms generated leaf by leaf: [0, 1) is cut into K = 2^k equal leaves; the occupancies are
+# multinomial(n_out; 1/K, ..), drawn by binomial splitting with p = 1/2 -- a node holding m uniforms hands
+# popcount(first m bits of its Philox stream) to its left child -- and the uniforms of leaf b are
+# (b 2^(53-k) + r) 2^-53 with fresh (53-k)-bit draws r.  Slot order = leaf order.
+MS_LEAF_TARGET = 32
+MS_SLOT_TREE = 64
+MS_SLOT_LEAF = 33
+
+
+def msort_levels(n_out):
+    k = 0
+    while (MS_LEAF_TARGET << k) < n_out:
+        k += 1
+    return k
+
+
+def msort_top_levels(k):
+    """levels whose nodes are coarse bins (one CTA each): pfb_msort.cu ms_plan"""
+    if k <= 4:
+        return 0
+    return max(k - 9, min(k - 4, 9))
+
+
+def _popcount32(x):
+    x = x.astype(np.uint32)
+    x = x - ((x >> np.uint32(1)) & np.uint32(0x55555555))
+    x = (x & np.uint32(0x33333333)) + ((x >> np.uint32(2)) & np.uint32(0x33333333))
+    x = (x + (x >> np.uint32(4))) & np.uint32(0x0F0F0F0F)
+    return ((x * np.uint32(0x01010101)) >> np.uint32(24)).astype(np.int64)
+
+
+def msort_leaf_counts(seed, offset, n_out):
+    """occupancy of the 2^k leaves (int64 array), by the popcount tree"""
+    k = msort_levels(n_out)
+    cnt = np.array([n_out], dtype=np.int64)
+    for l in range(k):
+        nblk = (cnt + 127) // 128                      # Philox blocks per node
+        node = np.repeat(np.arange(cnt.shape[0], dtype=np.uint64), nblk)
+        first = np.cumsum(nblk) - nblk
+        q = np.arange(int(nblk.sum()), dtype=np.uint64) - np.repeat(first, nblk).astype(np.uint64)
+        r = rng_block(seed, offset, (node << np.uint64(32)) | q, MS_SLOT_TREE + l)
+        bits = np.minimum(128, np.repeat(cnt, nblk) - q.astype(np.int64) * 128)   # bits used of each block
+        pc = np.zeros(q.shape[0], dtype=np.int64)
+        for j in range(4):
+            b = np.clip(bits - 32 * j, 0, 32)
+            mask = np.where(b >= 32, np.uint64(0xFFFFFFFF), (np.uint64(1) << b.astype(np.uint64)) - np.uint64(1))
+            pc += _popcount32(r[:, j].astype(np.uint64) & mask)
+        left = np.zeros(cnt.shape[0], dtype=np.int64)
+        np.add.at(left, node.astype(np.int64), pc)
+        nxt = np.empty(2 * cnt.shape[0], dtype=np.int64)
+        nxt[0::2] = left
+        nxt[1::2] = cnt - left
+        cnt = nxt
+    return cnt
+
+
+def msort_uniforms(seed, offset, n_out):
+    """the n_out uniforms of pfb_resample_msort in slot order, and the leaf of every slot"""
+    k = msort_levels(n_out)
+    cnt = msort_leaf_counts(seed, offset, n_out)
+    leaf = np.repeat(np.arange(cnt.shape[0], dtype=np.uint64), cnt)
+    # in-leaf draws: one Philox block per pair of slots (2 j, 2 j + 1) of a coarse bin (the unit one CTA works on)
+    k_top = msort_top_levels(k)
+    binc = cnt.reshape(1 << k_top, -1).sum(axis=1)
+    bin_id = np.repeat(np.arange(binc.shape[0], dtype=np.uint64), binc)
+    s = np.arange(n_out, dtype=np.uint64) - np.repeat(np.cumsum(binc) - binc, binc).astype(np.uint64)
+    r = rng_block(seed, offset, (bin_id << np.uint64(32)) | (s >> np.uint64(1)), MS_SLOT_LEAF)
+    odd = (s & np.uint64(1)).astype(bool)
+    hi = np.where(odd, r[:, 2], r[:, 0]).astype(np.uint64)
+    lo = np.where(odd, r[:, 3], r[:, 1]).astype(np.uint64)
+    r64 = (hi << np.uint64(32)) | lo
+    R = (leaf << np.uint64(53 - k)) | (r64 >> np.uint64(11 + k))
+    return R.astype(np.float64) * 2.0**-53, leaf.astype(np.int64)

@@ -135,6 +135,22 @@ class Engine:
                                           _stream(self.device)))
         self.launches += 1 if systematic else 3
 
+    def resample_msort(self, cdf, seed, offset, x_in, x_out, n_out, dim, idx_out=None, est_kind=L.EST_NONE, est_out=None,
+                       x_in_stride=0):
+        """exact multinomial resampling, offspring in CDF order (pfb_resample_msort)"""
+        n = cdf.shape[0]
+        ws, wsb = self._ensure_ws(n)
+        dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64
+        L.check(self.lib.pfb_resample_msort(dt, dim, n, n_out, _ptr(cdf), seed, offset, _ptr(x_in), x_in_stride,
+                                            _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
+                                            _stream(self.device)))
+        self.launches += 4  # count tree, record build + fill, resample
+
+    def msort_uniforms(self, out, seed, offset):
+        ws, wsb = self._ensure_ws(0)
+        L.check(self.lib.pfb_msort_uniforms(out.numel(), seed, offset, _ptr(out), ws, wsb, _stream(self.device)))
+        self.launches += 2
+
     def resample_sharded(self, cdf, cdf_offset, total, u0, j_begin, count, n_total_out, x_in, x_out, dim, idx_out=None,
                          est_kind=L.EST_NONE, est_out=None):
         dt = _DT[x_in.dtype] if x_in is not None else L.PFB_F64

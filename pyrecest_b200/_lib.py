@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 4
+ABI_VERSION = 5
 VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
@@ -95,6 +95,9 @@ SIGNATURES = {
     "pfb_resample_strided": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "pfb_resample_rng_strided": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, C.c_uint64, C.c_uint64, _vp, _i32, _vp, _vp, _i32,
                                            _vp, _vp, _i64, _vp]),
+    "pfb_resample_msort": (C.c_int, [C.c_int, _i32, _i64, _i64, _vp, C.c_uint64, C.c_uint64, _vp, _i32, _vp, _vp, _i32, _vp,
+                                     _vp, _i64, _vp]),
+    "pfb_msort_uniforms": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp, _i64, _vp]),
     "pfb_resample_sharded": (C.c_int, [C.c_int, _i32, _i64, _vp, C.c_double, C.c_double, C.c_double, _i64, _i64, _i64,
                                        _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),

@@ -45,7 +45,12 @@ constexpr int kGuideShift = 3;           // guide table: one bucket per 2^3 = 8 
 inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
 constexpr int kWsJobCap = 16384;                          // (source, first slot, count) triples of heavy particles
 constexpr int64_t kWsJobs = (int64_t)kWsJobCap * 3 * 8;
-inline int64_t ws_header() { return kWsCounters + kWsPartials + kWsJobs; }
+// count tree of the sorted-order multinomial resampling (pfb_msort.cu): node counts and left-child accumulators of
+// the top levels (2^18 ints each: up to 2^17 coarse bins) and the exclusive offsets of the coarse bins (2^17 + 64)
+constexpr int kMsTopMaxLevels = 17;
+constexpr int64_t kMsTreeInts = (int64_t)1 << (kMsTopMaxLevels + 1);
+constexpr int64_t kWsMs = (2 * kMsTreeInts + ((int64_t)1 << kMsTopMaxLevels) + 64) * 4;
+inline int64_t ws_header() { return kWsCounters + kWsPartials + kWsJobs + kWsMs; }
 // guide table of the resampling search: M = 2^k buckets, M >= n / 2^kGuideShift (PFB_GUIDE_SHIFT overrides)
 int guide_shift();
 inline int64_t guide_buckets(int64_t n) {
@@ -62,6 +67,7 @@ struct Workspace {
   unsigned int* counters;
   double* partials;
   long long* jobs;  // kWsJobCap triples (systematic resampling: offspring runs that are spread over the grid)
+  int32_t* ms;      // kWsMs bytes: count tree of pfb_resample_msort
   unsigned char* tiles;
   int64_t tile_bytes;
   int32_t* guide;

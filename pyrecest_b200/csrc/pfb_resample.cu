@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "pfb_common.cuh"
+#include "pfb_resample.cuh"
 
 namespace pfb {
 
@@ -57,6 +58,7 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out) {
   out->counters = reinterpret_cast<unsigned int*>(b);
   out->partials = reinterpret_cast<double*>(b + kWsCounters);
   out->jobs = reinterpret_cast<long long*>(b + kWsCounters + kWsPartials);
+  out->ms = reinterpret_cast<int32_t*>(b + kWsCounters + kWsPartials + kWsJobs);
   out->tiles = b + ws_header();
   out->tile_bytes = ws_bytes - ws_header();
   out->guide = reinterpret_cast<int32_t*>(b + guide_offset(n));
@@ -100,24 +102,6 @@ __device__ __forceinline__ int32_t ld_guide(const int32_t* p, uint64_t pol) {
   return v;
 }
 
-__device__ __forceinline__ bool cdf_le(double c, double total, double u, double tl, double th) {
-  if (c <= tl) return true;
-  if (c >= th) return false;
-  return __ddiv_rn(c, total) <= u;
-}
-
-template <bool RIGHT>
-__device__ __forceinline__ int64_t search_range(const double* __restrict__ cdf, int64_t lo, int64_t hi,
-                                                double total, double q) {
-  // RIGHT: first i in [lo, hi) with v_i > q (count of v_i <= q);  LEFT: first i with v_i >= q
-  while (lo < hi) {
-    const int64_t mid = lo + ((hi - lo) >> 1);
-    const double v = __ddiv_rn(__ldg(cdf + mid), total);
-    const bool go_right = RIGHT ? (v <= q) : (v < q);
-    if (go_right) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 // Element-driven guide build: b_i = floor(v_i M) is non-decreasing, and G[b] = first i with b_i >= b, so
 // element i owns the buckets (b_{i-1}, b_i].  The CDF is streamed once; long runs (a heavy particle
@@ -186,19 +170,6 @@ __global__ void __launch_bounds__(kThreads) guide_kernel(int64_t n, const double
 //     q_k < p  =>  v_k < u   (counted)        q_k > p  =>  v_k > u   (not counted)
 // and only q_k == p (probability ~ count / 65536) or count > 29 needs the exact search in the CDF itself.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRecShift = 4;
-constexpr int kRecEntries = 29;
-
-inline int64_t rec_buckets(int64_t n) {
-  int64_t want = n >> kRecShift;
-  int64_t M = 1;
-  while (M < want) M <<= 1;
-  return M;
-}
-inline int64_t rec_offset(int64_t n) {
-  return (guide_offset(n) + (guide_buckets(n) + 2) * (int64_t)sizeof(int32_t) + 255) & ~(int64_t)255;
-}
-inline int64_t rec_bytes(int64_t n) { return (rec_buckets(n) + 2) * 64; }
 static bool two_pass_record_build() {
   const char* e = getenv("PFB_RECORD_BUILD");  // "2pass": guide_kernel + bucket_record_kernel (kept as a cross-check)
   return e && e[0] == '2';
@@ -464,48 +435,6 @@ __global__ void __launch_bounds__(kThreads) record_fill_kernel(uint4* __restrict
   if (block_is_last(done_count) && threadIdx.x == 0) *job_count = 0u;  // self-cleaning
 }
 
-// One 32-byte sector in ONE load instruction (LDG.256, 32-byte aligned address).
-__device__ __forceinline__ void ld_sector(const void* p, uint64_t (&w)[4]) {
-  asm volatile("ld.global.nc.L2::64B.v4.u64 {%0, %1, %2, %3}, [%4];"
-               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
-               : "l"(p));
-}
-
-// Random gather of one particle record.  Component-wise loads of a record send one request per component
-// to L2 for what is one (or two) 32-byte sectors, and L2 does not merge misses in flight: the 24-byte T^3
-// record cost ~150 bytes of DRAM reads.  Here every covering sector is loaded exactly once (sector-aligned,
-// so the reads stay inside the 256-byte allocation granule) and the components are selected from registers.
-template <typename T, int D>
-__device__ __forceinline__ void gather_rec(const T* __restrict__ x, int64_t i, double (&r)[D], int64_t stride = D) {
-  constexpr int R = D * (int)sizeof(T);
-  constexpr int WPS = 32 / (int)sizeof(T);                  // components per sector
-  constexpr int NS = (R - (int)sizeof(T)) / 32 + 2;         // sectors a record can touch
-  const uintptr_t a = reinterpret_cast<uintptr_t>(x + i * stride);
-  const int off = (int)(a & 31) / (int)sizeof(T);
-  const unsigned char* base = reinterpret_cast<const unsigned char*>(a & ~(uintptr_t)31);
-  uint64_t raw[NS][4];
-#pragma unroll
-  for (int sct = 0; sct < NS; ++sct) {
-    if (sct == 0 || off * (int)sizeof(T) + R > 32 * sct) ld_sector(base + 32 * sct, raw[sct]);
-    else raw[sct][0] = raw[sct][1] = raw[sct][2] = raw[sct][3] = 0ull;
-  }
-  auto word = [&](int k) -> double {  // component k of the sector-aligned span (k is a compile-time constant)
-    if constexpr (sizeof(T) == 8) {
-      return __longlong_as_double((long long)raw[k / 4][k % 4]);
-    } else {
-      const uint64_t v = raw[k / 8][(k % 8) / 2];
-      return (double)__uint_as_float((k & 1) ? (uint32_t)(v >> 32) : (uint32_t)v);
-    }
-  };
-#pragma unroll
-  for (int c = 0; c < D; ++c) {
-    double v = word(c);
-#pragma unroll
-    for (int o = 1; o < WPS; ++o)
-      if (c + o < NS * WPS && off == o) v = word(c + o);
-    r[c] = v;
-  }
-}
 
 // phase 4 of the resampling kernels: gather the kBatch source records, store them, accumulate the fused estimate
 template <typename T, int D, int EST, int NE>
@@ -543,30 +472,6 @@ __device__ __forceinline__ void gather_store(const T* __restrict__ x_in, T* __re
   }
 }
 
-// deterministic grid reduction of the fused estimate: per-CTA partials, the last CTA sums them in a fixed order
-template <int NE>
-__device__ __forceinline__ void finish_estimate(double (&acc)[NE], double* red, Workspace ws, double* est_out,
-                                                int64_t n_out) {
-  block_sum<NE>(acc, red);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
-  }
-  if (block_is_last(ws.counters)) {
-    double t[NE];
-#pragma unroll
-    for (int k = 0; k < NE; ++k) t[k] = 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-#pragma unroll
-      for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)b * kPartialDoubles + k];
-    }
-    block_sum<NE>(t, red);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < NE; ++k) est_out[k] = t[k] / (double)n_out;
-    }
-  }
-}
 
 template <typename T, int D, int EST>
 __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n_out,
@@ -624,11 +529,15 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
         frac[q] = 0.0;
       } else {
         const double ub = uj[q] * dM;             // exact
-        const int64_t b = (int64_t)ub;
+        int64_t b = (int64_t)ub;
+        b = b < 0 ? 0 : (b > M ? M : b);
         frac[q] = ub - (double)b;                 // position of u inside its bucket, [0, 1)
         const int32_t* g = guide + run[q] * (M + 2);
         lo[q] = ld_guide(g + b, pol);
         hi[q] = ld_guide(g + b + 1, pol);
+        // (a run whose total is 0 / NaN leaves its guide unwritten: keep every later load inside the run)
+        lo[q] = lo[q] < 0 ? 0 : (lo[q] > (int32_t)run_len ? (int32_t)run_len : lo[q]);
+        hi[q] = hi[q] < lo[q] ? lo[q] : (hi[q] > (int32_t)run_len ? (int32_t)run_len : hi[q]);
       }
     }
     // phase 2: one 64-byte window of the CDF per particle, all loads independent.  Buckets longer than
@@ -672,6 +581,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(int64_t n, int64_t n
       else if (cnt == kWin && wst[q] + kWin < hi[q])  // everything is <= u: to its right
         r = search_range<true>(cdf + run[q] * run_pad, (int64_t)wst[q] + kWin, (int64_t)hi[q], total[q], uj[q]);
       if (r > run_len - 1) r = run_len - 1;
+      if (r < 0) r = 0;
       idx[q] = r;
     }
     // phase 4: gather, store, estimate
@@ -722,6 +632,7 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
       else uj[q] = __ldg(u + dst[q]);
       const double ub = uj[q] * dM;  // exact (M is a power of two), u in [0, 1)
       bkt[q] = (int64_t)ub;
+      bkt[q] = bkt[q] < 0 ? 0 : (bkt[q] > M ? M : bkt[q]);  // (an injected u outside [0, 1) must not leave the records)
       const uint32_t p = (uint32_t)((ub - (double)bkt[q]) * 65536.0);
       p2[q] = p | (p << 16);
     }
@@ -735,30 +646,8 @@ __global__ void __launch_bounds__(kThreads) resample_rec_kernel(int64_t n, int64
     int64_t idx[kBatch];
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
-      uint32_t w[16];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        w[2 * k] = (uint32_t)rec[q][k / 4][k % 4];
-        w[2 * k + 1] = (uint32_t)(rec[q][k / 4][k % 4] >> 32);
-      }
-      const int32_t base = (int32_t)w[0];
-      const uint32_t cnt = w[1] & 0xFFFFu;
-      uint32_t below = __vcmpltu2(w[1], p2[q]) & 0xFFFF0000u;
-      uint32_t eq = __vcmpeq2(w[1], p2[q]) & 0xFFFF0000u;
-      int nb = __popc(below);
-#pragma unroll
-      for (int k = 2; k < 16; ++k) {
-        nb += __popc(__vcmpltu2(w[k], p2[q]));
-        eq |= __vcmpeq2(w[k], p2[q]);
-      }
-      int64_t r = (int64_t)base + (nb >> 4);
-      if (eq != 0u || cnt > (uint32_t)kRecEntries) {  // a tie in the 16-bit grid, or a crowded bucket: exact search
-        int64_t hi = (int64_t)base + cnt;
-        if (cnt == 65535u) hi = (int64_t)(int32_t)__ldg(&recs[(run[q] * (M + 2) + bkt[q] + 1) * 4].x);
-        const double* crun = cdf + run[q] * run_pad;
-        r = search_range<true>(crun, (int64_t)base, hi, __ldg(crun + n - 1), uj[q]);
-      }
-      if (r > n - 1) r = n - 1;
+      const double* crun = cdf + run[q] * run_pad;
+      const int64_t r = record_decode(rec[q][0], rec[q][1], p2[q], recs + run[q] * (M + 2) * 4, bkt[q], crun, n, uj[q]);
       idx[q] = r;
     }
     int64_t src[kBatch];
@@ -1216,6 +1105,29 @@ extern "C" int pfb_workspace_init(void* ws, int64_t ws_bytes, void* stream) {
 }
 
 namespace pfb {
+// bucket records of one CDF in the workspace (record_build_kernel + record_fill_kernel, or the two-pass cross-check)
+int launch_record_build(int64_t n, const double* cdf, void* ws, const Workspace& W, cudaStream_t st, const uint4** recs_out,
+                        int64_t* Mr_out) {
+  const int64_t Mr = rec_buckets(n);  // the int32 guide of the Mr buckets is scratch for the record build
+  uint4* recs = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ws) + rec_offset(n));
+  if (two_pass_record_build()) {
+    guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, n);
+    PFB_LAUNCH_OK("guide_kernel");
+    bucket_record_kernel<<<stream_grid(Mr + 1, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, recs);
+    PFB_LAUNCH_OK("bucket_record_kernel");
+  } else {  // (the big-gap job list lives in the guide area: at most Mr / kBigGap + 1 jobs of 3 ints, and none if Mr <= kBigGap)
+    const int64_t tiles = (n + kRecTile - 1) / kRecTile;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(1, n, n, cdf, Mr, recs, W.guide, W.counters + 4);
+    PFB_LAUNCH_OK("record_build_kernel");
+    record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, W.guide, W.counters + 4, W.counters + 5);
+    PFB_LAUNCH_OK("record_fill_kernel");
+  }
+  *recs_out = recs;
+  *Mr_out = Mr;
+  return PFB_OK;
+}
+
 static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out, const double* cdf, const double* u,
                          RngKey key, int32_t systematic, const void* x_in, void* x_out, int64_t* idx_out,
                          int32_t est_kind, double* est_out, void* ws, int64_t ws_bytes, void* stream,
@@ -1242,21 +1154,10 @@ static int resample_impl(pfb_dtype dtype, int32_t dim, int64_t n, int64_t n_out,
     return PFB_OK;
   }
   if (bucket_records_enabled() && rec_buckets(n) <= W.guide_buckets) {
-    const int64_t Mr = rec_buckets(n);  // the int32 guide of the Mr buckets is scratch for the record build
-    uint4* recs = reinterpret_cast<uint4*>(static_cast<unsigned char*>(ws) + rec_offset(n));
-    if (two_pass_record_build()) {
-      guide_kernel<<<stream_grid((n + 3) / 4, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, n);
-      PFB_LAUNCH_OK("guide_kernel");
-      bucket_record_kernel<<<stream_grid(Mr + 1, 2), kThreads, 0, st>>>(n, cdf, W.guide, Mr, recs);
-      PFB_LAUNCH_OK("bucket_record_kernel");
-    } else {  // (the big-gap job list lives in the guide area: at most Mr / kBigGap + 1 jobs of 3 ints, and none if Mr <= kBigGap)
-      const int64_t tiles = (n + kRecTile - 1) / kRecTile;
-      const int64_t cap = (int64_t)sm_count() * 4;
-      record_build_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(1, n, n, cdf, Mr, recs, W.guide, W.counters + 4);
-      PFB_LAUNCH_OK("record_build_kernel");
-      record_fill_kernel<<<sm_count() * 4, kThreads, 0, st>>>(recs, W.guide, W.counters + 4, W.counters + 5);
-      PFB_LAUNCH_OK("record_fill_kernel");
-    }
+    const uint4* recs = nullptr;
+    int64_t Mr = 0;
+    rc = launch_record_build(n, cdf, ws, W, st, &recs, &Mr);
+    if (rc) return rc;
     PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_resample_rec<T, D>(n, n_out, cdf, u, x_in, x_out, idx_out, est_kind, est_out, W, st, recs, Mr, key, 1, 0, 0, x_in_stride))));
     if (rc) return rc;
     PFB_LAUNCH_OK("resample_rec_kernel");

@@ -6,7 +6,8 @@ Differences a pyRecEst user must know (all from BASELINE.json's north_star):
   * transitions and likelihoods come from a registry (registry.IdentityTransition /
     LinearTransition; Gaussian, (hypertoroidal) wrapped-normal, von Mises, von Mises-Fisher
     distributions).  Any other Python callable raises NotImplementedError -- it is not run on the CPU.
-  * extra, optional knobs: `resampling` ("multinomial" = reference, or "systematic"), `scan_exact`
+  * extra, optional knobs: `resampling` ("multinomial" = reference order; "multinomial_sorted" = the same exact
+    multinomial offspring counts emitted in CDF order, in-kernel draws only; or "systematic"), `scan_exact`
     (True = CDF bit-identical to numpy.cumsum), `validate` (read the device status word after each
     update to raise the reference's AssertionErrors; costs one tiny D2H sync).
   * HypersphericalParticleFilter exists (absent in the reference, configure_for_filter.py:90-100).
@@ -287,9 +288,18 @@ class AbstractParticleFilter:
         self._predicted_only_in_pad = False
         eng.scan(self._cdf, logw=self._logw, exact=self.scan_exact)
         systematic = self.resampling == "systematic"
-        if not systematic and self.resampling != "multinomial":
+        if self.resampling not in ("multinomial", "systematic", "multinomial_sorted"):
             raise ValueError(f"unknown resampling scheme {self.resampling!r}")
         src = prandom.source()
+        if self.resampling == "multinomial_sorted":
+            # exact multinomial offspring counts, emitted in CDF order (pfb_resample_msort): the draws exist only in the
+            # kernel, so there is no uniform stream to inject -- parity runs use "multinomial"
+            if not src.fused:
+                raise ValueError("resampling='multinomial_sorted' draws its uniforms in the kernel; injected uniforms "
+                                 "need resampling='multinomial' (the reference's order)")
+            eng.resample_msort(self._cdf, src.seed, src.next_offset(), x, self._alt, N, D, est_kind=self._est_kind(),
+                               est_out=self._est)
+            return self._finish_resample(x, keep)
         xg, stride = (gather[0], gather[1]) if (gather is not None and not systematic) else (x, 0)
         if src.fused:
             eng.resample_rng(self._cdf, src.seed, src.next_offset(), xg, self._alt, N, D, systematic=systematic,
@@ -298,6 +308,11 @@ class AbstractParticleFilter:
             u = src.uniforms((1,) if systematic else (N,), x.device)
             eng.resample(self._cdf, u, xg, self._alt, N, D, systematic=systematic, est_kind=self._est_kind(),
                          est_out=self._est, x_in_stride=stride)
+        return self._finish_resample(x, keep)
+
+    def _finish_resample(self, x, keep=None):
+        st = self._filter_state
+        N, D = x.shape
         del keep
         new = self._alt
         self._alt = x

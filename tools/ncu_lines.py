@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an ncu report's per-SASS-instruction samples / instruction counts by CUDA source line.
 
-  python tools/ncu_lines.py gpurun_out/prof.ncu-rep <kernel regex> <mangled-name substring> [top]
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep <kernel regex> <mangled-name substring> [top] [inst]
 
 ncu's CSV source page carries no line numbers, so the i-th SASS instruction of the kernel is matched
 with the i-th instruction of the same function in `nvdisasm -g` of the cubin inside libpfb.so
@@ -51,6 +51,7 @@ def sass_lines(mangled_sub):
 def main():
     rep, kre, sub = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+    by = 1 if (len(sys.argv) > 5 and sys.argv[5] == "inst") else 0  # sort by instructions instead of samples
     csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
                             capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(csvtxt)))
@@ -77,7 +78,7 @@ def main():
         tot_n += n
     print(f"total samples {tot_s}, warp instructions {tot_n}")
     src_cache = {}
-    for (f, ln), (s, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    for (f, ln), (s, n) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         text = ""
         for d in ("pyrecest_b200/csrc", "include"):
             pth = os.path.join(ROOT, d, f or "")
