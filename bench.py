@@ -338,7 +338,7 @@ def run_gpu(args):
         if ev:
             ev[0].record()
         # (with the padded gather copy the compact predicted particles are dead: not stored, as in filters.py)
-        eng.predict_loglik(pp, lp, x, None if gather is not None else x, nb, logw)
+        eng.predict_loglik(pp, lp, x, None if gather is not None else x, nb, logw, scaled=not args.log_weights)
         if ev:
             ev[1].record()
         eng.scan(cdf, logw=logw, exact=exact)
@@ -686,6 +686,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--log-weights", action="store_true", help="value leg: log-weights between the weighting kernel and the scan "
+                    "(PFB_WEIGHTS_LOG) instead of the slice-scaled linear weights")
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
     ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "multinomial_sorted", "systematic"])
     args = ap.parse_args()

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 5
+#define PFB_ABI_VERSION 6
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -127,7 +127,19 @@ typedef struct {
   const double* images_dev;  /* WN_MULTI: DEVICE table (n_images, 2D + 1): g_k = P o_k (D), h_k = o_k^T P o_k, o_k (D) */
   const double* mu_batch_dev; /* *_batched only: DEVICE (n_runs, D) likelihood centres, one measurement per run
                                  (NULL: `mu` for every run) */
+  int32_t out_format;        /* pfb_weight_format of the `logw` output of the weighting calls */
+  int32_t reserved;
 } pfb_lik_params;
+
+/* What the weighting calls (pfb_loglik, pfb_predict_loglik and their *_batched forms) write into `logw`:
+ *   PFB_WEIGHTS_LOG     log-weights  l_i = log pdf(x_i) (+ log w_prev_i)
+ *   PFB_WEIGHTS_SCALED  linear weights scaled per slice of 256 consecutive particles by a power of two,
+ *                       p_i = pdf(x_i) w_prev_i 2^(-e_s), e_s = ceil(max_slice(l) log2 e); the exponents stay in the
+ *                       workspace.  Only pfb_scan_cdf / pfb_scan_cdf_batched called next on the same buffers with
+ *                       PFB_SCAN_TILE_STATS_VALID | PFB_SCAN_SLICE_SCALED can read this format: its addends are
+ *                       p_i 2^(e_s - E), E the largest exponent -- exact scalings, so the step spends one exp per
+ *                       particle in all and keeps the range of the log domain. */
+typedef enum { PFB_WEIGHTS_LOG = 0, PFB_WEIGHTS_SCALED = 1 } pfb_weight_format;
 
 /* stats words written by the weighting / normalise kernels (device doubles) */
 enum {
@@ -143,6 +155,8 @@ typedef enum { PFB_SCAN_FAST = 0, PFB_SCAN_SEQEXACT = 1 } pfb_scan_mode;
 /* OR into `mode`: the workspace still holds the per-tile (max, sum exp) that pfb_loglik /
  * pfb_predict_loglik left for exactly this logw array, so pfb_scan_cdf can skip its own pass over it */
 #define PFB_SCAN_TILE_STATS_VALID 0x100
+/* OR into `mode` (together with PFB_SCAN_TILE_STATS_VALID): `logw` holds PFB_WEIGHTS_SCALED output */
+#define PFB_SCAN_SLICE_SCALED 0x200
 typedef enum { PFB_EST_NONE = 0, PFB_EST_SUM = 1, PFB_EST_TRIG = 2 } pfb_est_kind;
 typedef enum { PFB_MOM_MEAN = 0, PFB_MOM_TRIG = 1, PFB_MOM_SCATTER = 2, PFB_MOM_CENTRAL = 3 } pfb_moment_kind;
 

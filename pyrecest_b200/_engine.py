@@ -64,20 +64,24 @@ class Engine:
                                      _stream(self.device)))
         self.launches += 1
 
-    def loglik(self, lik, x, logw, w_prev=None, stats=None):
+    def loglik(self, lik, x, logw, w_prev=None, stats=None, scaled=False):
+        """scaled: write PFB_WEIGHTS_SCALED (slice-scaled linear weights, readable only by the scan that follows)
+        instead of log-weights"""
         n = x.shape[0]
         ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
-        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr())
+        lik.out_format = L.WEIGHTS_SCALED if scaled else L.WEIGHTS_LOG
+        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr(), bool(scaled))
         L.check(self.lib.pfb_loglik(C.byref(lik), _DT[x.dtype], n, _ptr(x), _ptr(w_prev), _ptr(logw), _ptr(st), ws,
                                     wsb, _stream(self.device)))
         self.launches += 1
 
-    def predict_loglik(self, params, lik, x_in, x_out, noise, logw, stats=None):
+    def predict_loglik(self, params, lik, x_in, x_out, noise, logw, stats=None, scaled=False):
         n = x_in.shape[0]
         ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
-        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr())
+        lik.out_format = L.WEIGHTS_SCALED if scaled else L.WEIGHTS_LOG
+        self._tile_stats_key = (logw.data_ptr(), n, st.data_ptr(), bool(scaled))
         L.check(self.lib.pfb_predict_loglik(C.byref(params), C.byref(lik), _DT[x_in.dtype], n, _ptr(x_in),
                                             _ptr(x_out), _ptr(noise), _ptr(logw), _ptr(st), ws, wsb,
                                             _stream(self.device)))
@@ -95,11 +99,12 @@ class Engine:
         ws, wsb = self._ensure_ws(n)
         st = self.stats if stats is None else stats
         mode = L.SCAN_SEQEXACT if exact else L.SCAN_FAST
-        have = logw is not None and self._tile_stats_key == (logw.data_ptr(), n, st.data_ptr())
+        key = self._tile_stats_key
+        have = logw is not None and key is not None and key[:3] == (logw.data_ptr(), n, st.data_ptr())
         if have:
-            mode |= L.SCAN_TILE_STATS_VALID
-        else:  # pfb_scan_cdf recomputes the per-tile stats for this input
-            self._tile_stats_key = None if logw is None else (logw.data_ptr(), n, st.data_ptr())
+            mode |= L.SCAN_TILE_STATS_VALID | (L.SCAN_SLICE_SCALED if key[3] else 0)
+        else:  # pfb_scan_cdf recomputes the per-tile stats for this input (which must hold log-weights)
+            self._tile_stats_key = None if logw is None else (logw.data_ptr(), n, st.data_ptr(), False)
         L.check(self.lib.pfb_scan_cdf(mode, n, _ptr(w), _ptr(logw), _ptr(cdf), _ptr(st), ws, wsb,
                                       _stream(self.device)))
         self.launches += (4 if exact else 2) + 1  # tile_combine | tile_stats, tile_prefix, maps + chain + final | final

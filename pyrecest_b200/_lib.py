@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 5
+ABI_VERSION = 6
 VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
@@ -26,6 +26,8 @@ LIK_GAUSS, LIK_WN_MULTI, LIK_WN_1D, LIK_VM, LIK_VMF = range(5)
 STAT_MAX, STAT_SUMEXP, STAT_SUMSQ, STAT_FLAGS, STAT_TOTAL, STAT_COUNT = 0, 1, 2, 3, 4, 8
 SCAN_FAST, SCAN_SEQEXACT = 0, 1
 SCAN_TILE_STATS_VALID = 0x100
+SCAN_SLICE_SCALED = 0x200
+WEIGHTS_LOG, WEIGHTS_SCALED = 0, 1
 EST_NONE, EST_SUM, EST_TRIG = 0, 1, 2
 MOM_MEAN, MOM_TRIG, MOM_SCATTER, MOM_CENTRAL = 0, 1, 2, 3
 
@@ -65,6 +67,7 @@ class LikParams(C.Structure):
         ("mu", C.c_double * PFB_MAXD), ("W", C.c_double * (PFB_MAXD * PFB_MAXD)),
         ("logc", C.c_double), ("kappa", C.c_double), ("sigma", C.c_double),
         ("images_dev", C.c_void_p), ("mu_batch_dev", C.c_void_p),
+        ("out_format", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -85,15 +85,9 @@ int carve_workspace(void* ws, int64_t ws_bytes, int64_t n, Workspace* out);
 // ---- numpy.mod(x, 2*pi) ----------------------------------------------------------------------
 // numpy/_core/src/npymath: mod = fmod(a, b); if (mod) { if ((b < 0) != (mod < 0)) mod += b; }
 // else mod = copysign(0, b).   fmod is exact, the add is one IEEE rounding (can return 2*pi).
-__device__ __forceinline__ double np_mod_2pi(double a) {
-  // fast exact paths for |a| < 4 pi (every in-range particle +- noise lands here):
-  //   [0, 2pi): fmod = a.   [2pi, 4pi): fmod = a - 2pi, exact by Sterbenz.   (-2pi, 0): fmod = a, then += 2pi.
-  if (a >= 0.0) {
-    if (a < kTwoPi) return a + 0.0;          // -0.0 -> +0.0 like copysign(0, b)
-    if (a < 2.0 * kTwoPi) return a - kTwoPi;
-  } else if (a > -kTwoPi) {
-    return a + kTwoPi;
-  }
+// general case of np_mod_2pi, out of line: fmod is ~150 instructions and the wrap is inlined at nine places of the
+// fused predict + weight kernel, whose instruction-cache misses were its largest stall reason
+static __device__ __noinline__ double np_mod_2pi_slow(double a) {
   double m = fmod(a, kTwoPi);
   if (m != 0.0) {
     if (m < 0.0) m += kTwoPi;
@@ -101,6 +95,23 @@ __device__ __forceinline__ double np_mod_2pi(double a) {
     m = 0.0;  // +0.0 also for -0.0 / negative multiples
   }
   return m;
+}
+
+// (fp64 literals are materialised with two UMOVs next to every instruction that uses them; values read from
+//  constant memory come as one LDCU per pair and stay in uniform registers)
+static __constant__ double kAngleConst[4] = {6.283185307179586476925286766559, 12.566370614359172953850573533118,
+                                             -6.283185307179586476925286766559, 3.141592653589793};
+__device__ __forceinline__ double np_mod_2pi(double a) {
+  // fast exact paths for |a| < 4 pi (every in-range particle +- noise lands here):
+  //   [0, 2pi): fmod = a.   [2pi, 4pi): fmod = a - 2pi, exact by Sterbenz.   (-2pi, 0): fmod = a, then += 2pi.
+  const double twopi = kAngleConst[0];
+  if (a >= 0.0) {
+    if (a < twopi) return a + 0.0;          // -0.0 -> +0.0 like copysign(0, b)
+    if (a < kAngleConst[1]) return a - twopi;
+  } else if (a > kAngleConst[2]) {
+    return a + twopi;
+  }
+  return np_mod_2pi_slow(a);
 }
 
 // ---- counter-based device RNG (Philox4x32-10) ------------------------------------------------------

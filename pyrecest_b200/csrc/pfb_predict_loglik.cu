@@ -106,7 +106,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
       for (int c = 0; c < D; ++c) {
         double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
         double s = np_mod_2pi(n[c] + mean);      // sample(): draw + mean, wrapped: s in [0, 2 pi]
-        out[c] = (s == kTwoPi) ? 0.0 : s;        // filter wraps again: mod(s) = s, except mod(2 pi) = 0
+        out[c] = (s == kAngleConst[0]) ? 0.0 : s;  // filter wraps again: mod(s) = s, except mod(2 pi) = 0
       }
     } else {
 #pragma unroll
@@ -232,7 +232,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     // exact fp64 quadratic form and, if they can contribute more than e^-37, an exp.
     double dev[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kPi) - kPi) - mu[c];
+    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kAngleConst[3]) - kAngleConst[3]) - mu[c];
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
     double best = INFINITY, sum = 0.0;
@@ -323,7 +323,7 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
             if (r <= lim) accumulate(images + k * ROW);
           }
         }
-        return L.logc - 0.5 * best + log_sum(sum);
+    return L.logc - 0.5 * best + log_sum(sum);
       }
     }
     // generic path (D > 3 or more than 64 images): the same screen in fp64, two passes
@@ -473,8 +473,24 @@ inline Seg seg_batched(int64_t n_runs, int64_t run_len) {
 // No CTA-wide barrier inside the tile loop: the likelihoods have data-dependent cost (image candidates,
 // series lengths), so every warp owns a contiguous 256-particle slice of the tile, reduces its own
 // (max, sum exp) with shuffles and stores it; pfb_scan_cdf combines the 8 partials of a tile.
-template <typename EVAL>
-__device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, double* stats, Workspace ws,
+//
+// Two output formats (pfb_lik_params.out_format):
+//   PFB_WEIGHTS_LOG     logw_i = log pdf_i; per slice (max, sum exp(l - max)).  One exp per particle here and one
+//                       more in every pass of the scan that turns log-weights into addends.
+//   PFB_WEIGHTS_SCALED  p_i = pdf_i 2^(-e_w), e_w = ceil(max_slice(l) log2 e) the slice's own binary exponent
+//                       (p_i <= ~1, the largest of a slice > 1/2); per slice (e_w, sum p).  The scan forms its
+//                       addends as p_i 2^(e_w - E) -- an exact scaling, no exp -- so the whole step spends ONE exp per
+//                       particle and keeps the range of the log domain (a slice of far-away particles scales to 0
+//                       only relative to the best slice, like exp(l - max) would).
+constexpr double kLog2e = 1.4426950408889634, kLn2 = 0.6931471805599453;
+__device__ __forceinline__ double slice_exponent(double m) {  // integer-valued; -inf for an empty slice
+  if (!(m > -INFINITY)) return -INFINITY;
+  const double e = ceil(m * kLog2e);
+  return e < -4000.0 ? -4000.0 : (e > 4000.0 ? 4000.0 : e);
+}
+
+template <bool SCALED, typename EVAL>
+__device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats, Workspace ws,
                                              double* red, EVAL eval) {
   const int64_t ntiles = sg.n_runs * sg.tpr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -483,45 +499,85 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* __restrict__ logw, 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t run = tile / sg.tpr;
     const int64_t lbase = (tile - run * sg.tpr) * kScanTile + warp * kWarpSpan + lane;
-    double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
+    if constexpr (SCALED) {
+      // pass 1 (not unrolled: the evaluation is long) parks the thread's 8 log-likelihoods in the output array itself
+      // (a register array indexed by the loop counter would go to local memory, a shared-memory column costs the
+      // L1 capacity the strided record loads live on); pass 2 (unrolled) reads them back -- the thread's own stores,
+      // still in L2 -- and exponentiates against the slice's exponent
+      constexpr int kPer = kWarpSpan / 32;
+      double m = -INFINITY;
 #pragma unroll 1
-    for (int k = 0; k < kWarpSpan / 32; ++k) {
-      const int64_t local = lbase + k * 32;
-      if (local < sg.run_len) {
-        const double v = eval(run * sg.run_len + local, run);
-        logw[run * sg.run_pad + local] = v;
-        if (v != v) {
-          gnan = 1.0;
-        } else if (v > -INFINITY) {
-          const double e = exp(-fabs(v - m));  // one exp for both cases (m = -inf: e = 0, sacc = 0 * 0 + 1)
-          sacc = (v > m) ? sacc * e + 1.0 : sacc + e;
+      for (int k = 0; k < kPer; ++k) {
+        const int64_t local = lbase + k * 32;
+        if (local < sg.run_len) {
+          double v = eval(run * sg.run_len + local, run);
+          if (v != v) { gnan = 1.0; v = -INFINITY; }
+          logw[run * sg.run_pad + local] = v;
           m = fmax(m, v);
         }
-      } else if (local < sg.run_pad) {
-        logw[run * sg.run_pad + local] = -INFINITY;  // padding of a batched run: weight 0
       }
+      const double wm = warp_max(m);
+      const double ew = slice_exponent(wm);
+      const double cw = ew * kLn2;
+      double sacc = 0.0;
+      double* mine = logw + run * sg.run_pad + lbase;
+      double cur = (lbase < sg.run_len) ? mine[0] : -INFINITY;
+#pragma unroll 1
+      for (int k = 0; k < kPer; ++k) {  // (not unrolled: eight inlined exps cost more in instruction fetch than they save)
+        const int64_t local = lbase + k * 32;
+        const double nxt = (k + 1 < kPer && local + 32 < sg.run_len) ? mine[(k + 1) * 32] : -INFINITY;
+        const double p = (cur > -INFINITY) ? exp(cur - cw) : 0.0;
+        if (local < sg.run_pad) mine[k * 32] = p;  // (padding of a batched run: weight 0)
+        sacc += p;
+        cur = nxt;
+      }
+      const double wsum = warp_sum(sacc);
+      if (lane == 0) {
+        ws.wpart[tile * 16 + 2 * warp] = ew;
+        ws.wpart[tile * 16 + 2 * warp + 1] = wsum;
+      }
+      gmax = fmax(gmax, wm);
+    } else {
+      double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
+#pragma unroll 1
+      for (int k = 0; k < kWarpSpan / 32; ++k) {
+        const int64_t local = lbase + k * 32;
+        if (local < sg.run_len) {
+          const double v = eval(run * sg.run_len + local, run);
+          logw[run * sg.run_pad + local] = v;
+          if (v != v) {
+            gnan = 1.0;
+          } else if (v > -INFINITY) {
+            const double e = exp(-fabs(v - m));  // one exp for both cases (m = -inf: e = 0, sacc = 0 * 0 + 1)
+            sacc = (v > m) ? sacc * e + 1.0 : sacc + e;
+            m = fmax(m, v);
+          }
+        } else if (local < sg.run_pad) {
+          logw[run * sg.run_pad + local] = -INFINITY;  // padding of a batched run: weight 0
+        }
+      }
+      const double wm = warp_max(m);
+      const double wsum = warp_sum((m > -INFINITY) ? sacc * exp(m - wm) : 0.0);
+      if (lane == 0) {
+        ws.wpart[tile * 16 + 2 * warp] = wm;
+        ws.wpart[tile * 16 + 2 * warp + 1] = wsum;
+      }
+      gmax = fmax(gmax, wm);
     }
-    const double wm = warp_max(m);
-    const double wsum = warp_sum((m > -INFINITY) ? sacc * exp(m - wm) : 0.0);
-    if (lane == 0) {
-      ws.wpart[tile * 16 + 2 * warp] = wm;
-      ws.wpart[tile * 16 + 2 * warp + 1] = wsum;
-    }
-    gmax = fmax(gmax, wm);
   }
   finish_max(gmax, gnan, stats, ws, red);
 }
 
-template <typename T, int D, int KIND>
+template <typename T, int D, int KIND, bool SCALED>
 __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg sg,
                                                           const T* __restrict__ x,
                                                           const double* __restrict__ w_prev,
-                                                          double* __restrict__ logw, double* stats,
+                                                          double* logw, double* stats,
                                                           Workspace ws) {
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
+  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double r[D];
     load_rec<T, D>(x, i, r);
     const double* mu = L.mu_batch_dev ? L.mu_batch_dev + run * D : L.mu;
@@ -531,17 +587,17 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
   });
 }
 
-template <typename T, int D, int MODE, int KIND, bool RNG>
-__global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 0) predict_loglik_kernel(pfb_predict_params p,
+template <typename T, int D, int MODE, int KIND, bool RNG, bool SCALED>
+__global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 5) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* __restrict__ x_in, T* x_out,
                                                                   const T* __restrict__ noise,
-                                                                  double* __restrict__ logw,
+                                                                  double* logw,
                                                                   double* stats, Workspace ws) {
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
+  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
     double out[D];
     predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
     if (x_out != nullptr) store_rec<T, D>(x_out, i, out);  // (NULL: only the padded copy is wanted, see pfb.h)
@@ -637,6 +693,7 @@ extern "C" int pfb_vm_strip_table(double kappa, double* table, double* area) {
 static int check_lik(const pfb_lik_params* L, int dim) {
   if (!L) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
   if (L->dim != dim) { set_error("likelihood dim %d != particle dim %d", L->dim, dim); return PFB_ERR_INVALID; }
+  if (L->out_format != PFB_WEIGHTS_LOG && L->out_format != PFB_WEIGHTS_SCALED) { set_error("bad out_format %d", L->out_format); return PFB_ERR_INVALID; }
   if (L->kind < PFB_LIK_GAUSS || L->kind > PFB_LIK_VMF) { set_error("unknown likelihood kind %d (arbitrary callables are not supported)", L->kind); return PFB_ERR_UNSUPPORTED; }
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
@@ -743,15 +800,18 @@ static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = tile_grid_seg(sg);
   const size_t sm = lik_smem(lik);
-  PFB_DISPATCH_DTYPE(dtype, {
-    if (lik->kind == PFB_LIK_WN_1D) {
-      loglik_kernel<T, 1, PFB_LIK_WN_1D><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);
-    } else if (lik->kind == PFB_LIK_VM) {
-      loglik_kernel<T, 1, PFB_LIK_VM><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);
-    } else {
-      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W))));
-    }
-  });
+#define PFB_LOGLIK_LAUNCH(S)                                                                                          \
+  PFB_DISPATCH_DTYPE(dtype, {                                                                                          \
+    if (lik->kind == PFB_LIK_WN_1D) {                                                                                  \
+      loglik_kernel<T, 1, PFB_LIK_WN_1D, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W); \
+    } else if (lik->kind == PFB_LIK_VM) {                                                                              \
+      loglik_kernel<T, 1, PFB_LIK_VM, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);    \
+    } else {                                                                                                           \
+      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W)))); \
+    }                                                                                                                  \
+  })
+  if (lik->out_format == PFB_WEIGHTS_SCALED) { PFB_LOGLIK_LAUNCH(true); } else { PFB_LOGLIK_LAUNCH(false); }
+#undef PFB_LOGLIK_LAUNCH
   PFB_LAUNCH_OK("loglik_kernel");
   return PFB_OK;
 }
@@ -763,13 +823,18 @@ static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* l
                             void* x_out, const void* noise, double* logw, double* stats, Workspace W,
                             cudaStream_t st) {
   const size_t sm = lik_smem(lik);
-  if (p->rng_kind != PFB_RNG_NONE) {
-    auto k = predict_loglik_kernel<T, D, MODE, KIND, true>;
-    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
-  } else {
-    auto k = predict_loglik_kernel<T, D, MODE, KIND, false>;
-    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W);
+  const bool scaled = lik->out_format == PFB_WEIGHTS_SCALED;
+#define PFB_FUSED_LAUNCH(R, S)                                                                                     \
+  {                                                                                                                \
+    auto k = predict_loglik_kernel<T, D, MODE, KIND, R, S>;                                                        \
+    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W); \
   }
+  if (p->rng_kind != PFB_RNG_NONE) {
+    if (scaled) PFB_FUSED_LAUNCH(true, true) else PFB_FUSED_LAUNCH(true, false)
+  } else {
+    if (scaled) PFB_FUSED_LAUNCH(false, true) else PFB_FUSED_LAUNCH(false, false)
+  }
+#undef PFB_FUSED_LAUNCH
   return PFB_OK;
 }
 

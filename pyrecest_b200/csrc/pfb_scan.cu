@@ -106,6 +106,19 @@ __device__ __forceinline__ long long inc_of(double p, int ue, bool* tie) {
   return (M >> sh) + (rem > half ? 1LL : 0LL);
 }
 
+// inc_of in floating point, for addends of a SAFE tile (every p_i <= the tile sum < 2^(e+1), so p / ulp < 2^54) whose
+// binade is not at the bottom of the range (ue >= -1000: 2^-ue is a normal double and p 2^-ue is exact):
+// k = p / ulp exactly, inc = floor(k) + [frac > 1/2], tie iff frac == 1/2 -- seven instructions instead of ~40 of
+// 64-bit integer work.
+__device__ __forceinline__ long long inc_of_fast(double p, double inv_ulp, bool* tie) {
+  const double k = p * inv_ulp;
+  const double f = floor(k);
+  const double d = k - f;  // exact
+  if (d == 0.5) *tie = true;
+  return __double2ll_rz(f) + (d > 0.5 ? 1LL : 0LL);
+}
+constexpr int kFastUlpMin = -1000;
+
 __device__ __forceinline__ double ulp_value(int ue) {  // 2^ue, ue >= -1074
   long long b = (ue >= -1022) ? ((long long)(ue + 1023) << 52) : (1LL << (ue + 1074));
   return __longlong_as_double(b);
@@ -292,6 +305,14 @@ __device__ __forceinline__ int block_min_int(int v, int* smem /* 33 */) {
 }
 
 // ---- tile sums and their prefix ------------------------------------------------------------------
+// input of the scan: plain weights, log-weights (addend exp(l - shift)), or the slice-scaled linear weights of
+// PFB_WEIGHTS_SCALED (addend p 2^(e_slice - E): an exact scaling, no exp)
+enum { kInW = 0, kInLog = 1, kInScaled = 2 };
+__device__ __forceinline__ double pow2_of(double d) {  // 2^d for integer-valued d (0 below the subnormals)
+  if (!(d > -1100.0)) return 0.0;
+  return scalbn(1.0, (int)d);
+}
+
 template <bool FROM_LOG>
 __global__ void __launch_bounds__(kThreads) tile_stats_kernel(int64_t n, const double* __restrict__ in,
                                                               const double* __restrict__ stats, TileState ts,
@@ -333,6 +354,27 @@ __global__ void __launch_bounds__(kThreads) tile_combine_kernel(TileState ts, co
   }
 }
 
+// the same for PFB_WEIGHTS_SCALED partials (slice exponent, sum p): tile exponent = largest slice exponent
+__global__ void __launch_bounds__(kThreads) tile_combine_scaled_kernel(TileState ts, const double* __restrict__ wpart,
+                                                                       int64_t ntiles) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += stride) {
+    double m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmax(m, wpart[t * 16 + 2 * w]);
+    double sacc = 0.0;
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const double ew = wpart[t * 16 + 2 * w];
+        if (ew > -INFINITY) sacc += wpart[t * 16 + 2 * w + 1] * pow2_of(ew - m);
+      }
+    }
+    ts.tmax[t] = m;
+    ts.tsum[t] = sacc;
+  }
+}
+
 // Segmented variant for batched runs: one warp per run.  The shift of a run is the max over its tiles.
 __global__ void __launch_bounds__(kThreads) tile_prefix_runs_kernel(TileState ts, int64_t n_runs, int tpr,
                                                                     int from_log) {
@@ -353,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) tile_prefix_runs_kernel(TileState ts
       double v = 0.0;
       if (t < tpr) {
         const double tm = ts.tmax[t0 + t];
-        const double sc = from_log ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0;
+        const double sc = from_log ? ((tm == -INFINITY) ? 0.0 : (from_log == kInScaled ? pow2_of(tm - M) : exp(tm - M))) : 1.0;
         v = ts.tsum[t0 + t] * sc;
       }
       double inc = v;
@@ -374,11 +416,21 @@ __global__ void __launch_bounds__(kThreads) tile_prefix_runs_kernel(TileState ts
 
 // one CTA: aprefix[t] = sum_{s<t} tsum[s] exp(tmax[s] - M), t = 0 .. ntiles - 1
 __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t ntiles,
-                                                           const double* __restrict__ max_ptr) {
+                                                           const double* __restrict__ max_ptr, int scaled) {
   __shared__ double s_warp[33];
   __shared__ double s_carry;
-  const double M = max_ptr ? *max_ptr : 0.0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double M = max_ptr ? *max_ptr : 0.0;
+  if (scaled) {  // the common exponent E = largest tile exponent
+    double m = -INFINITY;
+    for (int64_t t = threadIdx.x; t < ntiles; t += 1024) m = fmax(m, ts.tmax[t]);
+    m = warp_max(m);
+    if (lane == 0) s_warp[warp] = m;
+    __syncthreads();
+    m = s_warp[lane];
+    M = warp_max(m);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) s_carry = 0.0;
   __syncthreads();
   for (int64_t base = 0; base < ntiles; base += 1024) {
@@ -386,7 +438,7 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
     double v = 0.0;
     if (t < ntiles) {
       const double tm = ts.tmax[t];
-      const double sc = max_ptr ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0;
+      const double sc = scaled ? ((tm == -INFINITY) ? 0.0 : pow2_of(tm - M)) : (max_ptr ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0);
       v = ts.tsum[t] * sc;
     }
     double inc = v;
@@ -436,9 +488,9 @@ constexpr long long kTieBit = 1LL << 40;          // OR-ed into the binade of a 
 __device__ __forceinline__ bool cls_has_tie(long long c) { return c > (kTieBit >> 1); }  // binades are |e| < 1100
 __device__ __forceinline__ long long cls_binade(long long c) { return cls_has_tie(c) ? c - kTieBit : c; }
 
-template <bool FROM_LOG>
+template <int IN>
 __device__ __forceinline__ void load_tile(const double* __restrict__ in, int64_t n, int64_t tile, double shift,
-                                          double (&p)[kItems]) {
+                                          double (&p)[kItems], const double* __restrict__ wpart = nullptr) {
   const int64_t base = tile * kScanTile + (int64_t)threadIdx.x * kItems;
   if (base + kItems <= n) {
     const double2* q = reinterpret_cast<const double2*>(in + base);
@@ -449,11 +501,17 @@ __device__ __forceinline__ void load_tile(const double* __restrict__ in, int64_t
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) p[k] = (base + k < n) ? in[base + k] : (FROM_LOG ? -INFINITY : 0.0);
+    for (int k = 0; k < kItems; ++k) p[k] = (base + k < n) ? in[base + k] : (IN == kInLog ? -INFINITY : 0.0);
   }
-  if (FROM_LOG) {
+  if constexpr (IN == kInLog) {
 #pragma unroll
     for (int k = 0; k < kItems; ++k) p[k] = exp(p[k] - shift);  // exp(-inf) = 0
+  } else if constexpr (IN == kInScaled) {
+    // the 8 elements of a thread lie in one 256-particle slice (warp w of the weighting kernel): one power of two
+    const double ew = wpart[tile * 16 + 2 * (threadIdx.x >> 5)];
+    const double f = (ew > -INFINITY) ? pow2_of(ew - shift) : 0.0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) p[k] *= f;
   }
 }
 
@@ -482,9 +540,10 @@ __device__ __forceinline__ long long classify_tile(const TileState& ts, int64_t 
   return elo == ehi ? (long long)elo : kHardTile;
 }
 
-template <bool FROM_LOG>
+template <int IN>
 __global__ void __launch_bounds__(kThreads) scan_maps_kernel(int64_t n, const double* __restrict__ in, TileState ts,
-                                                             int64_t ntiles, int64_t tpr, double margin) {
+                                                             int64_t ntiles, int64_t tpr, double margin,
+                                                             const double* __restrict__ wpart) {
   __shared__ long long s_ll[72];
   long long* cls = reinterpret_cast<long long*>(ts.flagB);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -492,12 +551,18 @@ __global__ void __launch_bounds__(kThreads) scan_maps_kernel(int64_t n, const do
     if (threadIdx.x == 0) cls[tile] = e;
     if (e == kHardTile) continue;
     double p[kItems];
-    load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
+    load_tile<IN>(in, n, tile, IN != kInW ? ts.tmax[tile] : 0.0, p, wpart);
     const int ue = (int)e - 52;
     bool tie = false;
     long long inc = 0;
+    if (ue >= kFastUlpMin) {  // (block-uniform) floating-point form of the increments
+      const double inv_ulp = ulp_value(-ue);
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) inc += inc_of(p[k], ue, &tie);
+      for (int k = 0; k < kItems; ++k) inc += inc_of_fast(p[k], inv_ulp, &tie);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) inc += inc_of(p[k], ue, &tie);
+    }
     if (!__syncthreads_or(tie ? 1 : 0)) {  // no tie in the whole tile: the tile is a plain integer sum
       long long tot;
       block_excl_scan_ll(inc, s_ll, &tot);
@@ -591,10 +656,11 @@ __device__ __forceinline__ double hard_tile_walk(const double (&p)[kItems], int 
   return cur;
 }
 
-template <bool FROM_LOG>
+template <int IN>
 __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const double* __restrict__ in,
                                                               double* __restrict__ cdf, double* stats, TileState ts,
-                                                              int64_t n_runs, int64_t tpr, unsigned int* err) {
+                                                              int64_t n_runs, int64_t tpr, unsigned int* err,
+                                                              const double* __restrict__ wpart) {
   __shared__ long long s_ll[72];
   __shared__ int s_int[40];
   __shared__ double s_cur;
@@ -608,7 +674,7 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
       const long long e = (cls[t] == kHardTile) ? kHardTile : cls_binade(cls[t]);
       if (e == kHardTile) {
         double p[kItems], c[kItems];
-        load_tile<FROM_LOG>(in, n, t, FROM_LOG ? ts.tmax[t] : 0.0, p);
+        load_tile<IN>(in, n, t, IN != kInW ? ts.tmax[t] : 0.0, p, wpart);
         const int64_t left = n - t * kScanTile;
         const int cnt = (int)(left < kScanTile ? left : kScanTile);
         cur = hard_tile_walk(p, cnt, cur, c, s_ll, s_int, &s_cur);
@@ -695,10 +761,10 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
   }
 }
 
-template <bool EXACT, bool FROM_LOG>
+template <bool EXACT, int IN>
 __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const double* __restrict__ in,
                                                               double* __restrict__ cdf, double* stats, TileState ts,
-                                                              int64_t ntiles) {
+                                                              int64_t ntiles, const double* __restrict__ wpart) {
   __shared__ double s_dbl[40];
   __shared__ long long s_ll[72];
   const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
@@ -712,7 +778,7 @@ __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const d
       e = cls_binade(e);
     }
     double p[kItems], c[kItems];
-    load_tile<FROM_LOG>(in, n, tile, FROM_LOG ? ts.tmax[tile] : 0.0, p);
+    load_tile<IN>(in, n, tile, IN != kInW ? ts.tmax[tile] : 0.0, p, wpart);
     if constexpr (!EXACT) {
       double tsum = p[0];
 #pragma unroll
@@ -731,8 +797,14 @@ __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const d
         long long inc[kItems];
         bool tie = false;
         long long tsum = 0;
+        if (ue >= kFastUlpMin) {
+          const double inv_ulp = ulp_value(-ue);
 #pragma unroll
-        for (int k = 0; k < kItems; ++k) { inc[k] = inc_of(p[k], ue, &tie); tsum += inc[k]; }
+          for (int k = 0; k < kItems; ++k) { inc[k] = inc_of_fast(p[k], inv_ulp, &tie); tsum += inc[k]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kItems; ++k) { inc[k] = inc_of(p[k], ue, &tie); tsum += inc[k]; }
+        }
         long long tot;
         long long S = S0 + block_excl_scan_ll(tsum, s_ll, &tot);
 #pragma unroll
@@ -786,14 +858,18 @@ extern "C" int pfb_normalize(int64_t n, const double* logw, double* w_out, doubl
 
 namespace pfb {
 // n: elements in the (possibly padded) array; n_runs runs of tpr tiles each (n_runs = 1: tpr = all tiles)
-static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, double* cdf, double* stats,
+static int scan_impl(int32_t mode, int64_t n, const double* in, int in_kind, double* cdf, double* stats,
                      Workspace W, int64_t n_runs, int64_t tpr, bool have_tile_stats, cudaStream_t st) {
   const int64_t ntiles = n_runs * tpr;
   unsigned int* ticket = W.counters + 1;
   unsigned int* err = W.counters + 2;
   TileState ts = make_tile_state(W.tiles, ntiles, ticket);
+  const bool from_log = in_kind == kInLog, scaled = in_kind == kInScaled;
   // 1. per-tile sums: combine the partials the weighting kernel left in the workspace, or make them here
-  if (have_tile_stats) {
+  if (scaled) {
+    tile_combine_scaled_kernel<<<stream_grid(ntiles), kThreads, 0, st>>>(ts, W.wpart, ntiles);
+    PFB_LAUNCH_OK("tile_combine_scaled_kernel");
+  } else if (have_tile_stats) {
     tile_combine_kernel<<<stream_grid(ntiles), kThreads, 0, st>>>(ts, W.wpart, ntiles);
     PFB_LAUNCH_OK("tile_combine_kernel");
   } else {
@@ -804,31 +880,30 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, bool from_log, d
   }
   // 2. approximate prefix of the tile sums (one CTA; one warp per run when batched)
   if (n_runs == 1) {
-    tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr);
+    tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr, scaled ? 1 : 0);
     PFB_LAUNCH_OK("tile_prefix_kernel");
   } else {
     const int64_t warps = (int64_t)sm_count() * 8 * (kThreads / 32);
     const int g = (int)((n_runs < warps ? n_runs : warps) * 32 + kThreads - 1) / kThreads;
-    tile_prefix_runs_kernel<<<g, kThreads, 0, st>>>(ts, n_runs, (int)tpr, from_log ? 1 : 0);
+    tile_prefix_runs_kernel<<<g, kThreads, 0, st>>>(ts, n_runs, (int)tpr, in_kind);
     PFB_LAUNCH_OK("tile_prefix_runs_kernel");
   }
   // 3. the scan proper
   const double margin = 4.0 * (double)(n + kScanTile) * 1.1102230246251565e-16;
   const int tg = (int)(ntiles < (int64_t)sm_count() * 8 ? ntiles : (int64_t)sm_count() * 8);
+  const double* wp = W.wpart;
   if (mode == PFB_SCAN_SEQEXACT) {
     const int rg = (int)(n_runs < (int64_t)sm_count() * 8 ? n_runs : (int64_t)sm_count() * 8);
-    if (from_log) {
-      scan_maps_kernel<true><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin);
-      scan_chain_kernel<true><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err);
-      scan_final_kernel<true, true><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
-    } else {
-      scan_maps_kernel<false><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin);
-      scan_chain_kernel<false><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err);
-      scan_final_kernel<true, false><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
-    }
+#define PFB_SCAN_EXACT(IN)                                                                            \
+    scan_maps_kernel<IN><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin, wp);                \
+    scan_chain_kernel<IN><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err, wp);      \
+    scan_final_kernel<true, IN><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, wp);
+    if (scaled) { PFB_SCAN_EXACT(kInScaled) } else if (from_log) { PFB_SCAN_EXACT(kInLog) } else { PFB_SCAN_EXACT(kInW) }
+#undef PFB_SCAN_EXACT
   } else {
-    if (from_log) scan_final_kernel<false, true><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
-    else scan_final_kernel<false, false><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles);
+    if (scaled) scan_final_kernel<false, kInScaled><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, wp);
+    else if (from_log) scan_final_kernel<false, kInLog><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, wp);
+    else scan_final_kernel<false, kInW><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, wp);
   }
   PFB_LAUNCH_OK("scan kernels");
   return PFB_OK;
@@ -841,14 +916,16 @@ extern "C" int pfb_scan_cdf(int32_t mode, int64_t n, const double* w, const doub
   if ((w == nullptr) == (logw == nullptr)) { set_error("exactly one of w / logw must be given"); return PFB_ERR_INVALID; }
   if (!cdf || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   const bool have_tile_stats = (mode & PFB_SCAN_TILE_STATS_VALID) != 0 && logw != nullptr;
-  mode &= ~PFB_SCAN_TILE_STATS_VALID;
+  const bool scaled = (mode & PFB_SCAN_SLICE_SCALED) != 0;
+  if (scaled && !have_tile_stats) { set_error("PFB_SCAN_SLICE_SCALED needs the slice exponents a weighting call left in the workspace (PFB_SCAN_TILE_STATS_VALID, logw)"); return PFB_ERR_INVALID; }
+  mode &= ~(PFB_SCAN_TILE_STATS_VALID | PFB_SCAN_SLICE_SCALED);
   if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
   const double* in = w ? w : logw;
   if (((uintptr_t)in & 15) || ((uintptr_t)cdf & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
   Workspace W;
   int rc = carve_workspace(ws, ws_bytes, n, &W);
   if (rc) return rc;
-  return scan_impl(mode, n, in, logw != nullptr, cdf, stats, W, 1, scan_tiles(n), have_tile_stats, (cudaStream_t)stream);
+  return scan_impl(mode, n, in, scaled ? kInScaled : (logw != nullptr ? kInLog : kInW), cdf, stats, W, 1, scan_tiles(n), have_tile_stats, (cudaStream_t)stream);
 }
 
 extern "C" int pfb_scan_cdf_batched(int32_t mode, int64_t n_runs, int64_t run_len, const double* logw_pad,
@@ -856,7 +933,8 @@ extern "C" int pfb_scan_cdf_batched(int32_t mode, int64_t n_runs, int64_t run_le
   if (n_runs <= 0 || run_len <= 0) return PFB_OK;
   if (!logw_pad || !cdf_pad || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   if (!(mode & PFB_SCAN_TILE_STATS_VALID)) { set_error("pfb_scan_cdf_batched must follow pfb_loglik_batched / pfb_predict_loglik_batched on the same buffers"); return PFB_ERR_INVALID; }
-  mode &= ~PFB_SCAN_TILE_STATS_VALID;
+  const bool scaled = (mode & PFB_SCAN_SLICE_SCALED) != 0;
+  mode &= ~(PFB_SCAN_TILE_STATS_VALID | PFB_SCAN_SLICE_SCALED);
   if (mode != PFB_SCAN_FAST && mode != PFB_SCAN_SEQEXACT) { set_error("bad scan mode %d", mode); return PFB_ERR_INVALID; }
   if (((uintptr_t)logw_pad & 15) || ((uintptr_t)cdf_pad & 15)) { set_error("scan buffers must be 16-byte aligned"); return PFB_ERR_INVALID; }
   const int64_t tpr = scan_tiles(run_len);
@@ -864,5 +942,5 @@ extern "C" int pfb_scan_cdf_batched(int32_t mode, int64_t n_runs, int64_t run_le
   Workspace W;
   int rc = carve_workspace(ws, ws_bytes, n_pad, &W);
   if (rc) return rc;
-  return scan_impl(mode, n_pad, logw_pad, true, cdf_pad, stats, W, n_runs, tpr, true, (cudaStream_t)stream);
+  return scan_impl(mode, n_pad, logw_pad, scaled ? kInScaled : kInLog, cdf_pad, stats, W, n_runs, tpr, true, (cudaStream_t)stream);
 }

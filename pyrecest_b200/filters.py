@@ -243,17 +243,17 @@ class AbstractParticleFilter:
                     # with a padded gather copy the compact predicted particles are dead (the resampling reads the
                     # copy and replaces the particle set): not stored, unless a failed weight check has to leave them
                     dead = gather is not None
-                    eng.predict_loglik(p, lp, x, None if dead else x, noise, self._logw)  # fused K(1)+K(2), in place
+                    eng.predict_loglik(p, lp, x, None if dead else x, noise, self._logw, scaled=True)  # fused K(1)+K(2), in place
                     self._predicted_only_in_pad = dead
                 except NotImplementedError:  # (mode, likelihood) pair without a fused instantiation
                     fuse = False
             if not fuse:
                 eng.predict(p, x, x, noise)
-                eng.loglik(lp, x, self._logw)
+                eng.loglik(lp, x, self._logw, scaled=True)
         else:
             gather = None
             self._flush()
-            eng.loglik(lp, x, self._logw, w_prev=st._weights_or_none())
+            eng.loglik(lp, x, self._logw, w_prev=st._weights_or_none(), scaled=True)
         self._resample_from_logw(x, keep, gather)
 
     def _est_kind(self):

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     lib = L.lib()
-    assert lib.pfb_abi_version() == L.ABI_VERSION == 5
+    assert lib.pfb_abi_version() == L.ABI_VERSION == 6
     assert lib.pfb_workspace_bytes(0) >= 256
     assert lib.pfb_workspace_bytes(10**8) > lib.pfb_workspace_bytes(0)
 
@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     from pyrecest_b200 import _lib as L
 
     assert ctypes.sizeof(L.PredictParams) == 8 * 4 + 8 * (36 + 6 + 36 + 6 + 2) + 8 + 16 + 48 + 48 + 8 + 24 + 8 + 8
-    assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8 + 8
+    assert ctypes.sizeof(L.LikParams) == 4 * 4 + 8 * (6 + 36 + 3) + 8 + 8 + 8
 
 
 def test_argument_validation_without_gpu():

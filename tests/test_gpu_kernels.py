@@ -704,3 +704,45 @@ def test_resample_small_and_odd_sizes(eng, lookup_path):
         u0 = float(rng.random())
         eng.resample(cdf, dev(np.array([u0])), x, out, n_out, 2, systematic=True, idx_out=idx)
         assert np.array_equal(host(idx), O.systematic_indices(w, u0, n_out)), n
+
+
+@pytest.mark.parametrize("n", [1, 255, 257, 5000, 300_001])
+def test_slice_scaled_weights_scan_is_the_exact_cumsum_of_its_addends(eng, n):
+    """PFB_WEIGHTS_SCALED: p_i = pdf_i 2^(-e_s) per slice of 256 particles, e_s = ceil(max_slice(l) log2 e); the scan's
+    addends are p_i 2^(e_s - E) (exact scalings) and its CDF is numpy.cumsum of those addends, bit for bit."""
+    from pyrecest_b200 import registry as R
+    from pyrecest_b200.distributions import GaussianDistribution
+
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, 2)) * np.array([3.0, 40.0])  # log-likelihoods spread over ~1000 nats
+    xd = dev(x)
+    dist = GaussianDistribution(np.array([0.3, -0.2]), np.diag([0.5, 0.8]))
+    lp, keep = R.lik_params(dist, 2, images_to_device=R.device_put(xd.device))
+    logw = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.loglik(lp, xd, logw)
+    l = host(logw)
+    p = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.loglik(lp, xd, p, scaled=True)
+    cdf = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf, logw=p, exact=True)
+    assert eng.scan_error_flags() == 0
+    ph = host(p)
+    nsl = (n + 255) // 256
+    lpad = np.full(nsl * 256, -np.inf)
+    lpad[:n] = l
+    e = np.ceil(lpad.reshape(nsl, 256).max(axis=1) * 1.4426950408889634)
+    np.testing.assert_allclose(ph, np.exp(l - np.repeat(e, 256)[:n] * 0.6931471805599453), rtol=2e-12, atol=1e-300)
+    a = ph * np.exp2(np.repeat(e, 256)[:n] - e.max())
+    assert np.array_equal(host(cdf), np.cumsum(a))
+    # the same weights as the log format, up to rounding: normalised CDFs agree
+    cdf2 = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    eng.scan(cdf2, logw=logw, exact=True)
+    np.testing.assert_allclose(host(cdf) / host(cdf)[-1], host(cdf2) / host(cdf2)[-1], rtol=1e-12, atol=1e-15)
+    with pytest.raises(Exception):  # the scaled format cannot be re-read without its slice exponents
+        eng._tile_stats_key = None
+        eng.lib  # noqa: B018
+        from pyrecest_b200 import _lib as L
+        import ctypes as C
+        L.check(eng.lib.pfb_scan_cdf(L.SCAN_SEQEXACT | L.SCAN_SLICE_SCALED, n, None, C.c_void_p(p.data_ptr()),
+                                     C.c_void_p(cdf.data_ptr()), C.c_void_p(eng.stats.data_ptr()),
+                                     C.c_void_p(eng._ws.data_ptr()), eng._ws.numel(), None))

@@ -52,8 +52,11 @@ def main():
     rep, kre, sub = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
     by = 1 if (len(sys.argv) > 5 and sys.argv[5] == "inst") else 0  # sort by instructions instead of samples
-    csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
-                            capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # a source page exported on the GPU box (ncu -i rep --page source --csv): reports > 64 MB do not travel
+        csvtxt = open(rep).read()
+    else:
+        csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
+                                capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(csvtxt)))
     # several launches may be concatenated; take the first block
     hdr_idx = [i for i, r in enumerate(rows) if r and r[0] == "Address"]

@@ -23,8 +23,11 @@ def main():
         f, lh = spec.split(":")
         lo, hi = lh.split("-")
         ranges.append((name, f, int(lo), int(hi)))
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
-                         capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
+                             capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hidx = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
     hdr = rows[hidx[0]]
