@@ -411,6 +411,11 @@ def run_gpu(args):
     value = world * n / (ms_step * 1e-3)
     e2e_value = world * n / (e2e_ms * 1e-3)
 
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del noise_ring, u_ring, x, alt, logw, cdf, pf
+        torch.cuda.empty_cache()
+        sharded = sharded_block(args, world, rank, dev, args.steps, args.warmup, n=args.sharded_particles or None)
     if rank == 0:
         peak, peak_src = peaks()
         ab = algorithmic_bytes(D, E)
@@ -447,9 +452,139 @@ def run_gpu(args):
                 "sample": f"oracle/pf_oracle.py (vectorised numpy restatement, predict + likelihood split over {cpu_threads()} host threads) "
                           f"on {cpu_n} particles x 2 steps of the same workload, {cpu_s:.2f} s/step"},
         }
+        if sharded is not None:
+            line["sharded"] = sharded
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_block(args, world, rank, dev, steps, warmup, n=None):
+    """BASELINE.json configs[4] inside an N-GPU run: ONE EuclideanParticleFilter (R^4 constant velocity) sharded over
+    all ranks, 1.25e8 particles per GPU, global systematic resampling whose offspring are stored straight into the
+    owner rank's buffer over NVLink (pyrecest_b200.sharded, device-side plan).  Two scenarios -- `even` (all shards
+    statistically alike: almost every offspring stays on its rank) and `skewed` (shard g's particles sit 1.5 g sigma
+    away from the measurement, so most offspring are produced by shard 0 and cross to the other ranks; the particle
+    set is re-installed before every timed step, untimed, because one resampling step evens the shards out) -- and
+    the 1-GPU anchor: the same filter code with a one-rank group on every GPU at once.  Returns the dict rank 0
+    prints as the line's `sharded` block."""
+    import torch
+    import torch.distributed as dist
+
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.sharded import ShardedParticleFilter
+
+    name = "r4s"
+    manifold, D, E, n_default, desc = WORKLOADS[name]
+    n = n or n_default
+    P = workload_params(name)
+    prior, trans, noise_dist, lik_dist = make_dists(name, P)
+    lik = lik_dist.set_mode(P["z"])
+    prandom.seed(4321)  # the same seed on every rank: the shards derive their own streams from it
+    u_rng = np.random.default_rng(11)
+    u0s = u_rng.random(4096)
+    solo_groups = [dist.new_group([r]) for r in range(world)]  # (every rank must create every group)
+
+    def timed(pf, k_steps, k_warm, reset=None):
+        """per-step CUDA events, every step entered through a barrier; returns mean ms per step (max over ranks)"""
+        it = [0]
+
+        def step():
+            pf.predict_nonlinear(trans, noise_dist)
+            pf.update_nonlinear_using_likelihood(lik, u0=float(u0s[it[0] % 4096]))
+            it[0] += 1
+            return pf.get_point_estimate()
+
+        for _ in range(k_warm):
+            if reset is not None:
+                reset()
+            step()
+        evs = []
+        for _ in range(k_steps):
+            if reset is not None:
+                reset()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            est = step()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        pf.check()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / k_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        assert bool(torch.isfinite(est).all())
+        return float(ms)
+
+    out = {"workload": f"{name}: {desc}", "particles_per_gpu": n, "particles_total": n * world, "resampling": "systematic (global)",
+           "scan": "sequential-exact per shard against the global shift", "plan": "device-side (no host read of the shard totals)"}
+    # ---- the sharded filter, even scenario
+    pf = ShardedParticleFilter(manifold, n * world, D)
+    pf.filter_state = prior
+    pf.time_scatter = True
+    even_ms = timed(pf, steps, warmup)
+    made, remote = pf.offspring_traffic()
+    sc_ms = pf.scatter_ms()
+    tr = torch.tensor([made, remote], dtype=torch.float64, device=dev)
+    dist.all_reduce(tr)
+    out["even"] = {"ms_per_step": even_ms, "value": world * n / (even_ms * 1e-3),
+                   "offspring_crossing_nvlink_frac": float(tr[1] / tr[0]),
+                   "peer_store_bytes_per_step": int(tr[1]) * 8 * D, "scatter_kernel_ms": sc_ms}
+    # ---- skewed scenario: shard g sits 1.5 g sigma from the measurement; re-installed before every step (untimed)
+    x_even = pf.filter_state.d.clone()
+    x_skew = x_even.clone()
+    x_skew[:, :2] += 1.5 * rank
+    del x_even
+    skew_steps = max(3, min(steps, 8))
+    skew_ms = timed(pf, skew_steps, 2, reset=lambda: pf.set_local_particles(x_skew))
+    made, remote = pf.offspring_traffic()
+    sc_ms = pf.scatter_ms()
+    tr = torch.tensor([made, remote, remote], dtype=torch.float64, device=dev)
+    mx = tr[2:].clone()
+    dist.all_reduce(tr[:2])
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    scat = torch.tensor([sc_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(scat, op=dist.ReduceOp.MAX)
+    out["skewed"] = {"ms_per_step": skew_ms, "value": world * n / (skew_ms * 1e-3),
+                     "offspring_crossing_nvlink_frac": float(tr[1] / tr[0]),
+                     "peer_store_bytes_per_step": int(tr[1]) * 8 * D,
+                     "busiest_rank_peer_store_bytes": int(mx[0]) * 8 * D, "scatter_kernel_ms": float(scat),
+                     "busiest_rank_nvlink_store_gbs": int(mx[0]) * 8 * D / (float(scat) * 1e-3) / 1e9 if float(scat) > 0 else None,
+                     "nvlink_peak_gbs_per_direction": 770.0,
+                     "note": "particle set re-installed (untimed) before every timed step; " + str(skew_steps) + " steps"}
+    # ---- time in the step's three small collectives, back to back on the stream (not overlapped with anything)
+    a = torch.zeros(1, dtype=torch.float64, device=dev)
+    g = torch.zeros(world, dtype=torch.float64, device=dev)
+    e = torch.zeros(D, dtype=torch.float64, device=dev)
+    for k in range(13):
+        if k == 3:
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        dist.all_gather_into_tensor(g, a)
+        dist.all_reduce(e)
+    t1.record()
+    torch.cuda.synchronize()
+    coll = torch.tensor([t0.elapsed_time(t1) / 10], dtype=torch.float64, device=dev)
+    dist.all_reduce(coll, op=dist.ReduceOp.MAX)
+    out["collectives_ms_per_step"] = float(coll)
+    out["collectives"] = "all_reduce(MAX, 1 double) + all_gather(1 double per rank) + all_reduce(SUM, D doubles); offspring move by peer stores inside the scatter kernel, no all_to_all"
+    del pf, x_skew
+    torch.cuda.empty_cache()
+    # ---- anchor: the same filter with a one-rank group, on every GPU at once
+    solo = ShardedParticleFilter(manifold, n, D, group=solo_groups[rank])
+    solo.filter_state = prior
+    anchor_ms = timed(solo, max(3, min(steps, 10)), warmup)
+    del solo
+    torch.cuda.empty_cache()
+    out["anchor_1gpu_ms_per_step"] = anchor_ms
+    out["even"]["efficiency"] = anchor_ms / even_ms
+    out["skewed"]["efficiency"] = anchor_ms / skew_ms
+    return out
 
 
 def run_mc(args):
@@ -637,7 +772,7 @@ def run_sharded(args):
             "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "particles_total": n * world,
                        "resampling": "systematic (global)", "scan": "sequential-exact per shard",
                        "l2_policy": f"state {n * 8 * D / 1e6:.0f} MB per GPU, far larger than L2",
-                       "parallelism": f"particles sharded over {world} GPU(s); all_reduce(max) + all_gather(totals) + all_to_all_v(offspring) per step"},
+                       "parallelism": f"particles sharded over {world} GPU(s); all_reduce(max) + all_gather(totals) per step, offspring stored into the owner rank's buffer by the scatter kernel (peer stores over NVLink), all_reduce(sum) of the estimate"},
             "e2e": {"value": world * n / (float(e2e_ms) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(e2e_ms),
                     "h2d_bytes_per_step": int(8 * D), "d2h_bytes_per_step": int(8 * D + 8 * world),
                     "path": "public API: ShardedParticleFilter.predict_nonlinear + update + get_point_estimate"},
@@ -686,6 +821,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--fast-scan", action="store_true", help="plain blocked scan instead of the sequential-exact one")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded-filter block (configs[4])")
+    ap.add_argument("--sharded-particles", type=int, default=0, help="particles per GPU of the sharded block (default 1.25e8)")
     ap.add_argument("--log-weights", action="store_true", help="value leg: log-weights between the weighting kernel and the scan "
                     "(PFB_WEIGHTS_LOG) instead of the slice-scaled linear weights")
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")

@@ -290,6 +290,18 @@ int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, const double* 
                          double total, double u0, int64_t j_begin, int64_t count, int64_t n_total_out,
                          const void* x_in, void* x_out, int64_t* idx_out, int32_t est_kind, double* est_out,
                          void* ws, int64_t ws_bytes, void* stream);
+/* The same with the plan made on the device: ONE call per rank and step.  totals_dev: DEVICE array of the `world`
+ * shard totals in rank order (an all-gather of stats[PFB_STAT_TOTAL]); the shard offsets O_g = fl(O_{g-1} + T_{g-1}) and
+ * the global total are formed from it in the kernel, so the host never reads a weight.  peer_out: HOST array of `world`
+ * pointers, peer_out[r] = the (n, dim) output buffer of rank r (its own for r == rank, peer-mapped otherwise): the
+ * offspring of global slot j is stored at row j % n of peer_out[j / n].  Every source of this shard is visited once;
+ * est_sums receives the SUMS over the offspring produced here (x, or cos / sin per dimension): all-reduce them and
+ * divide by n * world.  status[0] (DEVICE) <- 1 when the global total is not a positive finite number (nothing is
+ * written then), else 0. */
+int pfb_resample_sharded_dev(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf, const double* totals_dev,
+                             int32_t world, int32_t rank, double u0, void* const* peer_out, const void* x_in,
+                             int32_t est_kind, double* est_sums, double* status, void* ws, int64_t ws_bytes,
+                             void* stream);
 /* fill `out` (n doubles) with the uniforms pfb_resample_rng would use (tests, debugging) */
 int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream);
 

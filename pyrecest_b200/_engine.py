@@ -165,6 +165,16 @@ class Engine:
                                               _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb, _stream(self.device)))
         self.launches += 1
 
+    def resample_sharded_dev(self, cdf, totals_dev, world, rank, u0, peer_ptrs, x_in, dim, est_kind, est_sums, status):
+        """device-planned sharded scatter (pfb_resample_sharded_dev): peer_ptrs = raw device pointers of every rank's
+        output buffer"""
+        ws, wsb = self._ensure_ws(0)
+        arr = (C.c_void_p * world)(*[C.c_void_p(p) for p in peer_ptrs])
+        L.check(self.lib.pfb_resample_sharded_dev(_DT[x_in.dtype], dim, cdf.shape[0], _ptr(cdf), _ptr(totals_dev), world,
+                                                  rank, float(u0), arr, _ptr(x_in), est_kind, _ptr(est_sums),
+                                                  _ptr(status), ws, wsb, _stream(self.device)))
+        self.launches += 2
+
     def rng_uniform(self, out, seed, offset):
         L.check(self.lib.pfb_rng_uniform(out.numel(), seed, offset, _ptr(out), _stream(self.device)))
         self.launches += 1

@@ -103,6 +103,8 @@ SIGNATURES = {
     "pfb_msort_uniforms": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp, _i64, _vp]),
     "pfb_resample_sharded": (C.c_int, [C.c_int, _i32, _i64, _vp, C.c_double, C.c_double, C.c_double, _i64, _i64, _i64,
                                        _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "pfb_resample_sharded_dev": (C.c_int, [C.c_int, _i32, _i64, _vp, _vp, _i32, _i32, C.c_double, C.POINTER(C.c_void_p), _vp, _i32,
+                                           _vp, _vp, _vp, _i64, _vp]),
     "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),

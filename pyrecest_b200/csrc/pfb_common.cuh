@@ -265,6 +265,39 @@ __device__ __forceinline__ void load_rec(const T* __restrict__ base, int64_t i, 
   }
 }
 
+// the same through ordinary (coherent) loads and without a restrict promise: for kernels that may run in place
+// (x_in == x_out in the predict kernels), where ld.global.nc through a restrict pointer would be undefined behaviour
+template <typename T, int D>
+__device__ __forceinline__ void load_rec_inplace(const T* base, int64_t i, double (&r)[D]) {
+  const T* p = base + i * D;
+  if constexpr (sizeof(T) == 8 && D % 2 == 0) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) {
+      double2 v = q[c];
+      r[2 * c] = v.x;
+      r[2 * c + 1] = v.y;
+    }
+  } else if constexpr (sizeof(T) == 4 && D % 4 == 0) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      float4 v = q[c];
+      r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+  } else if constexpr (sizeof(T) == 4 && D % 2 == 0) {
+    const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) {
+      float2 v = q[c];
+      r[2 * c] = v.x; r[2 * c + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) r[c] = (double)p[c];
+  }
+}
+
 template <typename T, int D>
 __device__ __forceinline__ void store_rec(T* __restrict__ base, int64_t i, const double (&r)[D]) {
   T* p = base + i * D;

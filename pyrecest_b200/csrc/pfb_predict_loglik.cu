@@ -82,10 +82,10 @@ __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T*
 }
 
 template <typename T, int D, int MODE, bool RNG>
-__device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T* __restrict__ x_in,
+__device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T* x_in,
                                             const T* __restrict__ noise, int64_t i, double (&out)[D]) {
   double x[D], y[D];
-  load_rec<T, D>(x_in, i, x);
+  load_rec_inplace<T, D>(x_in, i, x);  // (x_in may be x_out: every thread reads its own record before it writes it)
   apply_transition<D>(p, x, y);
   const bool has_noise = (noise != nullptr || RNG) && p.noise_cols > 0;
   if constexpr (MODE == PFB_PRED_EUCLID) {
@@ -384,7 +384,7 @@ __device__ __forceinline__ void store_padded(const pfb_predict_params& p, int64_
 
 template <typename T, int D, int MODE, bool RNG>
 __global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p, int64_t n,
-                                                           const T* __restrict__ x_in, T* x_out,
+                                                           const T* x_in, T* x_out,
                                                            const T* __restrict__ noise) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
 template <typename T, int D, int MODE, int KIND, bool RNG, bool SCALED>
 __global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 5) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
-                                                                  const T* __restrict__ x_in, T* x_out,
+                                                                  const T* x_in, T* x_out,
                                                                   const T* __restrict__ noise,
                                                                   double* logw,
                                                                   double* stats, Workspace ws) {

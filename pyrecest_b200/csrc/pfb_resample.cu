@@ -999,6 +999,175 @@ __global__ void __launch_bounds__(kThreads) systematic_fill_kernel(const T* __re
   if (block_is_last(ws.counters + 7) && threadIdx.x == 0) ws.counters[6] = 0u;  // self-cleaning
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sharded filter, device-side plan: ONE launch per rank and step produces every offspring of the rank's own sources
+// and stores each one straight into the buffer of the rank that owns its output slot (peer pointers over NVLink, or
+// the rank's own buffer).  Nothing is read back to the host: the shard offsets O_g = fl(O_{g-1} + T_{g-1}) and the
+// global total come from the all-gathered totals on the device, the comb offset u0 from a generator all ranks share.
+// Global slot j lives on rank j / n_loc at row j % n_loc.  est_sums receives the SUMS over the offspring produced
+// here (an all-reduce over the ranks makes the global estimate); status[0] <- 1 if the global total is not a positive
+// finite number (nothing is written then).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxShards = 16;
+struct PeerTable {
+  void* out[kMaxShards];
+};
+struct ShardGeom {
+  double offset, total;
+};
+__device__ __forceinline__ ShardGeom shard_geometry(const double* __restrict__ totals, int world, int rank) {
+  ShardGeom g{0.0, 0.0};
+  double o = 0.0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) g.offset = o;
+    o = __dadd_rn(o, totals[r]);
+  }
+  g.total = o;
+  return g;
+}
+template <typename T, int D>
+__device__ __forceinline__ void store_slot(const PeerTable& peers, int64_t n_loc, int64_t slot, const double (&r)[D]) {
+  int64_t rk = (int64_t)((double)slot / (double)n_loc);
+  int64_t row = slot - rk * n_loc;
+  if (row < 0) { --rk; row += n_loc; }
+  else if (row >= n_loc) { ++rk; row -= n_loc; }
+  store_rec<T, D>(static_cast<T*>(peers.out[rk]), row, r);
+}
+
+template <typename T, int D, int EST>
+__global__ void __launch_bounds__(kThreads) sharded_scatter_kernel(int64_t n, const double* __restrict__ cdf,
+                                                                   const double* __restrict__ totals, int world, int rank,
+                                                                   double u0, PeerTable peers, const T* __restrict__ x_in,
+                                                                   double* est_sums, double* status, Workspace ws,
+                                                                   int64_t big_cnt) {
+  constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
+  __shared__ double red[NE * 32];
+  const ShardGeom geo = shard_geometry(totals, world, rank);
+  const bool bad = !(geo.total > 0.0) || !(geo.total < INFINITY);
+  if (bad) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = 1.0;
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = 0.0;
+  const int64_t n_comb = n * world;
+  const double dn = (double)n_comb;
+  const double total = geo.total, cdf_offset = geo.offset;
+  // this shard's offspring are the slots [J(O_g / total), J(O_{g+1} / total)) -- implied by the per-source counts below,
+  // the first source starts where the previous shard's last source ended
+  const int lane = threadIdx.x & 31;
+  double acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+  const int64_t nround = (n + 31) & ~(int64_t)31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool last_shard = rank == world - 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    int64_t e = 0;  // first slot that no longer belongs to source i
+    if (i < n) {
+      if (i == n - 1 && last_shard) e = n_comb;
+      else e = comb_count_below(__ddiv_rn(__dadd_rn(cdf_offset, __ldg(cdf + i)), total), u0, dn, n_comb);
+    }
+    int64_t sbeg = __shfl_up_sync(0xffffffffu, e, 1);
+    if (lane == 0 && i < n) {
+      const double cprev = (i == 0) ? cdf_offset : __dadd_rn(cdf_offset, __ldg(cdf + i - 1));
+      sbeg = (i == 0 && rank == 0) ? 0 : comb_count_below(__ddiv_rn(cprev, total), u0, dn, n_comb);
+    }
+    const int64_t cnt = (i < n) ? e - sbeg : 0;
+    double r[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) r[c] = 0.0;
+    if (cnt > 0) {
+      load_rec<T, D>(x_in, i, r);
+      if constexpr (EST == PFB_EST_SUM) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = fma((double)cnt, r[c], acc[c]);
+      } else if constexpr (EST == PFB_EST_TRIG) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double sn, cs;
+          sincospi(r[c] * 0.3183098861837907, &sn, &cs);
+          acc[2 * c] = fma((double)cnt, cs, acc[2 * c]);
+          acc[2 * c + 1] = fma((double)cnt, sn, acc[2 * c + 1]);
+        }
+      }
+    }
+    if (cnt > 0 && cnt <= 2) {
+      for (int64_t t = 0; t < cnt; ++t) store_slot<T, D>(peers, n, sbeg + t, r);
+    }
+    if (cnt > big_cnt) {
+      const unsigned int slot = atomicAdd(ws.counters + 6, 1u);
+      if (slot < (unsigned int)kWsJobCap) { ws.jobs[3 * slot] = i; ws.jobs[3 * slot + 1] = sbeg; ws.jobs[3 * slot + 2] = cnt; }
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, cnt > 2 && cnt <= big_cnt);
+    while (longmask) {
+      const int src = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int64_t s0 = __shfl_sync(0xffffffffu, sbeg, src);
+      const int64_t c0 = __shfl_sync(0xffffffffu, cnt, src);
+      double rb[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) rb[c] = __shfl_sync(0xffffffffu, r[c], src);
+      for (int64_t t = lane; t < c0; t += 32) store_slot<T, D>(peers, n, s0 + t, rb);
+    }
+  }
+  if constexpr (EST != PFB_EST_NONE) {
+    block_sum<NE>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
+    }
+    if (block_is_last(ws.counters)) {
+      double t[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) t[k] = 0.0;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)b * kPartialDoubles + k];
+      }
+      block_sum<NE>(t, red);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) est_sums[k] = t[k];
+      }
+    }
+  }
+}
+
+// heavy particles of the sharded scatter: every queued run of offspring is written by the whole grid
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) sharded_fill_kernel(int64_t n, const T* __restrict__ x_in, PeerTable peers,
+                                                                Workspace ws) {
+  const unsigned int nj_raw = *reinterpret_cast<volatile unsigned int*>(ws.counters + 6);
+  const unsigned int nj = nj_raw < (unsigned int)kWsJobCap ? nj_raw : (unsigned int)kWsJobCap;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (unsigned int j = 0; j < nj; ++j) {
+    const int64_t src = ws.jobs[3 * j], s0 = ws.jobs[3 * j + 1], cnt = ws.jobs[3 * j + 2];
+    double r[D];
+    load_rec<T, D>(x_in, src, r);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += stride) store_slot<T, D>(peers, n, s0 + t, r);
+  }
+  if (block_is_last(ws.counters + 7) && threadIdx.x == 0) ws.counters[6] = 0u;  // self-cleaning
+}
+
+template <typename T, int D>
+static int launch_sharded_dev(int64_t n, const double* cdf, const double* totals, int world, int rank, double u0,
+                              const PeerTable& peers, const void* x_in, int est_kind, double* est_sums, double* status,
+                              Workspace W, cudaStream_t st) {
+  const int grid = stream_grid(n);
+  int64_t big_cnt = (n * world) >> 13;
+  if (big_cnt < 8192) big_cnt = 8192;
+#define PFB_SH_LAUNCH(E) sharded_scatter_kernel<T, D, E><<<grid, kThreads, 0, st>>>(n, cdf, totals, world, rank, u0, peers, (const T*)x_in, est_sums, status, W, big_cnt)
+  switch (est_kind) {
+    case PFB_EST_NONE: PFB_SH_LAUNCH(PFB_EST_NONE); break;
+    case PFB_EST_SUM: PFB_SH_LAUNCH(PFB_EST_SUM); break;
+    case PFB_EST_TRIG: PFB_SH_LAUNCH(PFB_EST_TRIG); break;
+    default: set_error("bad est_kind %d", est_kind); return PFB_ERR_INVALID;
+  }
+#undef PFB_SH_LAUNCH
+  sharded_fill_kernel<T, D><<<sm_count() * 4, kThreads, 0, st>>>(n, (const T*)x_in, peers, W);
+  return PFB_OK;
+}
+
 template <typename T, int D>
 static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, double total_imm, double u0_imm,
                              const double* u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count,
@@ -1300,6 +1469,31 @@ extern "C" int pfb_resample_sharded(pfb_dtype dtype, int32_t dim, int64_t n, con
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_systematic<T, D>(n, cdf, cdf_offset, total, u0, nullptr, RngKey{0, 0}, 0, j_begin, count, n_total_out, x_in, x_out, idx_out, est_kind, est_out, W, st))));
   if (rc) return rc;
   PFB_LAUNCH_OK("systematic_scatter_kernel");
+  return PFB_OK;
+}
+
+extern "C" int pfb_resample_sharded_dev(pfb_dtype dtype, int32_t dim, int64_t n, const double* cdf,
+                                        const double* totals_dev, int32_t world, int32_t rank, double u0,
+                                        void* const* peer_out, const void* x_in, int32_t est_kind, double* est_sums,
+                                        double* status, void* ws, int64_t ws_bytes, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if (!cdf || !totals_dev || !peer_out || !x_in || !status) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  if (world < 1 || world > kMaxShards || rank < 0 || rank >= world) { set_error("world %d / rank %d: 1..%d shards", world, rank, kMaxShards); return PFB_ERR_INVALID; }
+  if (est_kind != PFB_EST_NONE && !est_sums) { set_error("estimate requested without output"); return PFB_ERR_INVALID; }
+  if (n * (int64_t)world >= ((int64_t)1 << 40)) { set_error("comb too long"); return PFB_ERR_UNSUPPORTED; }
+  PeerTable peers{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_out[r]) { set_error("peer_out[%d] is NULL", r); return PFB_ERR_INVALID; }
+    if (peer_out[r] == x_in) { set_error("resampling cannot run in place"); return PFB_ERR_INVALID; }
+    peers.out[r] = peer_out[r];
+  }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_sharded_dev<T, D>(n, cdf, totals_dev, world, rank, u0, peers, x_in, est_kind, est_sums, status, W, st))));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("sharded_scatter_kernel");
   return PFB_OK;
 }
 

@@ -390,12 +390,18 @@ class AbstractDiracDistribution:
     # ---- storage ------------------------------------------------------------------------------
     @property
     def d(self):
+        """The live particle array.  A filter that owns this distribution predicts in place and ping-pongs two buffers
+        when it resamples, so a tensor taken from here is valid until the filter's next predict / update: clone() it to
+        keep it (the reference returns fresh arrays; copying 2.4 GB per access would not be a drop-in either)."""
         return self._d
 
     @d.setter
     def d(self, value):
-        self._d = _as_device_tensor(value, dtype=self._d.dtype if isinstance(value, torch.Tensor) is False else None,
-                                    device=self._d.device)
+        t = _as_device_tensor(value, dtype=self._d.dtype if isinstance(value, torch.Tensor) is False else None,
+                              device=self._d.device)
+        if isinstance(value, torch.Tensor) and t.data_ptr() == value.data_ptr():
+            t = t.clone()  # never alias a caller-owned tensor: the filter mutates its particle buffers in place
+        self._d = t
         self._est_cache = None
 
     @property

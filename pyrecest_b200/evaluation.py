@@ -101,6 +101,9 @@ class BatchedParticleFilter:
         else:
             lp, keep = R.lik_params(dist0, self.D, images_to_device=R.device_put(self.device))
         mu_dev = torch.as_tensor(z, dtype=torch.float64, device=self.device).contiguous()
+        if R.kind_of(dist0) in ("wn_multi", "wn_1d", "vm"):
+            # equivalent on the torus, and required: the pruned image table is built for centres in [0, 2 pi)^d
+            mu_dev = torch.remainder(mu_dev, 2.0 * np.pi)
         lp.mu_batch_dev = mu_dev.data_ptr()
         eng = self.eng
         if flat._pending is not None:

@@ -30,6 +30,20 @@ class DeviceDraws:
         self._offset += 1
         return self._offset
 
+    def derive(self, k):
+        """child source number k (e.g. the rank of a shard): an independent stream that is still a function of this
+        source's seed, so that SPMD code calling seed(s) with the same s on every rank stays reproducible without the
+        shards drawing identical noise"""
+        if not hasattr(self, "_children"):
+            self._children = {}
+        if k not in self._children:
+            z = (self.seed + 0x9E3779B97F4A7C15 * (int(k) + 1)) & (2**64 - 1)  # splitmix64 finaliser
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+            child = DeviceDraws(seed=(z ^ (z >> 31)) & (2**63 - 1))
+            self._children[k] = child
+        return self._children[k]
+
     def _gen(self, device):
         key = str(device)
         if key not in self._gens:
@@ -120,6 +134,18 @@ def seed(s):
     """Seed the device draw source (the analogue of pyrecest.backend.random.seed)."""
     global _SOURCE
     _SOURCE = DeviceDraws(seed=s)
+
+
+@contextlib.contextmanager
+def using(src):
+    """temporarily make `src` the draw source"""
+    global _SOURCE
+    saved = _SOURCE
+    _SOURCE = src
+    try:
+        yield src
+    finally:
+        _SOURCE = saved
 
 
 @contextlib.contextmanager

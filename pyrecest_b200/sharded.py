@@ -228,6 +228,11 @@ class ShardedParticleFilter:
         self._u0_rng = None
         self._sym = None        # [(tensor, handle)] x 2: the two particle buffers in symmetric memory (peer stores)
         self.peer_stores = True  # write remote offspring straight into the peer's buffer when symmetric memory works
+        # device-side plan (pfb_resample_sharded_dev): one kernel per step, no host read of the shard totals; the
+        # status of a step (global weight sum positive and finite) is checked when the NEXT step starts, or on check()
+        self.device_plan = True
+        self._dp = None          # persistent small device / pinned tensors of the device-planned path
+        self._pending_check = None
 
     def _symmetric_buffers(self, x):
         """Both particle buffers of the ping-pong in torch symmetric memory, so that every rank holds peer pointers
@@ -253,6 +258,7 @@ class ShardedParticleFilter:
                 self.peer_stores = False
                 return x, None
         (a, ha), (b, hb) = self._sym
+        self._sym_handles = {a.data_ptr(): ha, b.data_ptr(): hb}
         if x.data_ptr() == a.data_ptr():
             cur, nxt, hn = a, b, hb
         elif x.data_ptr() == b.data_ptr():
@@ -272,14 +278,26 @@ class ShardedParticleFilter:
         """the LOCAL shard as a Dirac distribution (weights 1/n_loc locally = 1/N globally after resampling)"""
         return self.local.filter_state
 
+    def _rank_source(self):
+        """the draw source of this shard: the global one when draws are injected, else its child number `rank` -- the
+        in-kernel Philox draws are keyed by (seed, call, LOCAL particle index), so shards sharing a seed would draw
+        identical noise"""
+        from . import random as prandom
+
+        src = prandom.source()
+        return src.derive(self.rank) if isinstance(src, prandom.DeviceDraws) else src
+
     @filter_state.setter
     def filter_state(self, prior):
+        from . import random as prandom
+
         self._est_sums = None
-        self.local.filter_state = prior  # every shard samples its own n_loc particles (seed differs per rank)
+        with prandom.using(self._rank_source()):
+            self.local.filter_state = prior  # every shard samples its own n_loc particles from its own stream
 
     def set_local_particles(self, x):
         self._est_sums = None
-        self.local.filter_state.d = x
+        self.local.filter_state.d = x  # (the setter clones a caller-owned device tensor: the filter mutates its buffers)
 
     def gather_particles(self):
         x = self.local.filter_state._records()
@@ -289,12 +307,16 @@ class ShardedParticleFilter:
 
     # -- predict / update ----------------------------------------------------------------------------------
     def predict_identity(self, noise_distribution):
-        self._est_sums = None
-        self.local.predict_identity(noise_distribution)
+        from .registry import IdentityTransition
+
+        self.predict_nonlinear(IdentityTransition(), noise_distribution)
 
     def predict_nonlinear(self, f, noise_distribution=None, function_is_vectorized=True, shift_instead_of_add=None):
+        from . import random as prandom
+
         self._est_sums = None
-        self.local.predict_nonlinear(f, noise_distribution, function_is_vectorized, shift_instead_of_add)
+        with prandom.using(self._rank_source()):
+            self.local.predict_nonlinear(f, noise_distribution, function_is_vectorized, shift_instead_of_add)
 
     def update_identity(self, meas_noise, measurement, shift_instead_of_add=True):
         from . import registry as R
@@ -343,6 +365,14 @@ class ShardedParticleFilter:
                 t = src.uniforms((1,), x.device)
                 dist.broadcast(t, src=0, group=self.group)
                 u0 = float(t.cpu())
+        self._last_u0 = u0
+        if self.device_plan and x.device.type == "cuda" and (peer_out is not None or self.world == 1):
+            self._update_device_plan(x, peer_out, local_max, u0)
+            loc._alt = x  # ping-pong
+            st._d = self._new.reshape(st._d.shape)
+            st._uniform = True
+            st._est_cache = None
+            return
         new, plan = sharded_systematic_resample(self.backend, x, loc._logw, local_max, u0, self.group, out=loc._alt,
                                                 est_kind="trig" if self.manifold == "torus" else "sum",
                                                 peer_out=peer_out)
@@ -352,6 +382,93 @@ class ShardedParticleFilter:
         st._d = new.reshape(st._d.shape)
         st._uniform = True
         st._est_cache = None
+
+    def _update_device_plan(self, x, peer_out, local_max, u0):
+        """scan against the global shift, all-gather the shard totals, ONE scatter kernel that stores every offspring
+        into the rank that owns its slot, all-reduce of the estimate sums (which is also the barrier before anyone
+        reads the new particles).  The host reads nothing; a failed weight check surfaces at the next step / check()."""
+        from . import _lib as L
+
+        loc = self.local
+        eng = loc._eng()
+        n_loc, D = x.shape
+        dev = x.device
+        if self._dp is None:
+            self._dp = {
+                "totals": torch.zeros(self.world, dtype=torch.float64, device=dev),
+                "est": torch.zeros(2 * L.PFB_MAXD, dtype=torch.float64, device=dev),
+                "status": torch.zeros(1, dtype=torch.float64, device=dev),
+                "host": torch.zeros(self.world + 1, dtype=torch.float64).pin_memory(),
+                "peers": {},
+            }
+        dp = self._dp
+        self.check()  # the previous step's status, copied to the host a step ago
+        if self.world > 1:
+            dist.all_reduce(local_max, op=dist.ReduceOp.MAX, group=self.group)
+        cdf, total = self.backend.scan(loc._logw, local_max)
+        if self.world > 1:
+            dist.all_gather_into_tensor(dp["totals"], total, group=self.group)
+        else:
+            dp["totals"].copy_(total)
+        out = loc._alt
+        key = out.data_ptr()
+        if key not in dp["peers"]:
+            if self.world == 1:
+                dp["peers"][key] = [out.data_ptr()]
+            else:
+                h = self._sym_handles[key]
+                dp["peers"][key] = [out.data_ptr() if r == self.rank else h.get_buffer(r, tuple(x.shape), x.dtype).data_ptr()
+                                    for r in range(self.world)]
+        trig = self.manifold == "torus"
+        dp["est"].zero_()
+        timing = getattr(self, "time_scatter", False)
+        if timing:
+            self._scatter_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._scatter_ev[0].record()
+        eng.resample_sharded_dev(cdf, dp["totals"], self.world, self.rank, u0, dp["peers"][key], x, D,
+                                 L.EST_TRIG if trig else L.EST_SUM, dp["est"], dp["status"])
+        if timing:
+            self._scatter_ev[1].record()
+        ne = 2 * D if trig else D
+        sums = dp["est"][:ne].clone()
+        if self.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)  # (also the barrier of the peer stores)
+        self._est_sums = sums
+        self._new = out
+        self.last_plan = None
+        self.last_totals = dp["totals"]
+        # status + totals to pinned host memory, without waiting for them
+        dp["host"][:1].copy_(dp["status"], non_blocking=True)
+        dp["host"][1:].copy_(dp["totals"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._pending_check = ev
+
+    def check(self):
+        """raise the reference's AssertionError if the last device-planned update saw a non-positive / non-finite global
+        weight sum (abstract_dirac_distribution.py:73-75); waits for that step's status copy only"""
+        ev = self._pending_check
+        if ev is None:
+            return
+        self._pending_check = None
+        ev.synchronize()
+        if float(self._dp["host"][0]) != 0.0:
+            raise AssertionError("The sum of all weights should be greater than 0.")
+
+    def scatter_ms(self):
+        """device time of the last scatter kernel pair (time_scatter = True); synchronises"""
+        a, b = self._scatter_ev
+        b.synchronize()
+        return a.elapsed_time(b)
+
+    def offspring_traffic(self):
+        """(offspring produced here, of which stored on other ranks) of the last device-planned update, from the totals
+        it left on the device -- a host-side restatement of the plan for reporting, not on the step's path"""
+        tot = [float(t) for t in self.last_totals.cpu()]
+        offs = shard_offsets(tot)
+        B = offspring_boundaries(offs, self._last_u0, self.n_total)
+        send, _ = exchange_plan(B, self.rank, self.world, self.n_loc)
+        return sum(send), sum(send) - send[self.rank]
 
     # -- estimate ------------------------------------------------------------------------------------------
     def get_point_estimate(self):

@@ -64,7 +64,8 @@ def main():
         if rank == 0:
             close = np.isclose(got, want, rtol=1e-12, atol=1e-13).all(axis=1)
             print(f"step {t}: particles differing from the sharded oracle: {(~close).sum()} of {N}; "
-                  f"estimate err {np.abs(est - want.mean(axis=0)).max():.2e}; plan {pf.last_plan['send']}")
+                  f"estimate err {np.abs(est - want.mean(axis=0)).max():.2e}; "
+                  f"(offspring produced here, stored on other ranks) {pf.offspring_traffic()}")
             ok &= (~close).sum() <= 4 and np.allclose(est, want.mean(axis=0), rtol=1e-9, atol=1e-12)
         ref = got
     if rank == 0:

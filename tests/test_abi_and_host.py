@@ -250,3 +250,16 @@ def test_reference_arm_line_has_the_contract_keys():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
+
+
+def test_derived_draw_sources_differ_per_shard_and_are_reproducible():
+    """shards seeded alike must not draw identical noise; the per-rank child stream is a pure function of
+    (seed, rank)."""
+    from pyrecest_b200 import random as prandom
+
+    a = prandom.DeviceDraws(seed=7)
+    b = prandom.DeviceDraws(seed=7)
+    assert a.derive(0).seed == b.derive(0).seed and a.derive(3).seed == b.derive(3).seed
+    seeds = {a.derive(r).seed for r in range(8)} | {a.seed}
+    assert len(seeds) == 9
+    assert a.derive(2) is a.derive(2)  # one child per rank: its call counter keeps advancing

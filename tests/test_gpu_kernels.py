@@ -746,3 +746,45 @@ def test_slice_scaled_weights_scan_is_the_exact_cumsum_of_its_addends(eng, n):
         L.check(eng.lib.pfb_scan_cdf(L.SCAN_SEQEXACT | L.SCAN_SLICE_SCALED, n, None, C.c_void_p(p.data_ptr()),
                                      C.c_void_p(cdf.data_ptr()), C.c_void_p(eng.stats.data_ptr()),
                                      C.c_void_p(eng._ws.data_ptr()), eng._ws.numel(), None))
+
+
+@pytest.mark.parametrize("world,skew,heavy", [(1, 0.0, False), (2, 0.0, False), (4, 6.0, False), (3, 0.0, True), (8, 3.0, False)])
+def test_sharded_device_plan_kernel_equals_sharded_oracle(eng, world, skew, heavy):
+    """pfb_resample_sharded_dev (one launch per rank, plan made on the device from the all-gathered totals): the G
+    ranks are emulated on one GPU by G launches that store into G output buffers through the peer table."""
+    from pyrecest_b200 import _lib as L
+
+    rng = np.random.default_rng(world * 7 + int(skew))
+    n_loc, D = 20_011, 4
+    N = n_loc * world
+    x = rng.standard_normal((N, D))
+    logw = -0.5 * np.sum((x - 0.3) ** 2, axis=1) - skew * (np.arange(N) // n_loc)
+    if heavy:
+        logw[n_loc + 5] += 40.0  # one particle of shard 1 takes nearly everything: offspring cross into every rank
+    M = logw.max()
+    u0 = 0.6180339887
+    shards = [np.exp(logw[g * n_loc:(g + 1) * n_loc] - M) for g in range(world)]
+    idx = O.sharded_systematic_indices(shards, u0)
+    cdfs, totals = [], []
+    for g in range(world):
+        c = torch.empty(n_loc, dtype=torch.float64, device="cuda:0")
+        eng.scan(c, w=dev(shards[g]), exact=True)
+        cdfs.append(c)
+        totals.append(float(np.cumsum(shards[g])[-1]))
+    totals_dev = dev(np.array(totals))
+    outs = [torch.full((n_loc, D), np.nan, dtype=torch.float64, device="cuda:0") for _ in range(world)]
+    ptrs = [o.data_ptr() for o in outs]
+    est = torch.zeros((world, 2 * L.PFB_MAXD), dtype=torch.float64, device="cuda:0")
+    status = torch.ones(1, dtype=torch.float64, device="cuda:0")
+    for g in range(world):
+        eng.resample_sharded_dev(cdfs[g], totals_dev, world, g, u0, ptrs, dev(x[g * n_loc:(g + 1) * n_loc]), D, L.EST_SUM,
+                                 est[g], status)
+    got = np.concatenate([host(o) for o in outs])
+    assert float(status) == 0.0
+    assert not np.isnan(got).any()  # every slot written exactly by its owner shard
+    assert np.array_equal(got, x[idx])
+    np.testing.assert_allclose(host(est)[:, :D].sum(axis=0), x[idx].sum(axis=0), rtol=1e-11, atol=1e-9)
+    # a zero total is reported through the status word and nothing is written
+    bad = torch.zeros(world, dtype=torch.float64, device="cuda:0")
+    eng.resample_sharded_dev(cdfs[0], bad, world, 0, u0, ptrs, dev(x[:n_loc]), D, L.EST_SUM, est[0], status)
+    assert float(status) == 1.0
