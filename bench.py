@@ -826,7 +826,7 @@ def main():
     ap.add_argument("--log-weights", action="store_true", help="value leg: log-weights between the weighting kernel and the scan "
                     "(PFB_WEIGHTS_LOG) instead of the slice-scaled linear weights")
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
-    ap.add_argument("--resampling", default="multinomial", choices=["multinomial", "multinomial_sorted", "systematic"])
+    ap.add_argument("--resampling", default="multinomial_sorted", choices=["multinomial", "multinomial_sorted", "systematic"])
     args = ap.parse_args()
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         args.no_cpu = True  # the CPU baseline is reported at N = 1 only

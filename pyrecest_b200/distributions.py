@@ -349,13 +349,26 @@ class HypertoroidalUniformDistribution:
         return torch.full((xs_t.reshape(-1, self.dim).shape[0],), 1.0 / TWO_PI**self.dim, dtype=torch.float64, device=xs_t.device)
 
 
+class CircularUniformDistribution(HypertoroidalUniformDistribution):
+    """circle/circular_uniform_distribution.py: the uniform density 1 / (2 pi) on the circle."""
+
+    def __init__(self):
+        HypertoroidalUniformDistribution.__init__(self, 1)
+
+
 class HypersphericalUniformDistribution:
-    """hypersphere_subset/hyperspherical_uniform_distribution.py:36-53 (prior sampling only):
-    normalised standard normals."""
+    """hypersphere_subset/hyperspherical_uniform_distribution.py:36-53: normalised standard normals;
+    pdf = 1 / surface area."""
 
     def __init__(self, dim):
         self.dim = dim
         self.input_dim = dim + 1
+
+    def pdf(self, xs):
+        xs_t = _as_device_tensor(xs)
+        D = self.dim + 1
+        area = 2.0 * math.pi ** (0.5 * D) / math.gamma(0.5 * D)
+        return torch.full((xs_t.reshape(-1, D).shape[0],), 1.0 / area, dtype=torch.float64, device=xs_t.device)
 
     def sample(self, n):
         dev = _default_device()

@@ -330,10 +330,24 @@ class AbstractParticleFilter:
         dist = R.as_distribution(likelihood)
         x = st._records()
         lp, keep = R.lik_params(dist, x.shape[1], images_to_device=R.device_put(x.device))
-        logw = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
-        self._eng().loglik(lp, x, logw)
+        # log(w_i pdf_i) from the weighting kernel, then the log-sum-exp reduction of pfb_normalize:
+        # sum_i w_i pdf_i = exp(max) * sum exp(l_i - max); no N-sized torch temporaries, nothing on the host
+        eng = self._eng()
+        N = x.shape[0]
+        if self._logw is None or self._logw.shape[0] != N or self._logw.device != x.device:
+            logw = torch.empty(N, dtype=torch.float64, device=x.device)
+        else:
+            logw = self._logw
+        stats = torch.empty(L.STAT_COUNT, dtype=torch.float64, device=x.device)
+        w_prev = st._weights_or_none()
+        eng.loglik(lp, x, logw, w_prev=w_prev, stats=stats)
+        eng.normalize(logw, stats=stats)
         del keep
-        return torch.sum(torch.exp(logw) * st.w)
+        out = torch.exp(stats[L.STAT_MAX]) * stats[L.STAT_SUMEXP]
+        out = torch.where(stats[L.STAT_MAX] == -math.inf, torch.zeros_like(out), out)  # pdf = 0 at every particle
+        if w_prev is None:
+            out = out / N  # uniform weights 1/N are not materialised
+        return out
 
     # ---- estimate ----------------------------------------------------------------------------------
     def get_point_estimate(self):

@@ -97,6 +97,11 @@ _KIND_BY_NAME = {
     "VMDistribution": "vm",
     "VonMisesFisherDistribution": "vmf",
     "VMFDistribution": "vmf",
+    # uniform densities (constant likelihood; association_likelihood of the reference's tests uses one)
+    "CircularUniformDistribution": "uniform",
+    "HypertoroidalUniformDistribution": "uniform",
+    "HypersphericalUniformDistribution": "uniform",
+    "HyperhemisphericalUniformDistribution": "uniform",
 }
 
 
@@ -373,6 +378,19 @@ def lik_params(dist, dim, images_to_device=None):
         p.mu[:dim] = mu.tolist()
         p.kappa = kappa
         p.logc = vmf_log_norm_const(kappa, dim)
+    elif k == "uniform":
+        # a constant density: the von Mises / von Mises-Fisher kernels with kappa = 0 evaluate exactly log c
+        name = type(dist).__name__
+        if "spher" in name:
+            # surface area of S^(dim-1) embedded in R^dim: 2 pi^(dim/2) / Gamma(dim/2)  (half of it for a hemisphere)
+            log_area = math.log(2.0) + 0.5 * dim * math.log(math.pi) - math.lgamma(0.5 * dim)
+            if "hemi" in name:
+                log_area -= math.log(2.0)
+            p.logc = -log_area
+        else:
+            p.logc = -dim * math.log(TWO_PI)
+        p.kind = L.LIK_VM if dim == 1 else L.LIK_VMF
+        p.kappa = 0.0
     else:
         raise NotImplementedError(f"{type(dist).__name__} is not a registry likelihood")
     return p, keep

@@ -439,3 +439,45 @@ def test_failed_update_leaves_predicted_particles_with_padded_gather():
         states.append(pf.filter_state.d.cpu().numpy().copy())
     assert np.isfinite(states[0]).all()
     assert np.array_equal(states[0], states[1])
+
+
+def test_association_likelihood_reference_known_answers():
+    """pyrecest/tests/filters/test_circular_particle_filter.py:115-130: sum_i w_i pdf(d_i) with a uniform likelihood is
+    1 / (2 pi) to 1e-10, and a von Mises likelihood centred on the particles gives more; computed by the weighting
+    kernel + the log-sum-exp reduction (no host arithmetic), also for non-uniform weights and on S^2."""
+    from pyrecest_b200.distributions import (
+        CircularDiracDistribution,
+        CircularUniformDistribution,
+        HypersphericalDiracDistribution,
+        HypersphericalUniformDistribution,
+        VonMisesDistribution,
+        VonMisesFisherDistribution,
+    )
+    from pyrecest_b200.filters import CircularParticleFilter, HypersphericalParticleFilter
+
+    dist = CircularDiracDistribution(np.array([1.0, 2.0, 3.0]), np.array([1 / 3, 1 / 3, 1 / 3]))
+    pf = CircularParticleFilter(3)
+    pf.filter_state = dist
+    assert abs(float(pf.association_likelihood(CircularUniformDistribution())) - 1.0 / (2.0 * math.pi)) < 1e-10
+    assert float(pf.association_likelihood(VonMisesDistribution(np.array(2.0), np.array(1.0)))) > 1.0 / (2.0 * math.pi)
+    assert float(pf.compute_association_likelihood(CircularUniformDistribution())) == float(
+        pf.association_likelihood(CircularUniformDistribution()))
+    # weighted particles against the oracle's restatement: sum w_i pdf(x_i)
+    rng = np.random.default_rng(5)
+    d = rng.random(5000) * 2 * np.pi
+    w = rng.random(5000)
+    w /= w.sum()
+    pf = CircularParticleFilter(5000)
+    pf.filter_state = CircularDiracDistribution(d, w)
+    vm = VonMisesDistribution(np.array(2.0), np.array(1.5))
+    ref = float(np.sum(w * O.likelihood("vm", d, {"mu": 2.0, "kappa": 1.5})))
+    np.testing.assert_allclose(float(pf.association_likelihood(vm)), ref, rtol=1e-12)
+    # sphere: uniform likelihood = 1 / (4 pi); VMF against the oracle
+    x = rng.standard_normal((4000, 3))
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    sp = HypersphericalParticleFilter(4000, 2)
+    sp.filter_state = HypersphericalDiracDistribution(x)
+    np.testing.assert_allclose(float(sp.association_likelihood(HypersphericalUniformDistribution(2))), 1 / (4 * math.pi), rtol=1e-12)
+    mu = np.array([0.0, 0.6, 0.8])
+    ref = float(np.mean(O.likelihood("vmf", x, {"mu": mu, "kappa": 3.0})))
+    np.testing.assert_allclose(float(sp.association_likelihood(VonMisesFisherDistribution(mu, 3.0))), ref, rtol=1e-12)
