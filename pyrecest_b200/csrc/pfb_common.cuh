@@ -102,16 +102,14 @@ static __device__ __noinline__ double np_mod_2pi_slow(double a) {
 static __constant__ double kAngleConst[4] = {6.283185307179586476925286766559, 12.566370614359172953850573533118,
                                              -6.283185307179586476925286766559, 3.141592653589793};
 __device__ __forceinline__ double np_mod_2pi(double a) {
-  // fast exact paths for |a| < 4 pi (every in-range particle +- noise lands here):
-  //   [0, 2pi): fmod = a.   [2pi, 4pi): fmod = a - 2pi, exact by Sterbenz.   (-2pi, 0): fmod = a, then += 2pi.
-  const double twopi = kAngleConst[0];
-  if (a >= 0.0) {
-    if (a < twopi) return a + 0.0;          // -0.0 -> +0.0 like copysign(0, b)
-    if (a < kAngleConst[1]) return a - twopi;
-  } else if (a > kAngleConst[2]) {
-    return a + twopi;
-  }
-  return np_mod_2pi_slow(a);
+  // fast exact paths for -2 pi < a < 4 pi (every in-range particle +- noise lands here), branch-free -- lanes of a
+  // warp fall on both sides of 2 pi all the time: r = a + {0, -2 pi, +2 pi}.
+  //   [0, 2pi): fmod = a; a + 0.0 also turns -0.0 into +0.0 like copysign(0, b).
+  //   [2pi, 4pi): fmod = a - 2pi, exact by Sterbenz.   (-2pi, 0): fmod = a, then += 2pi (one rounding, can return 2 pi).
+  double adj = (a >= kAngleConst[0]) ? kAngleConst[2] : 0.0;
+  adj = (a < 0.0) ? kAngleConst[0] : adj;
+  if (!(a > kAngleConst[2] && a < kAngleConst[1])) return np_mod_2pi_slow(a);  // (also NaN)
+  return a + adj;
 }
 
 // ---- counter-based device RNG (Philox4x32-10) ------------------------------------------------------

@@ -14,9 +14,17 @@ namespace pfb {
 // ---------------------------------------------------------------------------------------------
 // predict
 // ---------------------------------------------------------------------------------------------
-template <int D>
+// PLAIN (compile time): identity transition without offset and noise rows used as drawn (no factor, no mean) -- the
+// torus / sphere filters with von Mises(-Fisher) noise.  The small matrix products behind the run-time flags are
+// if-converted by ptxas: predicated off they still issue (~70 instructions per T^3 particle).
+template <int D, bool PLAIN>
 __device__ __forceinline__ void apply_transition(const pfb_predict_params& p, const double (&x)[D],
                                                  double (&y)[D]) {
+  if constexpr (PLAIN) {
+#pragma unroll
+    for (int r = 0; r < D; ++r) y[r] = x[r];
+    return;
+  }
   if (p.has_F) {
 #pragma unroll
     for (int r = 0; r < D; ++r) {
@@ -38,7 +46,7 @@ __device__ __forceinline__ void apply_transition(const pfb_predict_params& p, co
 // noise row in state space: rows as given, or z A (+ mu) for standard-normal input.  RNG: the draws come from the
 // in-kernel generator (p.rng_kind); a compile-time switch, so that the array-fed kernels do not carry the
 // samplers' registers.
-template <typename T, int D, bool RNG>
+template <typename T, int D, bool RNG, bool PLAIN>
 __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T* __restrict__ noise,
                                            int64_t i, double (&n)[D]) {
   double z[D];
@@ -63,6 +71,11 @@ __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T*
       for (int c = 0; c < D; ++c) z[c] = (double)(float)z[c];  // what an fp32 noise array would have held
     }
   }
+  if constexpr (PLAIN) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) n[c] = z[c];
+    return;
+  }
   if (p.has_A) {
 #pragma unroll
     for (int c = 0; c < D; ++c) {
@@ -81,17 +94,17 @@ __device__ __forceinline__ void load_noise(const pfb_predict_params& p, const T*
   }
 }
 
-template <typename T, int D, int MODE, bool RNG>
+template <typename T, int D, int MODE, bool RNG, bool PLAIN>
 __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T* x_in,
                                             const T* __restrict__ noise, int64_t i, double (&out)[D]) {
   double x[D], y[D];
   load_rec_inplace<T, D>(x_in, i, x);  // (x_in may be x_out: every thread reads its own record before it writes it)
-  apply_transition<D>(p, x, y);
+  apply_transition<D, PLAIN>(p, x, y);
   const bool has_noise = (noise != nullptr || RNG) && p.noise_cols > 0;
   if constexpr (MODE == PFB_PRED_EUCLID) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D, RNG>(p, noise, i, n);
+      load_noise<T, D, RNG, PLAIN>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) out[c] = y[c] + n[c];
     } else {
@@ -101,7 +114,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else if constexpr (MODE == PFB_PRED_TORUS_SHIFT) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D, RNG>(p, noise, i, n);
+      load_noise<T, D, RNG, PLAIN>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
@@ -115,7 +128,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else if constexpr (MODE == PFB_PRED_TORUS_ADD) {
     if (has_noise) {
       double n[D];
-      load_noise<T, D, RNG>(p, noise, i, n);          // includes the (host-wrapped) noise mean
+      load_noise<T, D, RNG, PLAIN>(p, noise, i, n);          // includes the (host-wrapped) noise mean
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         double s = np_mod_2pi(n[c]);
@@ -180,7 +193,7 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
   } else {  // PFB_PRED_SPHERE_ADD
     double n[D];
     if (has_noise) {
-      load_noise<T, D, RNG>(p, noise, i, n);
+      load_noise<T, D, RNG, PLAIN>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) y[c] += n[c];
     }
@@ -210,15 +223,16 @@ __device__ __forceinline__ double whitened_sq(const pfb_lik_params& L, const dou
   return maha;
 }
 
-constexpr double kPi = 3.141592653589793;
 constexpr double kImageCut = 90.0;  // screen: drop images whose maha exceeds the best one by this much (e^-45)
-constexpr float kScreenCut = 78.0f; // fp32 screen: kTermCut plus slack for its rounding (terms beyond kTermCut add nothing)
 constexpr double kTermCut = 76.0;   // a term e^-38 below the best one cannot change the fp64 sum
 
+// log pdf in two parts: the return value a and a linear factor `lin` >= 1 with pdf = exp(a) * lin (lin is 1 except
+// for the image sum of the hypertoroidal wrapped normal, whose callers can then skip the log of the sum).
 template <int D, int KIND>
-__device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const double* __restrict__ mu,
-                                             const double (&x)[D],
-                                             const double* __restrict__ images /* smem or null */) {
+__device__ __forceinline__ double loglik_parts(const pfb_lik_params& L, const double* __restrict__ mu,
+                                               const double (&x)[D],
+                                               const double* __restrict__ images /* smem or null */, double& lin) {
+  lin = 1.0;
   if constexpr (KIND == PFB_LIK_GAUSS) {
     double dev[D];
 #pragma unroll
@@ -226,15 +240,91 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
     return L.logc - 0.5 * whitened_sq<D>(L, dev);
   } else if constexpr (KIND == PFB_LIK_WN_MULTI) {
     // xs = (xs + pi) % (2 pi) - pi; sum over the image table of mvn.pdf(xs + 2 pi k).
-    // maha_k - maha_j = 2 (g_k - g_j).dev + (h_k - h_j) is linear in dev, so images are screened with
-    // r_k = 2 g_k.dev + h_k.  K <= 64 and D <= 3: the screen runs in fp32 on a float4 table and
-    // leaves a bit mask of candidates (a superset of {k : r_k <= min r + cut}); only those get the
-    // exact fp64 quadratic form and, if they can contribute more than e^-37, an exp.
-    double dev[D];
+    // maha_k - maha_0 = 2 g_k.dev + h_k is linear in dev = xs - mu, so t_k = g_k.dev + h_k / 2 (three fp64 FMAs)
+    // orders the images: the best one (smallest t) gets the exact quadratic form of the reference, every other
+    // image enters the sum through exp(-(t_k - t_best)) -- in fp32 when the term is below 2e-9 of the sum, through
+    // its own exact quadratic form when it is not (rare), not at all beyond e^-38.
+    double dev[D], xs[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) dev[c] = (np_mod_2pi(x[c] + kAngleConst[3]) - kAngleConst[3]) - mu[c];
+    for (int c = 0; c < D; ++c) {
+      xs[c] = np_mod_2pi(x[c] + kAngleConst[3]);
+      dev[c] = (xs[c] - kAngleConst[3]) - mu[c];
+    }
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
+    if constexpr (D <= 3) {
+      if (K <= 64) {
+        const double2* lt = reinterpret_cast<const double2*>(images + K * ROW + ((K * ROW) & 1));  // (g0, g1), (g2, h/2)
+        const double d0 = dev[0], d1 = D > 1 ? dev[D > 1 ? 1 : 0] : 0.0, d2 = D > 2 ? dev[D > 2 ? 2 : 0] : 0.0;
+        uint32_t mlo, mhi;  // candidate bits of images 0..31 / 32..63
+        int kref;           // the image whose exact quadratic form anchors the sum
+        auto lin_form = [&](int k) -> double {
+          const double2 a = lt[2 * k], b = lt[2 * k + 1];
+          return fma(a.x, d0, fma(a.y, d1, fma(b.x, d2, b.y)));
+        };
+        if (L.cell_grid > 0 && L.mu_batch_dev == nullptr) {
+          // the host has listed, per cell of the box of xs, the images that can come within e^-39 of the best one
+          // anywhere in the cell (registry.wn_cell_masks: a superset that contains the minimiser) and the image
+          // that is best at the cell's centre (no image beats it by more than e^500 anywhere in the cell)
+          const int G = L.cell_grid;
+          const double inv = (double)G * 0.15915494309189535;  // G / (2 pi)
+          int ci = 0, mul = 1;
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            int q = (int)(xs[c] * inv);
+            q = q < 0 ? 0 : (q >= G ? G - 1 : q);
+            ci += q * mul;
+            mul *= G;
+          }
+          const uint2* cells = reinterpret_cast<const uint2*>(lt + 2 * K);
+          const uint2 cand = cells[ci];
+          mlo = cand.x;
+          mhi = cand.y;
+          kref = reinterpret_cast<const unsigned char*>(cells + mul)[ci];
+        } else {
+          mlo = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
+          mhi = K > 32 ? (K >= 64 ? 0xFFFFFFFFu : ((1u << (K - 32)) - 1u)) : 0u;
+          double tmin = INFINITY;
+          kref = 0;
+          for (int k = 0; k < K; ++k) {
+            const double t = lin_form(k);
+            if (t < tmin) { tmin = t; kref = k; }
+          }
+        }
+        const double tref = lin_form(kref);
+        double sh[D];
+        {
+          const double* row = images + kref * ROW;
+#pragma unroll
+          for (int c = 0; c < D; ++c) sh[c] = dev[c] + row[D + 1 + c];
+        }
+        const double mbest = whitened_sq<D>(L, sh);
+        double extra = 0.0;
+        if (kref < 32) mlo &= ~(1u << kref); else mhi &= ~(1u << (kref - 32));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t m = half ? mhi : mlo;
+          while (m) {
+            const int k = __ffs((int)m) - 1 + 32 * half;
+            m &= m - 1u;
+            const double d = lin_form(k) - tref;
+            if (d <= 0.5 * kTermCut) {
+              if (d > 20.0) {
+                extra += (double)__expf(-(float)d);
+              } else {  // a term above 2e-9 of the anchor's: its own quadratic form, like the reference
+                const double* row = images + k * ROW;
+                double s2[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) s2[c] = dev[c] + row[D + 1 + c];
+                extra += exp(-0.5 * (whitened_sq<D>(L, s2) - mbest));
+              }
+            }
+          }
+        }
+        lin = 1.0 + extra;
+        return L.logc - 0.5 * mbest;
+      }
+    }
     double best = INFINITY, sum = 0.0;
     // exp(-d/2) of a term relative to the best one: fp64 where it matters, fp32 once the term is below
     // 2e-9 of the sum (relative error 1e-6 of 2e-9), nothing beyond e^-38
@@ -254,96 +344,25 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
         sum += rel_term(ma - best);
       }
     };
-    // log(sum), sum = 1 + s with s >= 0: the series is exact to fp64 for small s
-    auto log_sum = [](double sm) -> double {
-      const double sx = sm - 1.0;
-      if (sx == 0.0) return 0.0;
-      if (sx < 1e-5) return sx * (1.0 - sx * (0.5 - sx * (1.0 / 3.0)));
-      return log(sm);
-    };
-    if constexpr (D <= 3) {
-      if (K <= 64) {
-        const float4* scr = reinterpret_cast<const float4*>(images + K * ROW + ((K * ROW) & 1));
-        float df[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) df[c] = (c < D) ? (float)dev[c] : 0.0f;
-        float runmin = INFINITY;
-        uint32_t mlo = 0u, mhi = 0u;  // candidate bits of images 0..31 / 32..63 (branch-free, 32-bit ops)
-        if (L.cell_grid > 0 && L.mu_batch_dev == nullptr) {
-          // the host has listed, per cell of the dev box, the images that can pass the screen anywhere in the cell
-          // (registry.wn_cell_masks: a superset that contains the minimiser): the minimum of r over them is the
-          // minimum over all images, so the second loop below selects exactly what the full screen selects
-          const int G = L.cell_grid;
-          const double inv = (double)G * 0.15915494309189535;  // G / (2 pi)
-          int ci = 0, mul = 1;
-#pragma unroll
-          for (int c = 0; c < D; ++c) {
-            int q = (int)((dev[c] + (kPi + mu[c])) * inv);
-            q = q < 0 ? 0 : (q >= G ? G - 1 : q);
-            ci += q * mul;
-            mul *= G;
-          }
-          const uint64_t cand = reinterpret_cast<const uint64_t*>(scr + K)[ci];
-          mlo = (uint32_t)cand;
-          mhi = (uint32_t)(cand >> 32);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t m = half ? mhi : mlo;
-            while (m) {
-              const int k = __ffs((int)m) - 1 + 32 * half;
-              m &= m - 1u;
-              const float4 t = scr[k];
-              runmin = fminf(runmin, fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w));
-            }
-          }
-        } else {
-        const int K0 = K < 32 ? K : 32;
-        for (int k = 0; k < K0; ++k) {
-          const float4 t = scr[k];
-          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
-          mlo |= (r <= runmin + kScreenCut) ? (1u << k) : 0u;
-          runmin = fminf(runmin, r);
-        }
-        for (int k = 32; k < K; ++k) {
-          const float4 t = scr[k];
-          const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
-          mhi |= (r <= runmin + kScreenCut) ? (1u << (k - 32)) : 0u;
-          runmin = fminf(runmin, r);
-        }
-        }
-        const float lim = runmin + kScreenCut;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t m = half ? mhi : mlo;
-          while (m) {
-            const int k = __ffs((int)m) - 1 + 32 * half;
-            m &= m - 1u;
-            const float4 t = scr[k];
-            const float r = fmaf(2.0f, fmaf(t.x, df[0], fmaf(t.y, df[1], t.z * df[2])), t.w);
-            if (r <= lim) accumulate(images + k * ROW);
-          }
-        }
-    return L.logc - 0.5 * best + log_sum(sum);
-      }
-    }
     // generic path (D > 3 or more than 64 images): the same screen in fp64, two passes
     const double q0 = whitened_sq<D>(L, dev);
     double mmin = INFINITY;
     for (int k = 0; k < K; ++k) {
       const double* row = images + k * ROW;
-      double lin = row[0] * dev[0];
+      double lk = row[0] * dev[0];
 #pragma unroll
-      for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
-      mmin = fmin(mmin, fma(2.0, lin, q0) + row[D]);
+      for (int c = 1; c < D; ++c) lk = fma(row[c], dev[c], lk);
+      mmin = fmin(mmin, fma(2.0, lk, q0) + row[D]);
     }
     for (int k = 0; k < K; ++k) {
       const double* row = images + k * ROW;
-      double lin = row[0] * dev[0];
+      double lk = row[0] * dev[0];
 #pragma unroll
-      for (int c = 1; c < D; ++c) lin = fma(row[c], dev[c], lin);
-      if (fma(2.0, lin, q0) + row[D] - mmin <= kImageCut) accumulate(row);
+      for (int c = 1; c < D; ++c) lk = fma(row[c], dev[c], lk);
+      if (fma(2.0, lk, q0) + row[D] - mmin <= kImageCut) accumulate(row);
     }
-    return L.logc - 0.5 * best + log_sum(sum);
+    lin = sum;
+    return L.logc - 0.5 * best;
   } else if constexpr (KIND == PFB_LIK_WN_1D) {
     if (L.sigma > 10.0) return -log(kTwoPi);
     double xx = np_mod_2pi(x[0]);
@@ -368,6 +387,14 @@ __device__ __forceinline__ double loglik_one(const pfb_lik_params& L, const doub
   }
 }
 
+// log(lin), lin = 1 + s with s >= 0: the series is exact to fp64 for small s
+__device__ __forceinline__ double log_lin(double lin) {
+  const double sx = lin - 1.0;
+  if (sx == 0.0) return 0.0;
+  if (sx < 1e-5) return sx * (1.0 - sx * (0.5 - sx * (1.0 / 3.0)));
+  return log(lin);
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
@@ -382,14 +409,14 @@ __device__ __forceinline__ void store_padded(const pfb_predict_params& p, int64_
   store_rec<T, DP>(static_cast<T*>(p.x_pad_out), i, q);
 }
 
-template <typename T, int D, int MODE, bool RNG>
+template <typename T, int D, int MODE, bool RNG, bool PLAIN>
 __global__ void __launch_bounds__(kThreads) predict_kernel(pfb_predict_params p, int64_t n,
                                                            const T* x_in, T* x_out,
                                                            const T* __restrict__ noise) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     double out[D];
-    predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
+    predict_one<T, D, MODE, RNG, PLAIN>(p, x_in, noise, i, out);
     store_rec<T, D>(x_out, i, out);
     store_padded<T, D>(p, i, out);
   }
@@ -429,24 +456,22 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
   const int K = L.n_images;
   const int count = K * ROW;
   for (int k = threadIdx.x; k < count; k += blockDim.x) smem_img[k] = L.images_dev[k];
-  if (D <= 3 && K <= 64) {  // fp32 screen rows (g0, g1, g2, h) after the fp64 table (16-byte aligned: count*8 + pad)
-    float4* scr = reinterpret_cast<float4*>(smem_img + count + (count & 1));
+  if (D <= 3 && K <= 64) {  // linear-form rows (g0, g1, g2, h / 2) after the table (16-byte aligned: count*8 + pad)
+    double* lt = smem_img + count + (count & 1);
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
       const double* row = L.images_dev + k * ROW;
-      float4 t;
-      t.x = (float)row[0];
-      t.y = D > 1 ? (float)row[1] : 0.0f;
-      t.z = D > 2 ? (float)row[2] : 0.0f;
-      t.w = (float)row[D];
-      scr[k] = t;
+      lt[4 * k] = row[0];
+      lt[4 * k + 1] = D > 1 ? row[D > 1 ? 1 : 0] : 0.0;
+      lt[4 * k + 2] = D > 2 ? row[D > 2 ? 2 : 0] : 0.0;
+      lt[4 * k + 3] = 0.5 * row[D];
     }
-    if (L.cell_grid > 0) {  // candidate masks of the cell grid, after the screen rows
-      uint64_t* cells = reinterpret_cast<uint64_t*>(scr + K);
+    if (L.cell_grid > 0) {  // candidate masks of the cell grid, after the linear rows
+      uint64_t* cells = reinterpret_cast<uint64_t*>(lt + 4 * K);
       const uint64_t* src = reinterpret_cast<const uint64_t*>(L.images_dev + count);
       int nc = L.cell_grid;
       if (D > 1) nc *= L.cell_grid;
       if (D > 2) nc *= L.cell_grid;
-      for (int k = threadIdx.x; k < nc; k += blockDim.x) cells[k] = src[k];
+      for (int k = threadIdx.x; k < nc + (nc + 7) / 8; k += blockDim.x) cells[k] = src[k];  // masks, then the reference bytes
     }
   }
   __syncthreads();
@@ -477,11 +502,13 @@ inline Seg seg_batched(int64_t n_runs, int64_t run_len) {
 // Two output formats (pfb_lik_params.out_format):
 //   PFB_WEIGHTS_LOG     logw_i = log pdf_i; per slice (max, sum exp(l - max)).  One exp per particle here and one
 //                       more in every pass of the scan that turns log-weights into addends.
-//   PFB_WEIGHTS_SCALED  p_i = pdf_i 2^(-e_w), e_w = ceil(max_slice(l) log2 e) the slice's own binary exponent
-//                       (p_i <= ~1, the largest of a slice > 1/2); per slice (e_w, sum p).  The scan forms its
-//                       addends as p_i 2^(e_w - E) -- an exact scaling, no exp -- so the whole step spends ONE exp per
-//                       particle and keeps the range of the log domain (a slice of far-away particles scales to 0
-//                       only relative to the best slice, like exp(l - max) would).
+//   PFB_WEIGHTS_SCALED  p_i = pdf_i 2^(-e_s), e_s an integer exponent of the slice: ceil(max(l) log2 e) over the first
+//                       32 particles of the slice that have a non-zero weight (so p_i is of order 1; a later particle more
+//                       than e^600 above it makes the warp rescale what it has stored -- exact power-of-two scalings);
+//                       per slice (e_s, sum p).  The scan forms its addends as p_i 2^(e_s - E) -- an exact scaling, no
+//                       exp -- so the whole step spends ONE exp per particle, in a single pass, and keeps the range of
+//                       the log domain (a slice of far-away particles scales to 0 only relative to the best slice, like
+//                       exp(l - max) would).
 constexpr double kLog2e = 1.4426950408889634, kLn2 = 0.6931471805599453;
 __device__ __forceinline__ double slice_exponent(double m) {  // integer-valued; -inf for an empty slice
   if (!(m > -INFINITY)) return -INFINITY;
@@ -489,6 +516,21 @@ __device__ __forceinline__ double slice_exponent(double m) {  // integer-valued;
   return e < -4000.0 ? -4000.0 : (e > 4000.0 ? 4000.0 : e);
 }
 
+// a later batch of the slice lies more than e^600 above the slice exponent: move the exponent up and scale what the
+// warp has stored so far (lane-private columns of the output array)
+static __device__ __noinline__ double rescale_slice(double* mine, int k, int64_t lbase, int64_t run_pad, double eg,
+                                                    double a, double* sacc, double* pmax) {
+  const double en = slice_exponent(warp_max(a));
+  const double d = eg - en;
+  const double f = (d > -1100.0) ? scalbn(1.0, (int)d) : 0.0;
+  for (int j = 0; j < k; ++j)
+    if (lbase + (int64_t)j * 32 < run_pad) mine[j * 32] *= f;
+  *sacc *= f;
+  *pmax *= f;
+  return en;
+}
+
+// eval(i, run, lin) returns a with pdf_i = exp(a) * lin
 template <bool SCALED, typename EVAL>
 __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats, Workspace ws,
                                              double* red, EVAL eval) {
@@ -496,54 +538,58 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarpSpan = kScanTile / (kThreads / 32);  // 256 particles per warp and tile
   double gmax = -INFINITY, gnan = 0.0;
+  double bp = 0.0, bc = 0.0;  // SCALED: the largest weight so far is bp e^bc
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t run = tile / sg.tpr;
     const int64_t lbase = (tile - run * sg.tpr) * kScanTile + warp * kWarpSpan + lane;
     if constexpr (SCALED) {
-      // pass 1 (not unrolled: the evaluation is long) parks the thread's 8 log-likelihoods in the output array itself
-      // (a register array indexed by the loop counter would go to local memory, a shared-memory column costs the
-      // L1 capacity the strided record loads live on); pass 2 (unrolled) reads them back -- the thread's own stores,
-      // still in L2 -- and exponentiates against the slice's exponent
       constexpr int kPer = kWarpSpan / 32;
-      double m = -INFINITY;
-#pragma unroll 1
-      for (int k = 0; k < kPer; ++k) {
-        const int64_t local = lbase + k * 32;
-        if (local < sg.run_len) {
-          double v = eval(run * sg.run_len + local, run);
-          if (v != v) { gnan = 1.0; v = -INFINITY; }
-          logw[run * sg.run_pad + local] = v;
-          m = fmax(m, v);
-        }
-      }
-      const double wm = warp_max(m);
-      const double ew = slice_exponent(wm);
-      const double cw = ew * kLn2;
-      double sacc = 0.0;
+      double eg = -INFINITY, cg = 0.0, sacc = 0.0, pmax = 0.0;
       double* mine = logw + run * sg.run_pad + lbase;
-      double cur = (lbase < sg.run_len) ? mine[0] : -INFINITY;
 #pragma unroll 1
-      for (int k = 0; k < kPer; ++k) {  // (not unrolled: eight inlined exps cost more in instruction fetch than they save)
+      for (int k = 0; k < kPer; ++k) {  // (not unrolled: the evaluation is long)
         const int64_t local = lbase + k * 32;
-        const double nxt = (k + 1 < kPer && local + 32 < sg.run_len) ? mine[(k + 1) * 32] : -INFINITY;
-        const double p = (cur > -INFINITY) ? exp(cur - cw) : 0.0;
+        double a = -INFINITY, lin = 1.0;
+        if (local < sg.run_len) {
+          a = eval(run * sg.run_len + local, run, lin);
+          if (a != a || lin != lin) { gnan = 1.0; a = -INFINITY; }
+        }
+        if (!(eg > -INFINITY)) {  // (warp-uniform) no exponent yet: first batch, or only zero weights so far
+          eg = slice_exponent(warp_max(a));
+          cg = eg * kLn2;
+        } else if (__any_sync(0xffffffffu, a - cg > 600.0)) {
+          eg = rescale_slice(mine, k, lbase, sg.run_pad, eg, a, &sacc, &pmax);
+          cg = eg * kLn2;
+        }
+        const double p = (a > -INFINITY) ? exp(a - cg) * lin : 0.0;
         if (local < sg.run_pad) mine[k * 32] = p;  // (padding of a batched run: weight 0)
         sacc += p;
-        cur = nxt;
+        pmax = fmax(pmax, p);
       }
       const double wsum = warp_sum(sacc);
+      const double wp = warp_max(pmax);
       if (lane == 0) {
-        ws.wpart[tile * 16 + 2 * warp] = ew;
+        ws.wpart[tile * 16 + 2 * warp] = eg;
         ws.wpart[tile * 16 + 2 * warp + 1] = wsum;
       }
-      gmax = fmax(gmax, wm);
+      if (wp > 0.0) {  // running maximum of the weights, kept as (factor, log offset): logs only when the offsets differ
+        if (bp == 0.0 || cg == bc) {
+          bp = fmax(bp, wp);
+          bc = cg;
+        } else if (log(wp) + cg > log(bp) + bc) {
+          bp = wp;
+          bc = cg;
+        }
+      }
     } else {
       double m = -INFINITY, sacc = 0.0;  // running max and sum exp(l - m) of this thread's particles
 #pragma unroll 1
       for (int k = 0; k < kWarpSpan / 32; ++k) {
         const int64_t local = lbase + k * 32;
         if (local < sg.run_len) {
-          const double v = eval(run * sg.run_len + local, run);
+          double lin;
+          double v = eval(run * sg.run_len + local, run, lin);
+          v += log_lin(lin);
           logw[run * sg.run_pad + local] = v;
           if (v != v) {
             gnan = 1.0;
@@ -565,6 +611,7 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
       gmax = fmax(gmax, wm);
     }
   }
+  if constexpr (SCALED) gmax = (bp > 0.0) ? log(bp) + bc : -INFINITY;
   finish_max(gmax, gnan, stats, ws, red);
 }
 
@@ -577,17 +624,17 @@ __global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg 
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
+  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run, double& lin) {
     double r[D];
     load_rec<T, D>(x, i, r);
     const double* mu = L.mu_batch_dev ? L.mu_batch_dev + run * D : L.mu;
-    double l = loglik_one<D, KIND>(L, mu, r, images);
+    double l = loglik_parts<D, KIND>(L, mu, r, images, lin);
     if (w_prev != nullptr) l += log(w_prev[i]);
     return l;
   });
 }
 
-template <typename T, int D, int MODE, int KIND, bool RNG, bool SCALED>
+template <typename T, int D, int MODE, int KIND, bool RNG, bool SCALED, bool PLAIN>
 __global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 5) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* x_in, T* x_out,
@@ -597,9 +644,9 @@ __global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 
   extern __shared__ __align__(16) double smem_dyn[];
   __shared__ double red[32];
   const double* images = stage_images<D>(L, smem_dyn);
-  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run) {
+  weight_tiles<SCALED>(sg, logw, stats, ws, red, [&](int64_t i, int64_t run, double& lin) {
     double out[D];
-    predict_one<T, D, MODE, RNG>(p, x_in, noise, i, out);
+    predict_one<T, D, MODE, RNG, PLAIN>(p, x_in, noise, i, out);
     if (x_out != nullptr) store_rec<T, D>(x_out, i, out);  // (NULL: only the padded copy is wanted, see pfb.h)
     store_padded<T, D>(p, i, out);
     if constexpr (sizeof(T) == 4) {
@@ -608,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 
       for (int c = 0; c < D; ++c) out[c] = (double)(float)out[c];
     }
     const double* mu = L.mu_batch_dev ? L.mu_batch_dev + run * D : L.mu;
-    return loglik_one<D, KIND>(L, mu, out, images);
+    return loglik_parts<D, KIND>(L, mu, out, images, lin);
   });
 }
 
@@ -674,6 +721,7 @@ static double vm_strip_end(double kappa, double A, int K, double* table) {
   return a;
 }
 
+#ifndef PFB_PL_F32_TU
 extern "C" int pfb_vm_strip_table(double kappa, double* table, double* area) {
   if (!table || !area) { set_error("NULL table / area"); return PFB_ERR_INVALID; }
   if (!(kappa >= 1e-8) || !(kappa < 1e300)) { set_error("strip tables exist for 1e-8 <= kappa < inf (smaller kappas draw uniformly)"); return PFB_ERR_INVALID; }
@@ -690,6 +738,8 @@ extern "C" int pfb_vm_strip_table(double kappa, double* table, double* area) {
   return PFB_OK;
 }
 
+#endif
+
 static int check_lik(const pfb_lik_params* L, int dim) {
   if (!L) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
   if (L->dim != dim) { set_error("likelihood dim %d != particle dim %d", L->dim, dim); return PFB_ERR_INVALID; }
@@ -698,7 +748,7 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
     if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
-    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 16) + 8 > 40 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 32) + 8 > 40 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
     if (L->cell_grid != 0 && (L->cell_grid < 1 || L->cell_grid > 8 || dim > 3 || L->n_images > 64)) {
       set_error("cell_grid %d: candidate masks need 1 <= G <= 8, dim <= 3 and at most 64 images", L->cell_grid);
       return PFB_ERR_INVALID;
@@ -711,10 +761,11 @@ static size_t lik_smem(const pfb_lik_params* L) {
   if (L->kind != PFB_LIK_WN_MULTI) return 0;
   size_t cells = 0;
   if (L->cell_grid > 0) {
-    cells = 8;
+    cells = 1;
     for (int c = 0; c < L->dim; ++c) cells *= (size_t)L->cell_grid;
+    cells = cells * 8 + ((cells + 7) / 8) * 8;  // masks + one reference byte per cell
   }
-  return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 16 + cells;
+  return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 32 + cells;
 }
 
 #define PFB_DISPATCH_MODE(mode, ...)                                                       \
@@ -735,31 +786,6 @@ static size_t lik_smem(const pfb_lik_params* L) {
   }
 
 }  // namespace pfb
-
-using namespace pfb;
-
-extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t n, const void* x_in,
-                           void* x_out, const void* noise, void* stream) {
-  int rc = check_predict(p);
-  if (rc) return rc;
-  if (n <= 0) return PFB_OK;
-  if (!x_in || !x_out) { set_error("NULL particle pointer"); return PFB_ERR_INVALID; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stream_grid(n);
-  const bool rng = p->rng_kind != PFB_RNG_NONE;
-  PFB_DISPATCH_DTYPE(dtype, {
-    if (p->mode == PFB_PRED_SPHERE_VMF) {
-      if (rng) predict_kernel<T, 3, PFB_PRED_SPHERE_VMF, true><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
-      else predict_kernel<T, 3, PFB_PRED_SPHERE_VMF, false><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise);
-    } else if (rng) {
-      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE, true><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
-    } else {
-      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (predict_kernel<T, D, MODE, false><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise))));
-    }
-  });
-  PFB_LAUNCH_OK("predict_kernel");
-  return PFB_OK;
-}
 
 namespace pfb {
 static int tile_grid_seg(const Seg& sg) { return tile_grid(sg.n_runs * sg.tpr * (int64_t)kScanTile); }
@@ -787,32 +813,55 @@ static int one_wave_grid(K kernel, size_t smem, const Seg& sg) {
   return g;
 }
 
-static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const void* x, const double* w_prev,
-                       double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream) {
-  if (!lik) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
-  int rc = check_lik(lik, lik->dim);
-  if (rc) return rc;
-  if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
-  if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
-  Workspace W;
-  rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+static bool plain_predict(const pfb_predict_params* p) {
+  return !p->has_F && !p->has_b && !p->has_A && !p->has_mu_noise;
+}
+
+// ---- launches of one storage type T.  The fp64 instantiations live in this translation unit, the fp32 ones in
+// pfb_predict_loglik_f32.cu (which includes this file with PFB_PL_F32_TU defined): the two halves compile in parallel.
+template <typename T>
+int predict_launch(const pfb_predict_params* p, int64_t n, const void* x_in, void* x_out, const void* noise,
+                   cudaStream_t st) {
+  const int grid = stream_grid(n);
+  const bool rng = p->rng_kind != PFB_RNG_NONE;
+  const bool plain = plain_predict(p);
+#define PFB_PREDICT_LAUNCH(DD, MM, RR, PP) \
+  predict_kernel<T, DD, MM, RR, PP><<<grid, kThreads, 0, st>>>(*p, n, (const T*)x_in, (T*)x_out, (const T*)noise)
+  if (p->mode == PFB_PRED_SPHERE_VMF) {
+    if (rng) { if (plain) PFB_PREDICT_LAUNCH(3, PFB_PRED_SPHERE_VMF, true, true); else PFB_PREDICT_LAUNCH(3, PFB_PRED_SPHERE_VMF, true, false); }
+    else { if (plain) PFB_PREDICT_LAUNCH(3, PFB_PRED_SPHERE_VMF, false, true); else PFB_PREDICT_LAUNCH(3, PFB_PRED_SPHERE_VMF, false, false); }
+  } else if (plain && (p->mode == PFB_PRED_TORUS_SHIFT || p->mode == PFB_PRED_TORUS_ADD)) {
+    if (p->mode == PFB_PRED_TORUS_SHIFT) {
+      if (rng) { PFB_DISPATCH_DIM(p->dim, PFB_PREDICT_LAUNCH(D, PFB_PRED_TORUS_SHIFT, true, true)); }
+      else { PFB_DISPATCH_DIM(p->dim, PFB_PREDICT_LAUNCH(D, PFB_PRED_TORUS_SHIFT, false, true)); }
+    } else {
+      if (rng) { PFB_DISPATCH_DIM(p->dim, PFB_PREDICT_LAUNCH(D, PFB_PRED_TORUS_ADD, true, true)); }
+      else { PFB_DISPATCH_DIM(p->dim, PFB_PREDICT_LAUNCH(D, PFB_PRED_TORUS_ADD, false, true)); }
+    }
+  } else if (rng) {
+    PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, PFB_PREDICT_LAUNCH(D, MODE, true, false)));
+  } else {
+    PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, PFB_PREDICT_LAUNCH(D, MODE, false, false)));
+  }
+#undef PFB_PREDICT_LAUNCH
+  return PFB_OK;
+}
+
+template <typename T>
+int loglik_launch(const pfb_lik_params* lik, Seg sg, const void* x, const double* w_prev, double* logw, double* stats,
+                  Workspace W, cudaStream_t st) {
   const int grid = tile_grid_seg(sg);
   const size_t sm = lik_smem(lik);
 #define PFB_LOGLIK_LAUNCH(S)                                                                                          \
-  PFB_DISPATCH_DTYPE(dtype, {                                                                                          \
-    if (lik->kind == PFB_LIK_WN_1D) {                                                                                  \
-      loglik_kernel<T, 1, PFB_LIK_WN_1D, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W); \
-    } else if (lik->kind == PFB_LIK_VM) {                                                                              \
-      loglik_kernel<T, 1, PFB_LIK_VM, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);    \
-    } else {                                                                                                           \
-      PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W)))); \
-    }                                                                                                                  \
-  })
-  if (lik->out_format == PFB_WEIGHTS_SCALED) { PFB_LOGLIK_LAUNCH(true); } else { PFB_LOGLIK_LAUNCH(false); }
+  if (lik->kind == PFB_LIK_WN_1D) {                                                                                    \
+    loglik_kernel<T, 1, PFB_LIK_WN_1D, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);   \
+  } else if (lik->kind == PFB_LIK_VM) {                                                                                \
+    loglik_kernel<T, 1, PFB_LIK_VM, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);      \
+  } else {                                                                                                             \
+    PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W)))); \
+  }
+  if (lik->out_format == PFB_WEIGHTS_SCALED) { PFB_LOGLIK_LAUNCH(true) } else { PFB_LOGLIK_LAUNCH(false) }
 #undef PFB_LOGLIK_LAUNCH
-  PFB_LAUNCH_OK("loglik_kernel");
   return PFB_OK;
 }
 
@@ -824,16 +873,25 @@ static int launch_fused_one(const pfb_predict_params* p, const pfb_lik_params* l
                             cudaStream_t st) {
   const size_t sm = lik_smem(lik);
   const bool scaled = lik->out_format == PFB_WEIGHTS_SCALED;
-#define PFB_FUSED_LAUNCH(R, S)                                                                                     \
+  // the PLAIN kernels exist for the torus modes and S^2 von Mises-Fisher noise (identity transition, rows as drawn)
+  constexpr bool kHasPlain = MODE == PFB_PRED_TORUS_SHIFT || MODE == PFB_PRED_TORUS_ADD || MODE == PFB_PRED_SPHERE_VMF;
+  const bool plain = kHasPlain && plain_predict(p);
+#define PFB_FUSED_LAUNCH(R, S, P)                                                                                  \
   {                                                                                                                \
-    auto k = predict_loglik_kernel<T, D, MODE, KIND, R, S>;                                                        \
+    auto k = predict_loglik_kernel<T, D, MODE, KIND, R, S, P>;                                                     \
     k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*p, *lik, sg, (const T*)x_in, (T*)x_out, (const T*)noise, logw, stats, W); \
   }
-  if (p->rng_kind != PFB_RNG_NONE) {
-    if (scaled) PFB_FUSED_LAUNCH(true, true) else PFB_FUSED_LAUNCH(true, false)
-  } else {
-    if (scaled) PFB_FUSED_LAUNCH(false, true) else PFB_FUSED_LAUNCH(false, false)
+#define PFB_FUSED_RS(P)                                                                  \
+  if (p->rng_kind != PFB_RNG_NONE) {                                                     \
+    if (scaled) PFB_FUSED_LAUNCH(true, true, P) else PFB_FUSED_LAUNCH(true, false, P)    \
+  } else {                                                                               \
+    if (scaled) PFB_FUSED_LAUNCH(false, true, P) else PFB_FUSED_LAUNCH(false, false, P)  \
   }
+  if constexpr (kHasPlain) {
+    if (plain) { PFB_FUSED_RS(true) return PFB_OK; }
+  }
+  PFB_FUSED_RS(false)
+#undef PFB_FUSED_RS
 #undef PFB_FUSED_LAUNCH
   return PFB_OK;
 }
@@ -861,6 +919,71 @@ static int launch_fused(const pfb_predict_params* p, const pfb_lik_params* lik, 
   return PFB_ERR_UNSUPPORTED;
 }
 
+template <typename T>
+int fused_launch(const pfb_predict_params* p, const pfb_lik_params* lik, Seg sg, const void* x_in, void* x_out,
+                 const void* noise, double* logw, double* stats, Workspace W, cudaStream_t st) {
+  int rc = PFB_OK;
+  if (p->mode == PFB_PRED_SPHERE_VMF) {
+    rc = launch_fused<T, 3, PFB_PRED_SPHERE_VMF>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st);
+  } else {
+    PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (rc = launch_fused<T, D, MODE>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st))));
+  }
+  return rc;
+}
+
+template <typename T>
+int wrap_launch(int64_t count, const void* x_in, void* x_out, cudaStream_t st) {
+  wrap_kernel<T><<<stream_grid(count), kThreads, 0, st>>>(count, (const T*)x_in, (T*)x_out);
+  return PFB_OK;
+}
+
+#ifdef PFB_PL_F32_TU
+template int predict_launch<float>(const pfb_predict_params*, int64_t, const void*, void*, const void*, cudaStream_t);
+template int loglik_launch<float>(const pfb_lik_params*, Seg, const void*, const double*, double*, double*, Workspace, cudaStream_t);
+template int fused_launch<float>(const pfb_predict_params*, const pfb_lik_params*, Seg, const void*, void*, const void*, double*, double*, Workspace, cudaStream_t);
+template int wrap_launch<float>(int64_t, const void*, void*, cudaStream_t);
+#else
+extern template int predict_launch<float>(const pfb_predict_params*, int64_t, const void*, void*, const void*, cudaStream_t);
+extern template int loglik_launch<float>(const pfb_lik_params*, Seg, const void*, const double*, double*, double*, Workspace, cudaStream_t);
+extern template int fused_launch<float>(const pfb_predict_params*, const pfb_lik_params*, Seg, const void*, void*, const void*, double*, double*, Workspace, cudaStream_t);
+extern template int wrap_launch<float>(int64_t, const void*, void*, cudaStream_t);
+#endif
+}  // namespace pfb
+
+#ifndef PFB_PL_F32_TU
+using namespace pfb;
+
+extern "C" int pfb_predict(const pfb_predict_params* p, pfb_dtype dtype, int64_t n, const void* x_in,
+                           void* x_out, const void* noise, void* stream) {
+  int rc = check_predict(p);
+  if (rc) return rc;
+  if (n <= 0) return PFB_OK;
+  if (!x_in || !x_out) { set_error("NULL particle pointer"); return PFB_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, (rc = predict_launch<T>(p, n, x_in, x_out, noise, st)));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("predict_kernel");
+  return PFB_OK;
+}
+
+namespace pfb {
+static int loglik_impl(const pfb_lik_params* lik, pfb_dtype dtype, Seg sg, const void* x, const double* w_prev,
+                       double* logw, double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  if (!lik) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
+  int rc = check_lik(lik, lik->dim);
+  if (rc) return rc;
+  if (sg.n_runs <= 0 || sg.run_len <= 0) return PFB_OK;
+  if (!x || !logw || !stats) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  Workspace W;
+  rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, (rc = loglik_launch<T>(lik, sg, x, w_prev, logw, stats, W, st)));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("loglik_kernel");
+  return PFB_OK;
+}
+
 static int predict_loglik_impl(const pfb_predict_params* p, const pfb_lik_params* lik, pfb_dtype dtype, Seg sg,
                                const void* x_in, void* x_out, const void* noise, double* logw, double* stats,
                                void* ws, int64_t ws_bytes, void* stream) {
@@ -874,13 +997,7 @@ static int predict_loglik_impl(const pfb_predict_params* p, const pfb_lik_params
   rc = carve_workspace(ws, ws_bytes, sg.n_runs == 1 ? sg.run_len : sg.n_runs * sg.tpr * (int64_t)kScanTile, &W);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  PFB_DISPATCH_DTYPE(dtype, {
-    if (p->mode == PFB_PRED_SPHERE_VMF) {
-      rc = launch_fused<T, 3, PFB_PRED_SPHERE_VMF>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st);
-    } else {
-      PFB_DISPATCH_DIM(p->dim, PFB_DISPATCH_MODE(p->mode, (rc = launch_fused<T, D, MODE>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st))));
-    }
-  });
+  PFB_DISPATCH_DTYPE(dtype, (rc = fused_launch<T>(p, lik, sg, x_in, x_out, noise, logw, stats, W, st)));
   if (rc) return rc;
   PFB_LAUNCH_OK("predict_loglik_kernel");
   return PFB_OK;
@@ -919,8 +1036,10 @@ extern "C" int pfb_wrap_2pi(pfb_dtype dtype, int64_t count, const void* x_in, vo
   if (count <= 0) return PFB_OK;
   if (!x_in || !x_out) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = stream_grid(count);
-  PFB_DISPATCH_DTYPE(dtype, (wrap_kernel<T><<<grid, kThreads, 0, st>>>(count, (const T*)x_in, (T*)x_out)));
+  int rc = PFB_OK;
+  PFB_DISPATCH_DTYPE(dtype, (rc = wrap_launch<T>(count, x_in, x_out, st)));
+  if (rc) return rc;
   PFB_LAUNCH_OK("wrap_kernel");
   return PFB_OK;
 }
+#endif  // PFB_PL_F32_TU

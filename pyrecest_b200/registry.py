@@ -227,6 +227,8 @@ def wn_image_table_cached(mu, P, device_put=None):
     if hit is None:
         table, n_img = wn_image_table(mu, P)
         cells = wn_cell_masks(mu, table)
+        if cells is not None:
+            cells = wn_cell_table(mu, table, cells)
         flat = table.reshape(-1) if cells is None else np.concatenate([table.reshape(-1), cells.view(np.float64)])
         dev = device_put(flat) if device_put is not None else None
         if len(_IMAGE_TABLE_CACHE) > 256:
@@ -266,6 +268,35 @@ def wn_cell_masks(mu, table, G=WN_CELL_GRID):
     out = np.zeros(G ** d, dtype=np.uint64)
     out[flat] = bits
     return out
+
+
+def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0):
+    """Device form of the candidate grid: the uint64 masks followed by one reference byte per cell (padded to 8
+    bytes) -- the image that is best at the cell's centre, t_k = g_k.dev + h_k / 2 smallest.  The kernel anchors the
+    image sum there: exact quadratic form of the reference image, every other candidate through exp(-(t_k - t_ref)).
+    Returns None (no grid: the kernel finds the best image itself) if some candidate could beat the reference by more
+    than e^limit somewhere in its cell (tiny covariances), where that exp would overflow."""
+    mu = _np(mu).reshape(-1)
+    d = mu.shape[0]
+    K = table.shape[0]
+    g, h = table[:, :d], table[:, d]
+    lo = -math.pi - mu
+    wid = TWO_PI / G
+    idx = np.stack(np.meshgrid(*([np.arange(G)] * d), indexing="ij"), axis=-1).reshape(-1, d)
+    flat = (idx * (G ** np.arange(d))[None, :]).sum(axis=1)
+    bits = ((masks[flat][:, None] >> np.arange(K, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)  # (cells, K)
+    centre = lo + (idx + 0.5) * wid
+    t = centre @ g.T + 0.5 * h[None, :]
+    ref = np.where(bits, t, np.inf).argmin(axis=1)                                                         # (cells,)
+    a = lo + idx * wid - 1e-6
+    b = a + wid + 2e-6
+    dg = g[ref][:, None, :] - g[None, :, :]                                                                # (cells, K, d)
+    gain = np.maximum(dg * a[:, None, :], dg * b[:, None, :]).sum(axis=-1) + 0.5 * (h[ref][:, None] - h[None, :])
+    if np.any(np.where(bits, gain, -np.inf) > limit):
+        return None
+    refs = np.zeros(((G ** d + 7) // 8) * 8, dtype=np.uint8)
+    refs[flat] = ref.astype(np.uint8)
+    return np.concatenate([masks.view(np.uint8), refs]).view(np.uint64)
 
 
 def wn_image_table(mu, P, m=3, cut=None):
