@@ -112,6 +112,27 @@ __device__ __forceinline__ double np_mod_2pi(double a) {
   return a + adj;
 }
 
+// The same fast paths for the hot kernels, where a particle takes 3 D wraps: no branch per wrap -- the arguments
+// outside the fast range only raise `bad`, and the caller redoes the particle's wraps with np_mod_2pi_slow under ONE
+// branch (essentially never taken).  Results are those of np_mod_2pi wherever bad stays false.
+//   mod2pi_pos: +0 <= a < 4 pi (checked on the high word: negative values, -0.0, NaN and inf fail).
+//   mod2pi_any: -2 pi < a < 4 pi; ZERO_SAFE adds the a + 0.0 that turns -0.0 into +0.0 (call sites whose argument is
+//               a sum with a non-negative wrapped value cannot see -0.0).
+__device__ __forceinline__ double mod2pi_pos(double a, bool& bad) {
+  bad |= (unsigned)__double2hiint(a) >= 0x402921FBu;  // 4 pi = 0x402921FB54442D18
+  double r = a;
+  if (a >= kAngleConst[0]) r = a - kAngleConst[0];
+  return r;
+}
+template <bool ZERO_SAFE = false>
+__device__ __forceinline__ double mod2pi_any(double a, bool& bad) {
+  bad |= !(fabs(a - kAngleConst[3]) < 9.42477795);  // 3 pi - 1e-8 (NaN fails)
+  double r = ZERO_SAFE ? a + 0.0 : a;
+  if (a >= kAngleConst[0]) r = a - kAngleConst[0];
+  if (a < 0.0) r = a + kAngleConst[0];
+  return r;
+}
+
 // ---- counter-based device RNG (Philox4x32-10) ------------------------------------------------------
 // Draws are a pure function of (seed, offset, particle index, slot): no state to carry, the same
 // particle gets the same draw whatever the grid shape.  oracle/pf_oracle.py restates it in numpy.

@@ -112,31 +112,49 @@ __device__ __forceinline__ void predict_one(const pfb_predict_params& p, const T
       for (int c = 0; c < D; ++c) out[c] = y[c];
     }
   } else if constexpr (MODE == PFB_PRED_TORUS_SHIFT) {
+    bool bad = false;
     if (has_noise) {
       double n[D];
       load_noise<T, D, RNG, PLAIN>(p, noise, i, n);
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        double mean = np_mod_2pi(y[c]);          // set_mean wraps the particle
-        double s = np_mod_2pi(n[c] + mean);      // sample(): draw + mean, wrapped: s in [0, 2 pi]
-        out[c] = (s == kAngleConst[0]) ? 0.0 : s;  // filter wraps again: mod(s) = s, except mod(2 pi) = 0
+        const double mean = mod2pi_pos(y[c], bad);        // set_mean wraps the particle
+        const double s = mod2pi_any(n[c] + mean, bad);    // sample(): draw + mean, wrapped: s in [0, 2 pi]
+        out[c] = (s == kAngleConst[0]) ? 0.0 : s;         // filter wraps again: mod(s) = s, except mod(2 pi) = 0
+      }
+      if (bad) {  // some argument outside the fast range of the wraps: the general numpy.mod for this particle
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const double s = np_mod_2pi_slow(n[c] + np_mod_2pi_slow(y[c]));
+          out[c] = (s == kAngleConst[0]) ? 0.0 : s;
+        }
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < D; ++c) out[c] = np_mod_2pi(y[c]);
+      for (int c = 0; c < D; ++c) out[c] = mod2pi_pos(y[c], bad);
+      if (bad) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) out[c] = np_mod_2pi_slow(y[c]);
+      }
     }
   } else if constexpr (MODE == PFB_PRED_TORUS_ADD) {
+    bool bad = false;
     if (has_noise) {
       double n[D];
       load_noise<T, D, RNG, PLAIN>(p, noise, i, n);          // includes the (host-wrapped) noise mean
 #pragma unroll
-      for (int c = 0; c < D; ++c) {
-        double s = np_mod_2pi(n[c]);
-        out[c] = np_mod_2pi(y[c] + s);
+      for (int c = 0; c < D; ++c) out[c] = mod2pi_any(y[c] + mod2pi_any<true>(n[c], bad), bad);
+      if (bad) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) out[c] = np_mod_2pi_slow(y[c] + np_mod_2pi_slow(n[c]));
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < D; ++c) out[c] = np_mod_2pi(y[c]);
+      for (int c = 0; c < D; ++c) out[c] = mod2pi_pos(y[c], bad);
+      if (bad) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) out[c] = np_mod_2pi_slow(y[c]);
+      }
     }
   } else if constexpr (MODE == PFB_PRED_SPHERE_VMF) {
     static_assert(D == 3 || MODE != PFB_PRED_SPHERE_VMF, "VMF noise is implemented on S^2");
@@ -245,11 +263,15 @@ __device__ __forceinline__ double loglik_parts(const pfb_lik_params& L, const do
     // image enters the sum through exp(-(t_k - t_best)) -- in fp32 when the term is below 2e-9 of the sum, through
     // its own exact quadratic form when it is not (rare), not at all beyond e^-38.
     double dev[D], xs[D];
+    bool bad = false;
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-      xs[c] = np_mod_2pi(x[c] + kAngleConst[3]);
-      dev[c] = (xs[c] - kAngleConst[3]) - mu[c];
+    for (int c = 0; c < D; ++c) xs[c] = mod2pi_pos(x[c] + kAngleConst[3], bad);
+    if (bad) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) xs[c] = np_mod_2pi_slow(x[c] + kAngleConst[3]);
     }
+#pragma unroll
+    for (int c = 0; c < D; ++c) dev[c] = (xs[c] - kAngleConst[3]) - mu[c];
     const int K = L.n_images;
     constexpr int ROW = 2 * D + 1;
     if constexpr (D <= 3) {
@@ -517,17 +539,42 @@ __device__ __forceinline__ double slice_exponent(double m) {  // integer-valued;
 }
 
 // a later batch of the slice lies more than e^600 above the slice exponent: move the exponent up and scale what the
-// warp has stored so far (lane-private columns of the output array)
+// warp has stored so far (lane-private columns of the output array).  Returns the new exponent; *factor is the
+// power of two the caller's running sum and maximum have to be scaled by.
 static __device__ __noinline__ double rescale_slice(double* mine, int k, int64_t lbase, int64_t run_pad, double eg,
-                                                    double a, double* sacc, double* pmax) {
+                                                    double a, double* factor) {
   const double en = slice_exponent(warp_max(a));
   const double d = eg - en;
   const double f = (d > -1100.0) ? scalbn(1.0, (int)d) : 0.0;
   for (int j = 0; j < k; ++j)
     if (lbase + (int64_t)j * 32 < run_pad) mine[j * 32] *= f;
-  *sacc *= f;
-  *pmax *= f;
+  *factor = f;
   return en;
+}
+
+// exp(x) for x <= 700 (0 below -700: such a weight is 1e-304 of its slice's largest).  The usual reduction
+// x = k ln 2 + r, |r| <= ln 2 / 2, and a degree-11 polynomial (< 1 ulp in all); the coefficients sit in constant memory
+// (literals would be materialised with two moves in front of every DFMA: the library exp issues ~50 instructions).
+static __constant__ double kExpCoef[16] = {
+    1.4426950408889634,        // log2 e
+    6755399441055744.0,        // 1.5 * 2^52: adding it rounds to an integer in the low word
+    6.93147180559945286227e-01,  // ln 2, high part
+    2.31904681384629955842e-17,  // ln 2, low part
+    // Chebyshev interpolant of exp on [-ln 2 / 2, ln 2 / 2], degree 11, monomial form (approximation error 7e-18)
+    2.510158556723003e-08, 2.7632488519513105e-07, 2.7557267919196622e-06, 2.480148595312923e-05,
+    0.00019841269859107206, 0.0013888888951800668, 0.008333333333334735, 0.04166666666649038,
+    0.16666666666666652, 0.5000000000000018, 1.0, 1.0};
+__device__ __forceinline__ double exp_le700(double x) {
+  const double t = fma(x, kExpCoef[0], kExpCoef[1]);
+  const int k = __double2loint(t);
+  const double kd = t - kExpCoef[1];
+  double r = fma(kd, -kExpCoef[2], x);
+  r = fma(kd, -kExpCoef[3], r);
+  double q = kExpCoef[4];
+#pragma unroll
+  for (int j = 5; j < 16; ++j) q = fma(q, r, kExpCoef[j]);
+  const double y = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+  return (x < -700.0) ? 0.0 : y;
 }
 
 // eval(i, run, lin) returns a with pdf_i = exp(a) * lin
@@ -558,13 +605,16 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
           eg = slice_exponent(warp_max(a));
           cg = eg * kLn2;
         } else if (__any_sync(0xffffffffu, a - cg > 600.0)) {
-          eg = rescale_slice(mine, k, lbase, sg.run_pad, eg, a, &sacc, &pmax);
+          double f;
+          eg = rescale_slice(mine, k, lbase, sg.run_pad, eg, a, &f);
           cg = eg * kLn2;
+          sacc *= f;
+          pmax *= f;
         }
-        const double p = (a > -INFINITY) ? exp(a - cg) * lin : 0.0;
+        const double p = exp_le700(a - cg) * lin;  // (a = -inf: 0)
         if (local < sg.run_pad) mine[k * 32] = p;  // (padding of a batched run: weight 0)
         sacc += p;
-        pmax = fmax(pmax, p);
+        pmax = (p > pmax) ? p : pmax;
       }
       const double wsum = warp_sum(sacc);
       const double wp = warp_max(pmax);
