@@ -15,6 +15,7 @@ Differences a pyRecEst user must know (all from BASELINE.json's north_star):
 from __future__ import annotations
 
 import copy
+import os
 import math
 
 import numpy as np
@@ -237,7 +238,7 @@ class AbstractParticleFilter:
             gather = self._padded_gather_target(p, x)
             # measured (T^3, 1e8): the von Mises sampler inside the fused kernel costs occupancy and
             # instruction-cache misses -- 5.7 ms fused against 1.9 (predict) + 2.8 (weight) as two kernels
-            fuse = p.rng_kind != L.RNG_VONMISES
+            fuse = p.rng_kind != L.RNG_VONMISES or os.environ.get("PFB_FUSE_VM") == "1"
             if fuse:
                 try:
                     # with a padded gather copy the compact predicted particles are dead (the resampling reads the

@@ -22,3 +22,14 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(scope="session")
+def config0_inputs():
+    """injected draws + measurements of BASELINE.json configs[0] (tests/golden/config0_inputs.py)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("config0_inputs", os.path.join(GOLDEN, "config0_inputs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.config0_draws()

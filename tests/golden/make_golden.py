@@ -15,6 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle.ref_harness import LAST, DrawQueue, import_reference, injected_draws  # noqa: E402
+sys.path.insert(0, HERE)
+from config0_inputs import config0_draws  # noqa: E402
 
 import_reference()
 from pyrecest.distributions import (  # noqa: E402
@@ -365,6 +367,34 @@ def evaluation_summary(seed=10):
         arrs[f"{tag}_runtimes"], arrs[f"{tag}_failed"] = runtimes, failed
         arrs[f"{tag}_summary"] = np.array([[s_["error_mean"], s_["error_std"], s_["time_mean"], s_["failure_rate"]] for s_ in summ])
     save("evaluation_summary", **arrs)
+
+
+def config0(N=10_000, T=100):
+    """BASELINE.json configs[0] at full size through the real reference (about a minute): EuclideanParticleFilter
+    (10^4, 2), constant velocity, Gaussian noise and likelihood, 100 steps.  Outputs kept: the estimate and an index
+    checksum of every step, the resampled indices of steps 0 / 49 / 99 and the final particle set."""
+    import time
+
+    c = config0_draws(N, T)
+    pf = EuclideanParticleFilter(N, 2)
+    q = DrawQueue(normals=np.concatenate([c["Z0"].ravel(), c["Z"].ravel()]), uniforms=c["U"])
+    est, idx_sum, idx_keep, d_keep = [], [], {}, {}
+    t0 = time.perf_counter()
+    with injected_draws(q):
+        pf.filter_state = GaussianDistribution(np.zeros(2), np.eye(2))
+        for t in range(T):
+            pf.predict_nonlinear(lambda x: x @ c["F"].T, GaussianDistribution(np.zeros(2), c["Q"]))
+            pf.update_identity(GaussianDistribution(np.zeros(2), c["R"]), c["zs"][t])
+            idx = LAST["choice_idx"]
+            idx_sum.append([int(idx.sum()), int((idx * np.arange(1, N + 1)).sum() % (2 ** 61 - 1))])
+            if t in (0, T // 2 - 1, T - 1):
+                idx_keep[f"idx_{t}"] = idx.astype(np.int32)
+                d_keep[f"d_{t}"] = pf.filter_state.d.copy()
+            est.append(pf.get_point_estimate().copy())
+    secs = time.perf_counter() - t0
+    print(f"reference: {N} particles x {T} steps in {secs:.1f} s = {N * T / secs:.3g} particle-steps/s")
+    save("config0", N=N, T=T, zs=c["zs"], est=np.stack(est), idx_sum=np.array(idx_sum, dtype=np.int64),
+         reference_seconds=secs, **idx_keep, **d_keep)
 
 
 if __name__ == "__main__":

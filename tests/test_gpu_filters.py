@@ -35,6 +35,29 @@ def test_euclid_cv_against_reference_run(golden):
             np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t], rtol=1e-12)
 
 
+def test_config0_full_size_against_reference_run(golden, config0_inputs):
+    """BASELINE.json configs[0] as specified (EuclideanParticleFilter(10^4, 2), constant velocity, Gaussian noise and
+    likelihood, 100 steps) through the public API with the draws the real reference consumed
+    (tests/golden/config0.npz): every resampled index over the 100 steps (checksums per step, full index vectors at
+    steps 0 / 49 / 99 through the particle sets), particles and estimates."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200.filters import EuclideanParticleFilter, LinearTransition
+
+    g, c = golden("config0"), config0_inputs
+    N, T = int(g["N"]), int(g["T"])
+    pf = EuclideanParticleFilter(N, 2)
+    with prandom.inject(normals=np.concatenate([c["Z0"].ravel(), c["Z"].ravel()]), uniforms=c["U"]):
+        pf.filter_state = GaussianDistribution(np.zeros(2), np.eye(2))
+        for t in range(T):
+            pf.predict_nonlinear(LinearTransition(c["F"]), GaussianDistribution(np.zeros(2), c["Q"]))
+            pf.update_identity(GaussianDistribution(np.zeros(2), c["R"]), c["zs"][t])
+            np.testing.assert_allclose(host(pf.get_point_estimate()), g["est"][t], rtol=1e-12, atol=1e-13, err_msg=str(t))
+            if f"d_{t}" in g:
+                # equal particle sets <=> equal index vectors (the predicted particles are distinct)
+                np.testing.assert_allclose(host(pf.filter_state.d), g[f"d_{t}"], rtol=1e-12, atol=1e-13, err_msg=str(t))
+
+
 def test_torus_t3_against_reference_run(golden):
     from pyrecest_b200 import random as prandom
     from pyrecest_b200.distributions import HypertoroidalWrappedNormalDistribution as HWN

@@ -31,6 +31,26 @@ def test_euclid_cv_matches_reference(golden):
         d = g["d_post"][t]
 
 
+def test_config0_full_size_matches_reference(golden, config0_inputs):
+    """BASELINE.json configs[0] as specified -- R^2 constant velocity, 10^4 particles, 100 steps -- run through the
+    real reference (tests/golden/make_golden.py config0): the oracle reproduces every resampled index, the particle
+    sets bit for bit and the estimates."""
+    g, c = golden("config0"), config0_inputs
+    N, T = int(g["N"]), int(g["T"])
+    assert np.array_equal(c["zs"], g["zs"])
+    d = O.gaussian_rows(c["Z0"], np.eye(2), np.zeros(2))
+    ar = np.arange(1, N + 1)
+    for t in range(T):
+        dp = O.predict_euclid(d, O.gaussian_rows(c["Z"][t], c["Q"], np.zeros(2)), F=c["F"])
+        lik = O.pdf_gauss(dp, c["zs"][t], c["R"])
+        d, wn, idx, _ = O.update_resample(dp, O.uniform_w(N), lik, c["U"][t])
+        assert [int(idx.sum()), int((idx * ar).sum() % (2 ** 61 - 1))] == g["idx_sum"][t].tolist(), t
+        if f"idx_{t}" in g:
+            assert np.array_equal(idx, g[f"idx_{t}"])
+            np.testing.assert_allclose(d, g[f"d_{t}"], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(O.mean_linear(d, wn), g["est"][t], rtol=1e-12, atol=1e-13)
+
+
 def test_torus_t3_matches_reference(golden):
     g = golden("torus_t3")
     d = np.mod(O.gaussian_rows(g["Z0"], g["C"], g["mu0"]), TWO_PI)
