@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 6
+#define PFB_ABI_VERSION 7
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -72,7 +72,8 @@ typedef struct {
    * `noise` pointer is ignored and the draws are generated in the kernel with Philox4x32-10 keyed by
    * (rng_seed, rng_offset, particle index) -- nothing is read from or written to HBM for them */
   int32_t rng_kind;          /* pfb_rng_kind */
-  int32_t reserved;
+  int32_t rng_vm_table_stride; /* doubles per strip table in rng_vm_table_dev: 0 or 2 * PFB_VM_STRIPS = strips only;
+                                * PFB_VM_TABLE_DOUBLES = strips followed by the quick-accept thresholds */
   uint64_t rng_seed;
   uint64_t rng_offset;
   double rng_kappa[PFB_MAXD]; /* PFB_RNG_VONMISES: concentration per dimension */
@@ -93,6 +94,13 @@ typedef struct {
  * table[2k] = start a_k, table[2k+1] = width w_k and *area = A for one concentration kappa >= 1e-8. */
 #define PFB_VM_STRIPS 4096
 int pfb_vm_strip_table(double kappa, double* table, double* area);
+/* Quick-accept thresholds of the same table (host code): thr[k] is a 32-bit integer such that an acceptance word
+ * v32 < thr[k] is accepted anywhere in strip k (the density is decreasing, so its value at the strip's far end bounds it
+ * from below) -- ~99 % of the attempts are decided by one integer compare, with exactly the outcome of the full test.
+ * A device table with thresholds is the 2 * PFB_VM_STRIPS doubles of pfb_vm_strip_table followed by the PFB_VM_STRIPS
+ * uint32 thresholds (PFB_VM_TABLE_DOUBLES doubles in all; pfb_predict_params.rng_vm_table_stride says which). */
+#define PFB_VM_TABLE_DOUBLES (2 * PFB_VM_STRIPS + PFB_VM_STRIPS / 2)
+int pfb_vm_strip_thresholds(double kappa, const double* table, double area, uint32_t* thr);
 
 typedef enum {
   PFB_RNG_NONE = 0,

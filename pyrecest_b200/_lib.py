@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 6
+ABI_VERSION = 7
 VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
@@ -40,7 +40,7 @@ class PredictParams(C.Structure):
         ("F", C.c_double * (PFB_MAXD * PFB_MAXD)), ("b", C.c_double * PFB_MAXD),
         ("A", C.c_double * (PFB_MAXD * PFB_MAXD)), ("mu_noise", C.c_double * PFB_MAXD),
         ("kappa", C.c_double), ("exp_m2k", C.c_double),
-        ("rng_kind", C.c_int32), ("reserved", C.c_int32), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
+        ("rng_kind", C.c_int32), ("rng_vm_table_stride", C.c_int32), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
         ("rng_kappa", C.c_double * PFB_MAXD), ("rng_vm_area", C.c_double * PFB_MAXD),
         ("rng_vm_table_dev", C.c_void_p), ("rng_vm_table_idx", C.c_int32 * PFB_MAXD),
         ("x_pad_out", C.c_void_p), ("x_pad_stride", C.c_int32), ("reserved2", C.c_int32),
@@ -58,6 +58,7 @@ class PredictParams(C.Structure):
                 self.rng_vm_table_idx[c] = distinct.index(k)
                 self.rng_vm_area[c] = vm_strip_table(k)[1]
         self.rng_vm_table_dev = tables.data_ptr() if tables is not None else None
+        self.rng_vm_table_stride = tables.shape[1] if tables is not None else 0
         self._vm_tables = tables  # keeps the device memory alive as long as the params
 
 
@@ -109,6 +110,7 @@ SIGNATURES = {
     "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),
     "pfb_vm_strip_table": (C.c_int, [C.c_double, _vp, _vp]),
+    "pfb_vm_strip_thresholds": (C.c_int, [C.c_double, _vp, C.c_double, _vp]),
 }
 
 _LIB = None
@@ -173,7 +175,13 @@ def vm_tables_on_device(kappas: tuple, device: str):
 
     key = (kappas, device)
     if key not in _VM_DEV:
-        host = np.stack([vm_strip_table(k)[0] for k in kappas])
+        rows = []
+        for k in kappas:  # strips, then the quick-accept thresholds (PFB_VM_TABLE_DOUBLES doubles per kappa)
+            table, area = vm_strip_table(k)
+            thr = np.zeros(VM_STRIPS, dtype=np.uint32)
+            check(lib().pfb_vm_strip_thresholds(k, table.ctypes.data, area, thr.ctypes.data))
+            rows.append(np.concatenate([table.reshape(-1), thr.view(np.float64)]))
+        host = np.stack(rows)
         _VM_DEV[key] = torch.as_tensor(host, device=device).contiguous()
         if len(_VM_DEV) > 64:
             _VM_DEV.pop(next(iter(_VM_DEV)))

@@ -195,10 +195,16 @@ __device__ __forceinline__ bool vonmises_attempt(const pfb_predict_params& p, in
     *th_out = 3.141592653589793 * u;  // uniform on the circle
     return true;
   }
-  const double2 t = __ldg(reinterpret_cast<const double2*>(p.rng_vm_table_dev) +
-                          (int64_t)p.rng_vm_table_idx[c] * PFB_VM_STRIPS + strip);
+  const int stride = p.rng_vm_table_stride > 0 ? p.rng_vm_table_stride : 2 * PFB_VM_STRIPS;
+  const double* tab = p.rng_vm_table_dev + (int64_t)p.rng_vm_table_idx[c] * stride;
+  const double2 t = __ldg(reinterpret_cast<const double2*>(tab) + strip);
   const double th = t.x + u * t.y;
   *th_out = th;
+  // quick accept: the acceptance word is below the strip's threshold (the density at the strip's far end bounds the
+  // density at th from below) -- the outcome of the full test, without evaluating the density
+  if (stride == PFB_VM_TABLE_DOUBLES &&
+      v32 < __ldg(reinterpret_cast<const uint32_t*>(tab + 2 * PFB_VM_STRIPS) + strip))
+    return true;
   const float kf = (float)kap;
   const float sh = __sinf(0.5f * (float)th);  // |error| < 5e-7 on [0, pi/2]: inside the margin below
   const float rhs = __expf(-2.0f * kf * sh * sh) * (float)t.y;

@@ -666,7 +666,7 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
 }
 
 template <typename T, int D, int KIND, bool SCALED>
-__global__ void __launch_bounds__(kThreads) loglik_kernel(pfb_lik_params L, Seg sg,
+__global__ void __launch_bounds__(kThreads, KIND == PFB_LIK_WN_MULTI ? 5 : 4) loglik_kernel(pfb_lik_params L, Seg sg,
                                                           const T* __restrict__ x,
                                                           const double* __restrict__ w_prev,
                                                           double* logw, double* stats,
@@ -740,7 +740,8 @@ static int check_predict(const pfb_predict_params* p) {
     for (int c = 0; c < p->dim; ++c) {
       if (!(p->rng_kappa[c] >= 0.0)) { set_error("von Mises kappa[%d] must be >= 0", c); return PFB_ERR_INVALID; }
       if (p->rng_kappa[c] < 1e-8) continue;
-      if (!p->rng_vm_table_dev || !(p->rng_vm_area[c] > 0.0) || p->rng_vm_table_idx[c] < 0 || p->rng_vm_table_idx[c] >= PFB_MAXD) {
+      if ((p->rng_vm_table_stride != 0 && p->rng_vm_table_stride != 2 * PFB_VM_STRIPS && p->rng_vm_table_stride != PFB_VM_TABLE_DOUBLES) ||
+          !p->rng_vm_table_dev || !(p->rng_vm_area[c] > 0.0) || p->rng_vm_table_idx[c] < 0 || p->rng_vm_table_idx[c] >= PFB_MAXD) {
         set_error("von Mises draws need the strip table of kappa[%d] (pfb_vm_strip_table) on the device", c);
         return PFB_ERR_INVALID;
       }
@@ -788,6 +789,18 @@ extern "C" int pfb_vm_strip_table(double kappa, double* table, double* area) {
   return PFB_OK;
 }
 
+
+extern "C" int pfb_vm_strip_thresholds(double kappa, const double* table, double area, uint32_t* thr) {
+  if (!table || !thr || !(area > 0.0) || !(kappa >= 1e-8)) { set_error("NULL table / thresholds, or no strip table for this kappa"); return PFB_ERR_INVALID; }
+  for (int k = 0; k < PFB_VM_STRIPS; ++k) {
+    const double end = table[2 * k] + table[2 * k + 1];
+    const double sh = sin(0.5 * end);
+    // v32 < thr  =>  (v32 + 1/2) 2^-32 A < g(end) w (1 - 1e-9) <= g(t) w for every t of the strip, rounding included
+    const double r = exp(-2.0 * kappa * sh * sh) * table[2 * k + 1] / area * 4294967296.0 * (1.0 - 1e-9) - 2.0;
+    thr[k] = r <= 0.0 ? 0u : (r >= 4294967295.0 ? 4294967295u : (uint32_t)r);
+  }
+  return PFB_OK;
+}
 #endif
 
 static int check_lik(const pfb_lik_params* L, int dim) {
@@ -838,7 +851,6 @@ static size_t lik_smem(const pfb_lik_params* L) {
 }  // namespace pfb
 
 namespace pfb {
-static int tile_grid_seg(const Seg& sg) { return tile_grid(sg.n_runs * sg.tpr * (int64_t)kScanTile); }
 
 // One wave of CTAs for the tile loops: as many as are resident at once (the kernel's own occupancy), so that no
 // CTA starts when the others are half done.  Cached per kernel.
@@ -900,18 +912,23 @@ int predict_launch(const pfb_predict_params* p, int64_t n, const void* x_in, voi
 template <typename T>
 int loglik_launch(const pfb_lik_params* lik, Seg sg, const void* x, const double* w_prev, double* logw, double* stats,
                   Workspace W, cudaStream_t st) {
-  const int grid = tile_grid_seg(sg);
   const size_t sm = lik_smem(lik);
-#define PFB_LOGLIK_LAUNCH(S)                                                                                          \
-  if (lik->kind == PFB_LIK_WN_1D) {                                                                                    \
-    loglik_kernel<T, 1, PFB_LIK_WN_1D, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);   \
-  } else if (lik->kind == PFB_LIK_VM) {                                                                                \
-    loglik_kernel<T, 1, PFB_LIK_VM, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);      \
-  } else {                                                                                                             \
-    PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, (loglik_kernel<T, D, KIND, S><<<grid, kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W)))); \
+#define PFB_LOGLIK_ONE(DD, KK, S)                                                                         \
+  {                                                                                                       \
+    auto k = loglik_kernel<T, DD, KK, S>;                                                                 \
+    k<<<one_wave_grid(k, sm, sg), kThreads, sm, st>>>(*lik, sg, (const T*)x, w_prev, logw, stats, W);     \
+  }
+#define PFB_LOGLIK_LAUNCH(S)                                                                  \
+  if (lik->kind == PFB_LIK_WN_1D) {                                                            \
+    PFB_LOGLIK_ONE(1, PFB_LIK_WN_1D, S)                                                        \
+  } else if (lik->kind == PFB_LIK_VM) {                                                        \
+    PFB_LOGLIK_ONE(1, PFB_LIK_VM, S)                                                           \
+  } else {                                                                                     \
+    PFB_DISPATCH_DIM(lik->dim, PFB_DISPATCH_KIND(lik->kind, PFB_LOGLIK_ONE(D, KIND, S)));      \
   }
   if (lik->out_format == PFB_WEIGHTS_SCALED) { PFB_LOGLIK_LAUNCH(true) } else { PFB_LOGLIK_LAUNCH(false) }
 #undef PFB_LOGLIK_LAUNCH
+#undef PFB_LOGLIK_ONE
   return PFB_OK;
 }
 
