@@ -582,9 +582,32 @@ __global__ void __launch_bounds__(kThreads) scan_maps_kernel(int64_t n, const do
 // walks the binades inside one (hard) tile starting from the exact value `cur`; fills c[] and returns the
 // exact value at the end of the tile (identical in every thread)
 __device__ __forceinline__ double hard_tile_walk(const double (&p)[kItems], int cnt, double cur, double (&c)[kItems],
-                                                 long long* s_ll, int* s_int, double* s_cur) {
+                                                 long long* s_ll, int* s_int, double* s_cur, bool lead) {
   const int tb = threadIdx.x * kItems;
   int pos = 0;
+  if (lead) {
+    // (block-uniform) first tile of a run: the running sum starts at 0 and doubles every few elements, a binade --
+    // one CTA-wide pass of the loop below -- each.  The first 32 * kItems elements sit in warp 0's registers: it walks
+    // them with plain sequential adds, lane after lane (256 dependent adds, ~1.5 us), and the binade loop takes over
+    // where the crossings have become sparse.
+    if (threadIdx.x < 32) {
+      double v = cur;
+      for (int l = 0; l < 32; ++l) {
+        if ((int)threadIdx.x == l) {
+#pragma unroll
+          for (int k = 0; k < kItems; ++k)
+            if (tb + k < cnt) { v = __dadd_rn(v, p[k]); c[k] = v; }
+        }
+        v = __shfl_sync(0xffffffffu, v, l);
+      }
+      if (threadIdx.x == 0) *s_cur = v;
+    }
+    __syncthreads();
+    cur = *s_cur;
+    pos = 32 * kItems;
+    __syncthreads();
+    if (pos >= cnt) return cur;
+  }
   while (true) {
     if (cur == 0.0) {  // leading zeros: 0 + p = p exactly
       int mine = 0x7fffffff;
@@ -677,7 +700,7 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
         load_tile<IN>(in, n, t, IN != kInW ? ts.tmax[t] : 0.0, p, wpart);
         const int64_t left = n - t * kScanTile;
         const int cnt = (int)(left < kScanTile ? left : kScanTile);
-        cur = hard_tile_walk(p, cnt, cur, c, s_ll, s_int, &s_cur);
+        cur = hard_tile_walk(p, cnt, cur, c, s_ll, s_int, &s_cur, t == t_begin);
         store_tile(cdf, n, t, c);
         if (t * kScanTile + cnt == n && threadIdx.x == 0) stats[PFB_STAT_TOTAL] = cur;
         ++t;
