@@ -227,6 +227,14 @@ class WrappedNormalDistribution(HypertoroidalWrappedNormalDistribution):
     def trigonometric_moment(self, n):
         return np.exp(1j * n * self.mu - n**2 * self.sigma**2 / 2)
 
+    @staticmethod
+    def from_moment(m):
+        """:186-190  the wrapped normal with first trigonometric moment m."""
+        m = complex(_host(m).reshape(-1)[0]) if not isinstance(m, complex) else m
+        mu = np.mod(np.angle(m), 2.0 * np.pi)
+        sigma = np.sqrt(-2.0 * np.log(np.abs(m)))
+        return WrappedNormalDistribution(np.array(mu), np.array(sigma))
+
 
 WNDistribution = WrappedNormalDistribution
 
@@ -526,8 +534,17 @@ class AbstractDiracDistribution:
         cdf = torch.empty(N, dtype=torch.float64, device=x.device)
         w = self._w
         eng.scan(cdf, w=w.contiguous(), exact=exact)
-        out = torch.empty((n, x.shape[1]), dtype=x.dtype, device=x.device)
         src = prandom.source()
+        if x.shape[1] > L.PFB_MAXD:
+            # records wider than the gather kernels' PFB_MAXD components (SE(3): 7): the kernel yields the indices,
+            # the rows are picked by torch
+            idx = torch.empty(n, dtype=torch.int64, device=x.device)
+            if src.fused:
+                eng.resample_rng(cdf, src.seed, src.next_offset(), None, None, n, 1, idx_out=idx)
+            else:
+                eng.resample(cdf, src.uniforms((n,), x.device), None, None, n, 1, idx_out=idx)
+            return x.index_select(0, idx)
+        out = torch.empty((n, x.shape[1]), dtype=x.dtype, device=x.device)
         if src.fused:
             eng.resample_rng(cdf, src.seed, src.next_offset(), x, out, n, x.shape[1])
         else:
@@ -673,6 +690,12 @@ class CircularDiracDistribution(HypertoroidalDiracDistribution):
         HypertoroidalDiracDistribution.__init__(self, d_t, w, dim=1)
         assert w is None or tuple(d_t.squeeze().shape) == tuple(self._w.shape), "The shapes of d and w should match."
 
+    def to_wn(self):
+        """circle/abstract_circular_distribution.py:58-68: wrapped normal with the same first trigonometric moment
+        (the moment is one launch of the moment kernel; two doubles come back)."""
+        m = self.trigonometric_moment(1)
+        return WrappedNormalDistribution.from_moment(complex(m.reshape(-1)[0].item()))
+
 
 class ToroidalDiracDistribution(HypertoroidalDiracDistribution):
     """hypertorus/toroidal_dirac_distribution.py:9-55."""
@@ -806,3 +829,61 @@ class HypersphericalDiracDistribution(AbstractHypersphereSubsetDiracDistribution
     def mean(self):
         """abstract_hyperspherical_distribution.py:37-45."""
         return self.mean_direction()
+
+
+class LinHypersphereCartProdDiracDistribution(LinBoundedCartProdDiracDistribution):
+    """cart_prod/lin_hypersphere_cart_prod_dirac_distribution.py:11-25 -- a unit vector of bound_dim + 1 components
+    first, then linear components.  The records can be wider than the moment / gather kernels' PFB_MAXD (SE(3): 7), so
+    every moment is taken on a marginal copy, as the reference does."""
+
+    _manifold = "lin_hypersphere"
+
+    def __init__(self, bound_dim, d, w=None):
+        d_t = _as_device_tensor(d)
+        nrm = torch.linalg.norm(d_t[:, : int(bound_dim) + 1], dim=-1)
+        assert float((nrm - 1.0).abs().max()) < 1e-5, "The hypersphere ssubset part of d must be normalized"
+        AbstractDiracDistribution.__init__(self, d, w)
+        self.bound_dim = int(bound_dim)
+        self.lin_dim = self._d.shape[1] - self.bound_dim - 1
+        self.dim = self.bound_dim + self.lin_dim
+        self.input_dim = self.dim + 1
+
+    def marginalize_periodic(self):
+        """lin_bounded_cart_prod_dirac_distribution.py:17-20: d[:, bound_dim:] -- for a hypersphere part of
+        bound_dim + 1 components this keeps the unit vector's LAST component next to the linear ones; the reference
+        slices there, and so do linear_mean() / linear_covariance() built on it."""
+        return LinearDiracDistribution(self._d[:, self.bound_dim:].contiguous(), None if self._uniform else self._w.clone())
+
+    def linear_mean(self):
+        return self.marginalize_periodic().mean()
+
+    def linear_covariance(self, approximate_mean=False):
+        if approximate_mean:
+            warnings.warn("Formula for mean is trivial, so approximate_mean is ignored.")
+        return self.marginalize_periodic().covariance()
+
+    def marginalize_linear(self):
+        return HyperhemisphericalDiracDistribution(self._d[:, : self.bound_dim + 1].contiguous(),
+                                                   None if self._uniform else self._w.clone())
+
+    def hybrid_mean(self):
+        """mean axis of the unit-vector part, then the mean of the linear components proper.  PARITY UNPINNED: the
+        reference's hybrid_mean() raises ValueError for these classes (its hemispherical mean_direction is broken)."""
+        lin = LinearDiracDistribution(self._d[:, self.bound_dim + 1:].contiguous(), None if self._uniform else self._w.clone())
+        return torch.cat((self.marginalize_linear().mean(), lin.mean()))
+
+
+class SE3DiracDistribution(LinHypersphereCartProdDiracDistribution):
+    """se3_dirac_distribution.py:13-48: (N, 7) records, unit quaternion (last component >= 0 by convention) first,
+    translation last."""
+
+    def __init__(self, d, w=None):
+        LinHypersphereCartProdDiracDistribution.__init__(self, 3, d, w)
+
+    def mean(self):
+        return self.hybrid_mean()
+
+    @staticmethod
+    def from_distribution(distribution, n_particles):
+        assert isinstance(n_particles, int) and n_particles > 0, "n_particles must be a positive integer"
+        return SE3DiracDistribution(distribution.sample(n_particles))

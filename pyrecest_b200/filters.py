@@ -32,6 +32,7 @@ from .distributions import (
     HypersphericalDiracDistribution,
     HypertoroidalDiracDistribution,
     LinearDiracDistribution,
+    WrappedNormalDistribution,
     _as_device_tensor,
     _default_device,
 )
@@ -590,3 +591,42 @@ class HyperhemisphericalParticleFilter(HypersphericalParticleFilter):
 
     def get_point_estimate(self):
         return self.filter_state.mean_axis()
+
+
+# -------------------------------------------------------------------------------------------------
+class WrappedNormalFilter:
+    """wrapped_normal_filter.py:10-32: a circular filter whose state is a wrapped normal; the particle-based update
+    (update_nonlinear_particle) runs on the device path: samples of the state, CircularDiracDistribution.reweigh,
+    moment matching."""
+
+    def __init__(self, wn=None):
+        self._filter_state = wn if wn is not None else WrappedNormalDistribution(np.array(0.0), np.array(1.0))
+
+    @property
+    def filter_state(self):
+        return self._filter_state
+
+    @filter_state.setter
+    def filter_state(self, new_state):
+        if not hasattr(new_state, "sigma"):
+            raise ValueError("the state of a WrappedNormalFilter is a WrappedNormalDistribution")
+        self._filter_state = copy.deepcopy(new_state)
+
+    def predict_identity(self, wn_sys):
+        """:18-20  convolution of two wrapped normals: means add (mod 2 pi), variances add."""
+        a, b = self._filter_state, wn_sys
+        mu = np.mod(float(np.asarray(a.mu).reshape(-1)[0]) + float(np.asarray(b.mu).reshape(-1)[0]), 2.0 * math.pi)
+        sig = math.sqrt(float(np.asarray(a.sigma).reshape(-1)[0]) ** 2 + float(np.asarray(b.sigma).reshape(-1)[0]) ** 2)
+        self._filter_state = WrappedNormalDistribution(np.array(mu), np.array(sig))
+
+    def update_nonlinear_particle(self, likelihood, z, n=100):
+        """:27-32  n = 100 samples of the state, reweighed by likelihood(z, .), matched by a wrapped normal.
+        `likelihood` is a registry distribution (the reference's callable likelihood(z, x) = its pdf centred at z,
+        evaluated at x); anything else is rejected, nothing is evaluated on the CPU."""
+        dist = copy.deepcopy(R.as_distribution(likelihood)).set_mode(R._np(z))
+        wd = CircularDiracDistribution(self._filter_state.sample(n))
+        self._filter_state = wd.reweigh(dist).to_wn()
+
+    def get_point_estimate(self):
+        """abstract_circular_filter / abstract_filter: the mean direction of the state."""
+        return float(np.asarray(self._filter_state.mu).reshape(-1)[0])

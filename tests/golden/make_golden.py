@@ -397,6 +397,52 @@ def config0(N=10_000, T=100):
          reference_seconds=secs, **idx_keep, **d_keep)
 
 
+def se3_and_wn_filter(seed=11):
+    """SURVEY 8(f) rank 4, the rest: SE3DiracDistribution (unit quaternion part first, then the translation) and
+    WrappedNormalFilter.update_nonlinear_particle.  What the reference can do is recorded: the marginals,
+    linear_mean / linear_covariance (taken on d[:, bound_dim:] = the LAST FOUR columns -- the reference slices at
+    bound_dim = 3 although the quaternion has four components; a drop-in has to return the same), reweigh and sample
+    of the 7-component records.  hybrid_mean() / mean() raise ValueError in the reference (the hemispherical mean
+    direction is broken there): parity unpinned."""
+    from pyrecest.distributions.se3_dirac_distribution import SE3DiracDistribution
+    from pyrecest.filters.wrapped_normal_filter import WrappedNormalFilter
+
+    rng = np.random.default_rng(seed)
+    N = 700
+    q = rng.standard_normal((N, 4)) * np.array([0.3, 0.3, 0.3, 1.0])
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[q[:, 3] < 0] *= -1.0
+    d = np.hstack([q, rng.standard_normal((N, 3)) * 2.0 + np.array([1.0, -2.0, 0.5])])
+    w = rng.random(N)
+    w /= w.sum()
+    s3 = SE3DiracDistribution(d, w)
+    arrs = {"se3_d": d, "se3_w": w, "se3_linear_mean": np.asarray(s3.linear_mean()),
+            "se3_linear_cov": np.asarray(s3.linear_covariance()),
+            "se3_quat_moment": np.asarray(s3.marginalize_linear().moment()),
+            "se3_periodic_marginal_mean": np.asarray(s3.marginalize_periodic().mean())}
+    lik = np.exp(-0.5 * np.sum((d[:, 4:] - 1.0) ** 2, axis=1)) * (1.5 + d[:, 3])
+    arrs["se3_lik"] = lik
+    rw = s3.reweigh(lambda x: np.exp(-0.5 * np.sum((x[:, 4:] - 1.0) ** 2, axis=1)) * (1.5 + x[:, 3]))
+    arrs["se3_reweighed_w"] = rw.w
+    u = rng.random(400)
+    with injected_draws(DrawQueue(uniforms=u)):
+        arrs["se3_sample"] = rw.sample(400)
+        arrs["se3_sample_idx"] = LAST["choice_idx"].copy()
+    arrs["se3_sample_u"] = u
+    # WrappedNormalFilter.update_nonlinear_particle (wrapped_normal_filter.py:27-32): 100 samples of the state,
+    # reweigh by likelihood(z, .), moment-match a wrapped normal.  The samples are injected (the method draws them
+    # from numpy's global stream).
+    for tag, (mu0, sig0, z, kap) in {"wnf_a": (1.0, 0.8, 2.0, 2.0), "wnf_b": (5.9, 0.4, 0.3, 6.0)}.items():
+        f = WrappedNormalFilter(WrappedNormalDistribution(np.array(mu0), np.array(sig0)))
+        smp = np.mod(mu0 + sig0 * rng.standard_normal(100), 2 * np.pi)
+        f.filter_state.sample = lambda n, smp=smp: smp[:n]
+        f.update_nonlinear_particle(lambda zz, x, kap=kap: VonMisesDistribution(np.array(zz), kap).pdf(x), z)
+        arrs[f"{tag}_in"] = np.array([mu0, sig0, z, kap])
+        arrs[f"{tag}_samples"] = smp
+        arrs[f"{tag}_out"] = np.array([float(f.filter_state.mu), float(f.filter_state.sigma)])
+    save("se3_and_wn_filter", **arrs)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # regenerate only the named fixtures
         for name in sys.argv[1:]:

@@ -504,3 +504,58 @@ def test_association_likelihood_reference_known_answers():
     mu = np.array([0.0, 0.6, 0.8])
     ref = float(np.mean(O.likelihood("vmf", x, {"mu": mu, "kappa": 3.0})))
     np.testing.assert_allclose(float(sp.association_likelihood(VonMisesFisherDistribution(mu, 3.0))), ref, rtol=1e-12)
+
+
+def test_se3_dirac_against_reference_run(golden):
+    """SE3DiracDistribution (7-component records: unit quaternion, translation): the marginals, linear_mean /
+    linear_covariance (on the reference's d[:, bound_dim:] slice), reweigh with caller-computed likelihood values,
+    and sample with the injected uniforms -- indices bit for bit (tests/golden/se3_and_wn_filter.npz)."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HyperhemisphericalDiracDistribution, LinearDiracDistribution, SE3DiracDistribution
+
+    g = golden("se3_and_wn_filter")
+    s3 = SE3DiracDistribution(g["se3_d"], g["se3_w"])
+    assert (s3.dim, s3.bound_dim, s3.lin_dim, s3.input_dim) == (6, 3, 3, 7)
+    np.testing.assert_allclose(host(s3.linear_mean()), g["se3_linear_mean"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(host(s3.linear_covariance()), g["se3_linear_cov"], rtol=1e-11, atol=1e-13)
+    ml = s3.marginalize_linear()
+    assert isinstance(ml, HyperhemisphericalDiracDistribution) and ml.d.shape == (700, 4)
+    np.testing.assert_allclose(host(ml.moment()), g["se3_quat_moment"], rtol=1e-12, atol=1e-14)
+    mp = s3.marginalize_periodic()
+    assert isinstance(mp, LinearDiracDistribution)
+    np.testing.assert_allclose(host(mp.mean()), g["se3_periodic_marginal_mean"], rtol=1e-12, atol=1e-14)
+    rw = s3.reweigh(g["se3_lik"])
+    np.testing.assert_allclose(host(rw.w), g["se3_reweighed_w"], rtol=1e-12)
+    with prandom.inject(uniforms=g["se3_sample_u"]):
+        smp = host(rw.sample(400))
+    assert np.array_equal(smp, g["se3_d"][g["se3_sample_idx"]])
+    assert np.array_equal(smp, g["se3_sample"])
+    # hybrid_mean / mean: mean axis of the quaternion part + mean translation (the reference raises here)
+    hm = host(s3.mean())
+    assert hm.shape == (7,) and abs(np.linalg.norm(hm[:4]) - 1.0) < 1e-12 and hm[3] >= 0
+    np.testing.assert_allclose(hm[4:], g["se3_w"] @ g["se3_d"][:, 4:], rtol=1e-12)
+    with pytest.raises(AssertionError):
+        SE3DiracDistribution(np.ones((4, 7)))
+
+
+@pytest.mark.parametrize("tag", ["wnf_a", "wnf_b"])
+def test_wrapped_normal_filter_particle_update_against_reference_run(golden, tag):
+    """WrappedNormalFilter.update_nonlinear_particle (wrapped_normal_filter.py:27-32) with the reference's 100
+    state samples injected: the moment-matched wrapped normal equals the reference's."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import VonMisesDistribution, WrappedNormalDistribution
+    from pyrecest_b200.filters import WrappedNormalFilter
+
+    g = golden("se3_and_wn_filter")
+    mu0, sig0, z, kap = g[f"{tag}_in"]
+    f = WrappedNormalFilter(WrappedNormalDistribution(np.array(mu0), np.array(sig0)))
+    smp = g[f"{tag}_samples"]
+    f.filter_state.sample = lambda n: torch.as_tensor(smp[:n], device="cuda:0")
+    f.update_nonlinear_particle(VonMisesDistribution(np.array(0.0), kap), z)
+    np.testing.assert_allclose([float(f.filter_state.mu), float(np.asarray(f.filter_state.sigma).reshape(-1)[0])], g[f"{tag}_out"], rtol=1e-11)
+    assert f.get_point_estimate() == pytest.approx(g[f"{tag}_out"][0], rel=1e-11)
+    with pytest.raises(NotImplementedError):
+        f.update_nonlinear_particle(lambda zz, x: x, z)
+    f.predict_identity(WrappedNormalDistribution(np.array(6.0), np.array(0.3)))
+    assert float(f.filter_state.mu) == pytest.approx((g[f"{tag}_out"][0] + 6.0) % (2 * np.pi), rel=1e-12)
+    assert float(np.asarray(f.filter_state.sigma).reshape(-1)[0]) == pytest.approx(math.hypot(g[f"{tag}_out"][1], 0.3), rel=1e-12)

@@ -209,3 +209,24 @@ def test_evaluation_summary_against_reference_run(golden, tag, manifold):
     dev, rows = O.summarize(manifold, g[f"{tag}_est"], g[f"{tag}_gt"], g[f"{tag}_runtimes"], g[f"{tag}_failed"])
     np.testing.assert_allclose(dev, g[f"{tag}_dev"], rtol=1e-13, atol=1e-15)
     np.testing.assert_allclose(rows, g[f"{tag}_summary"], rtol=1e-12)
+
+
+def test_se3_dirac_and_wn_filter_update_against_reference_run(golden):
+    """the oracle's generic Dirac pieces on the reference's SE(3) run (7-component records) and its
+    WrappedNormalFilter.update_nonlinear_particle run"""
+    g = golden("se3_and_wn_filter")
+    d, w = g["se3_d"], g["se3_w"]
+    np.testing.assert_allclose(O.mean_linear(d[:, 3:], w), g["se3_linear_mean"], rtol=1e-13)   # the reference's slice
+    np.testing.assert_allclose(O.covariance_linear(d[:, 3:], w), g["se3_linear_cov"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.scatter(d[:, :4], w), g["se3_quat_moment"], rtol=1e-13, atol=1e-15)
+    wp = O.reweigh(w, g["se3_lik"])
+    np.testing.assert_allclose(wp, g["se3_reweighed_w"], rtol=1e-14)
+    idx = O.multinomial_indices(g["se3_reweighed_w"], g["se3_sample_u"])
+    assert np.array_equal(idx, g["se3_sample_idx"]) and np.array_equal(d[idx], g["se3_sample"])
+    for tag in ("wnf_a", "wnf_b"):
+        mu0, sig0, z, kap = g[f"{tag}_in"]
+        x = g[f"{tag}_samples"]
+        wn = O.reweigh(O.uniform_w(x.shape[0]), O.pdf_vm(x, z, kap))
+        m = O.trig_moment(x[:, None], wn)[0]
+        out = [np.mod(np.angle(m), TWO_PI), np.sqrt(-2.0 * np.log(np.abs(m)))]
+        np.testing.assert_allclose(out, g[f"{tag}_out"], rtol=1e-12)
