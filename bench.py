@@ -518,7 +518,9 @@ def sharded_block(args, world, rank, dev, steps, warmup, n=None):
         return float(ms)
 
     out = {"workload": f"{name}: {desc}", "particles_per_gpu": n, "particles_total": n * world, "resampling": "systematic (global)",
-           "scan": "sequential-exact per shard against the global shift", "plan": "device-side (no host read of the shard totals)"}
+           "scan": "sequential-exact per shard against the global shift", "plan": "device-side (no host read of the shard totals)",
+           "exchange": "pull: every rank produces its own slots and reads remote sources (CDF shard + particles, peer-mapped "
+                       "symmetric memory) over NVLink inside the resampling kernel; all stores local"}
     # ---- the sharded filter, even scenario
     pf = ShardedParticleFilter(manifold, n * world, D)
     pf.filter_state = prior
@@ -530,7 +532,7 @@ def sharded_block(args, world, rank, dev, steps, warmup, n=None):
     dist.all_reduce(tr)
     out["even"] = {"ms_per_step": even_ms, "value": world * n / (even_ms * 1e-3),
                    "offspring_crossing_nvlink_frac": float(tr[1] / tr[0]),
-                   "peer_store_bytes_per_step": int(tr[1]) * 8 * D, "scatter_kernel_ms": sc_ms}
+                   "remote_offspring_bytes_per_step": int(tr[1]) * 8 * D, "resample_kernel_ms": sc_ms}
     # ---- skewed scenario: shard g sits 1.5 g sigma from the measurement; re-installed before every step (untimed)
     x_even = pf.filter_state.d.clone()
     x_skew = x_even.clone()
@@ -548,9 +550,10 @@ def sharded_block(args, world, rank, dev, steps, warmup, n=None):
     dist.all_reduce(scat, op=dist.ReduceOp.MAX)
     out["skewed"] = {"ms_per_step": skew_ms, "value": world * n / (skew_ms * 1e-3),
                      "offspring_crossing_nvlink_frac": float(tr[1] / tr[0]),
-                     "peer_store_bytes_per_step": int(tr[1]) * 8 * D,
-                     "busiest_rank_peer_store_bytes": int(mx[0]) * 8 * D, "scatter_kernel_ms": float(scat),
-                     "busiest_rank_nvlink_store_gbs": int(mx[0]) * 8 * D / (float(scat) * 1e-3) / 1e9 if float(scat) > 0 else None,
+                     "remote_offspring_bytes_per_step": int(tr[1]) * 8 * D,
+                     "busiest_rank_remote_offspring_bytes": int(mx[0]) * 8 * D, "resample_kernel_ms": float(scat),
+                     # (an upper bound of the bytes read over NVLink: a remote source with k offspring is read once)
+                     "busiest_rank_nvlink_read_gbs_upper": int(mx[0]) * 8 * D / (float(scat) * 1e-3) / 1e9 if float(scat) > 0 else None,
                      "nvlink_peak_gbs_per_direction": 770.0,
                      "note": "particle set re-installed (untimed) before every timed step; " + str(skew_steps) + " steps"}
     # ---- time in the step's three small collectives, back to back on the stream (not overlapped with anything)
@@ -572,7 +575,7 @@ def sharded_block(args, world, rank, dev, steps, warmup, n=None):
     coll = torch.tensor([t0.elapsed_time(t1) / 10], dtype=torch.float64, device=dev)
     dist.all_reduce(coll, op=dist.ReduceOp.MAX)
     out["collectives_ms_per_step"] = float(coll)
-    out["collectives"] = "all_reduce(MAX, 1 double) + all_gather(1 double per rank) + all_reduce(SUM, D doubles); offspring move by peer stores inside the scatter kernel, no all_to_all"
+    out["collectives"] = "all_reduce(MAX, 1 double) + all_gather(1 double per rank) + all_reduce(SUM, D doubles); particles move by peer loads inside the resampling kernel, no all_to_all"
     del pf, x_skew
     torch.cuda.empty_cache()
     # ---- anchor: the same filter with a one-rank group, on every GPU at once
@@ -828,6 +831,12 @@ def main():
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
     ap.add_argument("--resampling", default="multinomial_sorted", choices=["multinomial", "multinomial_sorted", "systematic"])
     args = ap.parse_args()
+    # stdout carries ONE JSON line: libraries that print to file descriptor 1 from native code (NCCL's version banner at
+    # communicator init) are sent to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         args.no_cpu = True  # the CPU baseline is reported at N = 1 only
     if args.warmup < 3 and args.impl == "ours":
@@ -844,6 +853,7 @@ def main():
         run_mc(args)
     else:
         run_gpu(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define PFB_MAXD 6           /* max stored components per particle (R^d, T^d: d; S^d: d+1) */
-#define PFB_ABI_VERSION 7
+#define PFB_ABI_VERSION 8
 
 typedef enum { PFB_F64 = 0, PFB_F32 = 1 } pfb_dtype;
 
@@ -310,6 +310,19 @@ int pfb_resample_sharded_dev(pfb_dtype dtype, int32_t dim, int64_t n, const doub
                              int32_t world, int32_t rank, double u0, void* const* peer_out, const void* x_in,
                              int32_t est_kind, double* est_sums, double* status, void* ws, int64_t ws_bytes,
                              void* stream);
+/* The same resampling in PULL form: this rank produces exactly its own n output slots (x_out, local) and reads the
+ * sources they come from wherever they live.  peer_cdf[r] / peer_x[r] (HOST arrays of `world` pointers): the CDF
+ * shard (n doubles, from pfb_scan_cdf against the global shift) and the (n, dim) particle buffer of rank r -- its
+ * own for r == rank, peer-mapped otherwise (remote sources are read over NVLink with ordinary loads; every store is
+ * local).  The work per rank is its n slots whatever the weights, where the push form makes the owner of the heavy
+ * sources produce all their offspring.  The caller must order the peers' scans before this call (the all-gather of
+ * the totals does) and a collective after it before any rank overwrites a buffer a peer may still be reading (the
+ * all-reduce of est_sums does).  est_sums: SUMS over this rank's n offspring.  Identical offspring to
+ * pfb_resample_sharded_dev, slot for slot. */
+int pfb_resample_sharded_pull(pfb_dtype dtype, int32_t dim, int64_t n, const double* const* peer_cdf,
+                              const void* const* peer_x, const double* totals_dev, int32_t world, int32_t rank,
+                              double u0, void* x_out, int32_t est_kind, double* est_sums, double* status, void* ws,
+                              int64_t ws_bytes, void* stream);
 /* fill `out` (n doubles) with the uniforms pfb_resample_rng would use (tests, debugging) */
 int pfb_rng_uniform(int64_t n, uint64_t rng_seed, uint64_t rng_offset, double* out, void* stream);
 

@@ -175,6 +175,17 @@ class Engine:
                                                   _ptr(status), ws, wsb, _stream(self.device)))
         self.launches += 2
 
+    def resample_sharded_pull(self, cdf_ptrs, x_ptrs, totals_dev, world, rank, u0, x_out, n, dim, est_kind, est_sums, status):
+        """pull-form sharded resampling (pfb_resample_sharded_pull): cdf_ptrs / x_ptrs = raw device pointers of every
+        rank's CDF shard and particle buffer (peer-mapped for the other ranks); the output is local"""
+        ws, wsb = self._ensure_ws(0)
+        ca = (C.c_void_p * world)(*[C.c_void_p(p) for p in cdf_ptrs])
+        xa = (C.c_void_p * world)(*[C.c_void_p(p) for p in x_ptrs])
+        L.check(self.lib.pfb_resample_sharded_pull(_DT[x_out.dtype], dim, n, ca, xa, _ptr(totals_dev), world, rank, float(u0),
+                                                   _ptr(x_out), est_kind, _ptr(est_sums), _ptr(status), ws, wsb,
+                                                   _stream(self.device)))
+        self.launches += 3
+
     def rng_uniform(self, out, seed, offset):
         L.check(self.lib.pfb_rng_uniform(out.numel(), seed, offset, _ptr(out), _stream(self.device)))
         self.launches += 1

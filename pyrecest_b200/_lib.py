@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6
-ABI_VERSION = 7
+ABI_VERSION = 8
 VM_STRIPS = 4096
 RNG_NONE, RNG_NORMAL, RNG_VONMISES, RNG_VMF = range(4)
 PFB_F64, PFB_F32 = 0, 1
@@ -106,6 +106,8 @@ SIGNATURES = {
                                        _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "pfb_resample_sharded_dev": (C.c_int, [C.c_int, _i32, _i64, _vp, _vp, _i32, _i32, C.c_double, C.POINTER(C.c_void_p), _vp, _i32,
                                            _vp, _vp, _vp, _i64, _vp]),
+    "pfb_resample_sharded_pull": (C.c_int, [C.c_int, _i32, _i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _i32, _i32,
+                                            C.c_double, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_rng_uniform": (C.c_int, [_i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "pfb_moments": (C.c_int, [_i32, C.c_int, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "pfb_wrap_2pi": (C.c_int, [C.c_int, _i64, _vp, _vp, _vp]),

@@ -1168,6 +1168,253 @@ static int launch_sharded_dev(int64_t n, const double* cdf, const double* totals
   return PFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sharded filter, PULL form: every rank produces exactly its own n_loc output slots, reading the sources they come
+// from wherever they live -- the CDF shard and the particle buffer of every rank are peer-mapped (torch symmetric
+// memory), remote ones are read over NVLink with ordinary loads, all stores are local.  The push form above makes
+// the rank that OWNS the heavy sources produce all their offspring: with the weight concentrated in one shard that
+// rank does world x the work while the others idle.  Here the work per rank is its n_loc slots whatever the
+// weights; what the skew costs is the NVLink read of the remote sources, inside the same kernel as the local work.
+//   sharded_pull_plan_kernel   one warp per source shard: the range [a_s, b_s) of shard s's sources whose offspring
+//                              intersect this rank's slots (two bisections on the peer's CDF)
+//   sharded_pull_kernel        the sources of every non-empty range, one thread each (as in the scatter kernel),
+//                              offspring clipped to the rank's slot range
+// ---------------------------------------------------------------------------------------------
+struct PeerInputs {
+  const double* cdf[kMaxShards];
+  const void* x[kMaxShards];
+};
+struct PullGeom {
+  double offset[kMaxShards + 1];  // O_0 = 0, O_{s+1} = fl(O_s + T_s); offset[world] = the global total
+};
+__device__ __forceinline__ PullGeom pull_geometry(const double* __restrict__ totals, int world) {
+  PullGeom g;
+  double o = 0.0;
+  for (int r = 0; r < world; ++r) { g.offset[r] = o; o = __dadd_rn(o, totals[r]); }
+  g.offset[world] = o;
+  return g;
+}
+// first slot that no longer belongs to source i of shard s
+__device__ __forceinline__ int64_t pull_end_slot(const double* cdf_s, int64_t i, int64_t n, bool last_shard, double off,
+                                                 double total, double u0, double dn, int64_t n_comb) {
+  if (i == n - 1 && last_shard) return n_comb;
+  return comb_count_below(__ddiv_rn(__dadd_rn(off, cdf_s[i]), total), u0, dn, n_comb);
+}
+
+__global__ void __launch_bounds__(32 * kMaxShards) sharded_pull_plan_kernel(int64_t n, PeerInputs in, const double* __restrict__ totals,
+                                                                     int world, int rank, double u0, long long* plan,
+                                                                     double* status) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const PullGeom geo = pull_geometry(totals, world);
+  const double total = geo.offset[world];
+  const bool bad = !(total > 0.0) || !(total < INFINITY);
+  if (threadIdx.x == 0) status[0] = bad ? 1.0 : 0.0;
+  if (warp >= world || lane != 0) return;
+  const int s = warp;
+  long long a = 0, b = 0;
+  if (!bad) {
+    const int64_t n_comb = n * world;
+    const double dn = (double)n_comb;
+    const int64_t S0 = (int64_t)rank * n, S1 = S0 + n;
+    const double* cdf_s = in.cdf[s];
+    const bool last = s == world - 1;
+    auto E = [&](int64_t i) { return pull_end_slot(cdf_s, i, n, last, geo.offset[s], total, u0, dn, n_comb); };
+    // first slot of the shard, and one past its last: empty intersections need no remote read at all
+    const int64_t first_slot = s == 0 ? 0 : comb_count_below(__ddiv_rn(geo.offset[s], total), u0, dn, n_comb);
+    const int64_t end_slot = last ? n_comb : comb_count_below(__ddiv_rn(geo.offset[s + 1], total), u0, dn, n_comb);
+    if (first_slot < S1 && end_slot > S0) {
+      int64_t lo = 0, hi = n;  // a = first i with E(i) > S0 (its offspring reach into the rank's slots)
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (E(mid) > S0) hi = mid; else lo = mid + 1; }
+      a = lo;
+      hi = n;                  // first i >= a with E(i) >= S1: the last source that can own a slot below S1
+      while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (E(mid) >= S1) hi = mid; else lo = mid + 1; }
+      b = lo < n ? lo + 1 : n;
+    }
+  }
+  plan[2 * s] = a;
+  plan[2 * s + 1] = b;
+}
+
+template <typename T, int D, int EST, int kU>
+__global__ void __launch_bounds__(kThreads) sharded_pull_kernel(int64_t n, PeerInputs in, const double* __restrict__ totals,
+                                                                int world, int rank, double u0,
+                                                                const long long* __restrict__ plan, T* __restrict__ x_out,
+                                                                double* est_sums, const double* __restrict__ status,
+                                                                Workspace ws, int64_t big_cnt) {
+  constexpr int NE = (EST == PFB_EST_SUM) ? D : (EST == PFB_EST_TRIG ? 2 * D : 1);
+  __shared__ double red[NE * 32];
+  if (status[0] != 0.0) return;  // (the plan kernel found the global total invalid: nothing is written)
+  const PullGeom geo = pull_geometry(totals, world);
+  const double total = geo.offset[world];
+  const int64_t n_comb = n * world;
+  const double dn = (double)n_comb;
+  const int64_t S0 = (int64_t)rank * n, S1 = S0 + n;
+  const int lane = threadIdx.x & 31;
+  double acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+  // A warp takes kU x 32 consecutive sources per round and issues the loads of all kU groups together: a remote
+  // source costs an NVLink round trip, and one 8-byte load per thread in flight keeps only ~1/3 of the link's
+  // bandwidth-delay product busy.
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int s = 0; s < world; ++s) {
+    const int64_t a = plan[2 * s], b = plan[2 * s + 1];
+    if (b <= a) continue;
+    const double* cdf_s = in.cdf[s];
+    const T* x_s = static_cast<const T*>(in.x[s]);
+    const double off = geo.offset[s];
+    const bool last = s == world - 1;
+    const int64_t i0 = a & ~(int64_t)31;  // rounds stay aligned to 32 sources
+    const int64_t nchunks = (b - i0 + 32 * kU - 1) / (32 * kU);
+    for (int64_t ch = warp_global; ch < nchunks; ch += nwarps) {
+      const int64_t base = i0 + ch * (32 * kU);
+      double cv[kU];
+      bool mine[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = base + u * 32 + lane;
+        mine[u] = i >= a && i < b;
+        cv[u] = mine[u] ? cdf_s[i] : 0.0;
+      }
+      // the slot where the chunk's first source starts (lane 0 only needs it)
+      int64_t prev_end = 0;
+      {
+        const int64_t ifirst = base > a ? base : a;  // first source of this chunk that is mine
+        if (lane == 0) {
+          prev_end = (ifirst == 0) ? (s == 0 ? 0 : comb_count_below(__ddiv_rn(off, total), u0, dn, n_comb))
+                                   : pull_end_slot(cdf_s, ifirst - 1, n, false, off, total, u0, dn, n_comb);
+        }
+      }
+      int64_t e[kU], row0[kU], cnt[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = base + u * 32 + lane;
+        e[u] = 0;
+        if (mine[u]) e[u] = (i == n - 1 && last) ? n_comb : comb_count_below(__ddiv_rn(__dadd_rn(off, cv[u]), total), u0, dn, n_comb);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = base + u * 32 + lane;
+        int64_t sbeg = __shfl_up_sync(0xffffffffu, e[u], 1);
+        const int64_t carry = __shfl_sync(0xffffffffu, u > 0 ? e[u > 0 ? u - 1 : 0] : prev_end, u > 0 ? 31 : 0);
+        const int64_t first_start = __shfl_sync(0xffffffffu, prev_end, 0);  // (every lane takes part in the shuffle)
+        if (lane == 0) sbeg = carry;
+        if (i == a) sbeg = first_start;  // (the range starts inside a round: the lanes below are not mine)
+        const int64_t c0 = sbeg < S0 ? S0 : sbeg, c1 = e[u] > S1 ? S1 : e[u];
+        cnt[u] = mine[u] && c1 > c0 ? c1 - c0 : 0;
+        row0[u] = c0 - S0;
+      }
+      double r[kU][D];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) r[u][c] = 0.0;
+        if (cnt[u] > 0) load_rec_inplace<T, D>(x_s, base + u * 32 + lane, r[u]);  // (ordinary loads: a peer's memory)
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (cnt[u] > 0) {
+          if constexpr (EST == PFB_EST_SUM) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = fma((double)cnt[u], r[u][c], acc[c]);
+          } else if constexpr (EST == PFB_EST_TRIG) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              double sn, cs;
+              sincospi(r[u][c] * 0.3183098861837907, &sn, &cs);
+              acc[2 * c] = fma((double)cnt[u], cs, acc[2 * c]);
+              acc[2 * c + 1] = fma((double)cnt[u], sn, acc[2 * c + 1]);
+            }
+          }
+        }
+        if (cnt[u] > 0 && cnt[u] <= 2) {
+          for (int64_t t = 0; t < cnt[u]; ++t) store_rec<T, D>(x_out, row0[u] + t, r[u]);
+        }
+        if (cnt[u] > big_cnt) {
+          const unsigned int slot = atomicAdd(ws.counters + 6, 1u);
+          if (slot < (unsigned int)(kWsJobCap - 16)) {
+            ws.jobs[3 * slot] = ((long long)s << 48) | (base + u * 32 + lane);
+            ws.jobs[3 * slot + 1] = row0[u];
+            ws.jobs[3 * slot + 2] = cnt[u];
+          }
+        }
+        unsigned longmask = __ballot_sync(0xffffffffu, cnt[u] > 2 && cnt[u] <= big_cnt);
+        while (longmask) {
+          const int src = __ffs(longmask) - 1;
+          longmask &= longmask - 1;
+          const int64_t s0 = __shfl_sync(0xffffffffu, row0[u], src);
+          const int64_t k0 = __shfl_sync(0xffffffffu, cnt[u], src);
+          double rb[D];
+#pragma unroll
+          for (int c = 0; c < D; ++c) rb[c] = __shfl_sync(0xffffffffu, r[u][c], src);
+          for (int64_t t = lane; t < k0; t += 32) store_rec<T, D>(x_out, s0 + t, rb);
+        }
+      }
+    }
+  }
+  if constexpr (EST != PFB_EST_NONE) {
+    block_sum<NE>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < NE; ++k) ws.partials[(int64_t)blockIdx.x * kPartialDoubles + k] = acc[k];
+    }
+    if (block_is_last(ws.counters)) {
+      double t[NE];
+#pragma unroll
+      for (int k = 0; k < NE; ++k) t[k] = 0.0;
+      for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) t[k] += ws.partials[(int64_t)bb * kPartialDoubles + k];
+      }
+      block_sum<NE>(t, red);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) est_sums[k] = t[k];
+      }
+    }
+  }
+}
+
+// heavy particles of the pull kernel: every queued run of offspring is written by the whole grid
+template <typename T, int D>
+__global__ void __launch_bounds__(kThreads) sharded_pull_fill_kernel(PeerInputs in, T* __restrict__ x_out, Workspace ws) {
+  const unsigned int nj_raw = *reinterpret_cast<volatile unsigned int*>(ws.counters + 6);
+  const unsigned int nj = nj_raw < (unsigned int)(kWsJobCap - 16) ? nj_raw : (unsigned int)(kWsJobCap - 16);  // (the tail holds the plan)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (unsigned int j = 0; j < nj; ++j) {
+    const long long tag = ws.jobs[3 * j];
+    const int64_t row0 = ws.jobs[3 * j + 1], cnt = ws.jobs[3 * j + 2];
+    double r[D];
+    load_rec_inplace<T, D>(static_cast<const T*>(in.x[tag >> 48]), tag & 0xFFFFFFFFFFFFLL, r);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += stride) store_rec<T, D>(x_out, row0 + t, r);
+  }
+  if (block_is_last(ws.counters + 7) && threadIdx.x == 0) ws.counters[6] = 0u;  // self-cleaning
+}
+
+template <typename T, int D>
+static int launch_sharded_pull(int64_t n, const PeerInputs& in, const double* totals, int world, int rank, double u0,
+                               void* x_out, int est_kind, double* est_sums, double* status, Workspace W, cudaStream_t st) {
+  long long* plan = reinterpret_cast<long long*>(W.jobs) + 3 * (int64_t)kWsJobCap - 2 * kMaxShards;  // tail of the job list
+  sharded_pull_plan_kernel<<<1, 32 * kMaxShards, 0, st>>>(n, in, totals, world, rank, u0, plan, status);
+  const int grid = stream_grid(n);
+  int64_t big_cnt = (n * world) >> 13;
+  if (big_cnt < 8192) big_cnt = 8192;
+  static const int unroll = getenv("PFB_PULL_UNROLL") ? atoi(getenv("PFB_PULL_UNROLL")) : 4;
+#define PFB_PULL_LAUNCH(E)                                                                                                          \
+  if (unroll == 1) sharded_pull_kernel<T, D, E, 1><<<grid, kThreads, 0, st>>>(n, in, totals, world, rank, u0, plan, (T*)x_out, est_sums, status, W, big_cnt); \
+  else sharded_pull_kernel<T, D, E, 4><<<grid, kThreads, 0, st>>>(n, in, totals, world, rank, u0, plan, (T*)x_out, est_sums, status, W, big_cnt)
+  switch (est_kind) {
+    case PFB_EST_NONE: PFB_PULL_LAUNCH(PFB_EST_NONE); break;
+    case PFB_EST_SUM: PFB_PULL_LAUNCH(PFB_EST_SUM); break;
+    case PFB_EST_TRIG: PFB_PULL_LAUNCH(PFB_EST_TRIG); break;
+    default: set_error("bad est_kind %d", est_kind); return PFB_ERR_INVALID;
+  }
+#undef PFB_PULL_LAUNCH
+  sharded_pull_fill_kernel<T, D><<<sm_count() * 4, kThreads, 0, st>>>(in, (T*)x_out, W);
+  return PFB_OK;
+}
+
 template <typename T, int D>
 static int launch_systematic(int64_t n, const double* cdf, double cdf_offset, double total_imm, double u0_imm,
                              const double* u0_ptr, RngKey key, int u0_mode, int64_t j_begin, int64_t count,
@@ -1494,6 +1741,32 @@ extern "C" int pfb_resample_sharded_dev(pfb_dtype dtype, int32_t dim, int64_t n,
   PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_sharded_dev<T, D>(n, cdf, totals_dev, world, rank, u0, peers, x_in, est_kind, est_sums, status, W, st))));
   if (rc) return rc;
   PFB_LAUNCH_OK("sharded_scatter_kernel");
+  return PFB_OK;
+}
+
+extern "C" int pfb_resample_sharded_pull(pfb_dtype dtype, int32_t dim, int64_t n, const double* const* peer_cdf,
+                                         const void* const* peer_x, const double* totals_dev, int32_t world,
+                                         int32_t rank, double u0, void* x_out, int32_t est_kind, double* est_sums,
+                                         double* status, void* ws, int64_t ws_bytes, void* stream) {
+  if (n <= 0) return PFB_OK;
+  if (!peer_cdf || !peer_x || !totals_dev || !x_out || !status || !ws) { set_error("NULL pointer"); return PFB_ERR_INVALID; }
+  if (world < 1 || world > kMaxShards || rank < 0 || rank >= world) { set_error("world %d / rank %d: 1..%d shards", world, rank, kMaxShards); return PFB_ERR_INVALID; }
+  if (est_kind != PFB_EST_NONE && !est_sums) { set_error("estimate requested without output"); return PFB_ERR_INVALID; }
+  if (n * (int64_t)world >= ((int64_t)1 << 40)) { set_error("comb too long"); return PFB_ERR_UNSUPPORTED; }
+  PeerInputs in{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_cdf[r] || !peer_x[r]) { set_error("peer_cdf[%d] / peer_x[%d] is NULL", r, r); return PFB_ERR_INVALID; }
+    if (peer_x[r] == x_out) { set_error("resampling cannot run in place"); return PFB_ERR_INVALID; }
+    in.cdf[r] = peer_cdf[r];
+    in.x[r] = peer_x[r];
+  }
+  Workspace W;
+  int rc = carve_workspace(ws, ws_bytes, 0, &W);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  PFB_DISPATCH_DTYPE(dtype, PFB_DISPATCH_DIM(dim, (rc = launch_sharded_pull<T, D>(n, in, totals_dev, world, rank, u0, x_out, est_kind, est_sums, status, W, st))));
+  if (rc) return rc;
+  PFB_LAUNCH_OK("sharded_pull_kernel");
   return PFB_OK;
 }
 

@@ -231,6 +231,11 @@ class ShardedParticleFilter:
         # device-side plan (pfb_resample_sharded_dev): one kernel per step, no host read of the shard totals; the
         # status of a step (global weight sum positive and finite) is checked when the NEXT step starts, or on check()
         self.device_plan = True
+        # pull form (pfb_resample_sharded_pull): every rank produces its own n_loc slots and reads remote sources over
+        # NVLink, so the work stays balanced when the weight sits in few shards; False = the push form (the owner of a
+        # source stores its offspring into the peers' buffers)
+        self.pull = True
+        self._sym_cdf = None     # (tensor, handle): the CDF shard in symmetric memory (read by the peers in pull form)
         self._dp = None          # persistent small device / pinned tensors of the device-planned path
         self._pending_check = None
 
@@ -405,12 +410,48 @@ class ShardedParticleFilter:
         self.check()  # the previous step's status, copied to the host a step ago
         if self.world > 1:
             dist.all_reduce(local_max, op=dist.ReduceOp.MAX, group=self.group)
+        pull = self.pull  # (one rank: the same kernel with a one-entry peer table)
+        if pull and self.world > 1 and self._sym_cdf is None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = self.group if self.group is not None else dist.group.WORLD
+            t = symm_mem.empty((n_loc,), dtype=torch.float64, device=dev)
+            self._sym_cdf = (t, symm_mem.rendezvous(t, grp.group_name))
+        if pull and self.world > 1:
+            self.backend._cdf = self._sym_cdf[0]  # the scan writes the shard's CDF where the peers can read it
         cdf, total = self.backend.scan(loc._logw, local_max)
         if self.world > 1:
-            dist.all_gather_into_tensor(dp["totals"], total, group=self.group)
+            dist.all_gather_into_tensor(dp["totals"], total, group=self.group)  # (orders every peer's scan before the reads below)
         else:
             dp["totals"].copy_(total)
         out = loc._alt
+        if pull:
+            kx = ("pull", x.data_ptr())
+            if kx not in dp["peers"]:
+                if self.world == 1:
+                    dp["peers"][kx] = ([cdf.data_ptr()], [x.data_ptr()])
+                else:
+                    hx, hc = self._sym_handles[x.data_ptr()], self._sym_cdf[1]
+                    dp["peers"][kx] = (
+                        [cdf.data_ptr() if r == self.rank else hc.get_buffer(r, (n_loc,), torch.float64).data_ptr() for r in range(self.world)],
+                        [x.data_ptr() if r == self.rank else hx.get_buffer(r, tuple(x.shape), x.dtype).data_ptr() for r in range(self.world)])
+            cdf_ptrs, x_ptrs = dp["peers"][kx]
+            trig = self.manifold == "torus"
+            dp["est"].zero_()
+            timing = getattr(self, "time_scatter", False)
+            if timing:
+                self._scatter_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self._scatter_ev[0].record()
+            eng.resample_sharded_pull(cdf_ptrs, x_ptrs, dp["totals"], self.world, self.rank, u0, out, n_loc, D,
+                                      L.EST_TRIG if trig else L.EST_SUM, dp["est"], dp["status"])
+            if timing:
+                self._scatter_ev[1].record()
+            ne = 2 * D if trig else D
+            sums = dp["est"][:ne].clone()
+            if self.world > 1:  # (also the barrier: no rank overwrites a buffer while a peer may still be reading it)
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            self._finish_device_plan(sums, out, dp)
+            return
         key = out.data_ptr()
         if key not in dp["peers"]:
             if self.world == 1:
@@ -433,6 +474,9 @@ class ShardedParticleFilter:
         sums = dp["est"][:ne].clone()
         if self.world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)  # (also the barrier of the peer stores)
+        self._finish_device_plan(sums, out, dp)
+
+    def _finish_device_plan(self, sums, out, dp):
         self._est_sums = sums
         self._new = out
         self.last_plan = None
@@ -441,7 +485,7 @@ class ShardedParticleFilter:
         dp["host"][:1].copy_(dp["status"], non_blocking=True)
         dp["host"][1:].copy_(dp["totals"], non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
+        ev.record(torch.cuda.current_stream(out.device))
         self._pending_check = ev
 
     def check(self):
@@ -467,7 +511,9 @@ class ShardedParticleFilter:
         tot = [float(t) for t in self.last_totals.cpu()]
         offs = shard_offsets(tot)
         B = offspring_boundaries(offs, self._last_u0, self.n_total)
-        send, _ = exchange_plan(B, self.rank, self.world, self.n_loc)
+        send, recv = exchange_plan(B, self.rank, self.world, self.n_loc)
+        if self.pull and self.world > 1:  # pull form: (offspring produced here = n_loc, of which from remote sources)
+            return sum(recv), sum(recv) - recv[self.rank]
         return sum(send), sum(send) - send[self.rank]
 
     # -- estimate ------------------------------------------------------------------------------------------

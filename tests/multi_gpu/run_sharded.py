@@ -44,6 +44,7 @@ def main():
     F[0, 2] = F[1, 3] = 1.0
     Q, R = 0.1 * np.eye(D), 0.5 * np.eye(D)
     pf = ShardedParticleFilter("euclid", N, D)
+    pf.pull = os.environ.get("PULL", "1") == "1"  # pull form (default) or push form of the exchange
     sl = slice(rank * n_loc, (rank + 1) * n_loc)
     pf.set_local_particles(x0[sl])
     ref = x0
@@ -63,7 +64,7 @@ def main():
         want = dp[idx]
         if rank == 0:
             close = np.isclose(got, want, rtol=1e-12, atol=1e-13).all(axis=1)
-            print(f"step {t}: particles differing from the sharded oracle: {(~close).sum()} of {N}; "
+            print(f"[{'pull' if pf.pull else 'push'}] step {t}: particles differing from the sharded oracle: {(~close).sum()} of {N}; "
                   f"estimate err {np.abs(est - want.mean(axis=0)).max():.2e}; "
                   f"(offspring produced here, stored on other ranks) {pf.offspring_traffic()}")
             ok &= (~close).sum() <= 4 and np.allclose(est, want.mean(axis=0), rtol=1e-9, atol=1e-12)

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), n
     lib = L.lib()
-    assert lib.pfb_abi_version() == L.ABI_VERSION == 7
+    assert lib.pfb_abi_version() == L.ABI_VERSION == 8
     assert lib.pfb_workspace_bytes(0) >= 256
     assert lib.pfb_workspace_bytes(10**8) > lib.pfb_workspace_bytes(0)
 

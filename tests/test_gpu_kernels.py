@@ -795,3 +795,55 @@ def test_sharded_device_plan_kernel_equals_sharded_oracle(eng, world, skew, heav
     bad = torch.zeros(world, dtype=torch.float64, device="cuda:0")
     eng.resample_sharded_dev(cdfs[0], bad, world, 0, u0, ptrs, dev(x[:n_loc]), D, L.EST_SUM, est[0], status)
     assert float(status) == 1.0
+
+
+@pytest.mark.parametrize("skew", [False, True])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_resampling_pull_and_push_with_all_shards_on_one_device(eng, world, skew):
+    """pfb_resample_sharded_pull / pfb_resample_sharded_dev with the `world` shards of one filter living on the same
+    GPU (the peer tables simply point at local buffers): every rank's output equals the oracle's global systematic
+    resampling of the sharded CDF, row for row -- the NCCL / NVLink run of the same kernels is
+    tests/multi_gpu/run_sharded.py."""
+    from pyrecest_b200 import _lib as L
+
+    rng = np.random.default_rng(100 * world + skew)
+    n, D = 70_001, 4
+    x = [rng.standard_normal((n, D)) for _ in range(world)]
+    p = [rng.random(n) * (np.exp(-3.0 * g) if skew else 1.0) for g in range(world)]
+    if skew:
+        p[0][1234] = 40_000.0   # a heavy particle: its offspring span ranks and go through the job list
+    u0 = 0.6180339887
+    idx = O.sharded_systematic_indices(p, u0)
+    want = np.concatenate(x)[idx].reshape(world, n, D)
+    xd = [dev(a) for a in x]
+    cdfs = []
+    totals = torch.zeros(world, dtype=torch.float64, device="cuda:0")
+    for g in range(world):
+        c = torch.empty(n, dtype=torch.float64, device="cuda:0")
+        eng.scan(c, w=dev(p[g]), exact=True)
+        totals[g] = c[-1]
+        cdfs.append(c)
+    status = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+    est = torch.zeros(2 * L.PFB_MAXD, dtype=torch.float64, device="cuda:0")
+    # pull: one call per rank, local output
+    sums = np.zeros(D)
+    for r in range(world):
+        out = torch.empty((n, D), dtype=torch.float64, device="cuda:0")
+        eng.resample_sharded_pull([c.data_ptr() for c in cdfs], [a.data_ptr() for a in xd], totals, world, r, u0, out, n, D,
+                                  L.EST_SUM, est, status)
+        assert float(status[0]) == 0.0
+        assert np.array_equal(host(out), want[r]), (world, skew, r)
+        sums += host(est)[:D]
+    np.testing.assert_allclose(sums, want.reshape(-1, D).sum(axis=0), rtol=1e-11, atol=1e-9)
+    # push: one call per rank, every rank stores into the owners' buffers
+    outs = [torch.empty((n, D), dtype=torch.float64, device="cuda:0") for _ in range(world)]
+    for r in range(world):
+        eng.resample_sharded_dev(cdfs[r], totals, world, r, u0, [o.data_ptr() for o in outs], xd[r], D, L.EST_SUM, est, status)
+    for r in range(world):
+        assert np.array_equal(host(outs[r]), want[r]), (world, skew, r)
+    # an invalid global total: status 1, nothing written
+    totals[0] = float("nan")
+    out = torch.full((n, D), 7.0, dtype=torch.float64, device="cuda:0")
+    eng.resample_sharded_pull([c.data_ptr() for c in cdfs], [a.data_ptr() for a in xd], totals, world, 0, u0, out, n, D,
+                              L.EST_SUM, est, status)
+    assert float(status[0]) == 1.0 and bool((out == 7.0).all())
