@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpfb.so")
+LIB_PATH = os.environ.get("PFB_LIB_PATH") or os.path.join(HERE, "lib", "libpfb.so")  # (override: A/B builds of the library)
 CSRC = os.path.join(HERE, "csrc")
 
 PFB_MAXD = 6

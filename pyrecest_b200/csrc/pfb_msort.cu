@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) msort_guide_kernel(int64_t n, const 
 }
 
 template <typename T, int D, int EST>
-__global__ void __launch_bounds__(kThreads, 3) msort_resample_kernel(
+__global__ void __launch_bounds__(kThreads, 4) msort_resample_kernel(
     int64_t n, int64_t n_out, const double* __restrict__ cdf, const T* __restrict__ x_in, int64_t x_in_stride,
     T* __restrict__ x_out, int64_t* __restrict__ idx_out, double* est_out, Workspace ws, RngKey key, int k, int k_top,
     const int32_t* __restrict__ cnt_top, const int32_t* __restrict__ offs, const int32_t* __restrict__ guide) {
