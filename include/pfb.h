@@ -136,7 +136,10 @@ typedef struct {
   const double* mu_batch_dev; /* *_batched only: DEVICE (n_runs, D) likelihood centres, one measurement per run
                                  (NULL: `mu` for every run) */
   int32_t out_format;        /* pfb_weight_format of the `logw` output of the weighting calls */
-  int32_t reserved;
+  int32_t cell_span;         /* 0: the cell grid covers the box of ONE measurement (above).  1: it covers
+                                dev = wrap(x) - mu in [-3 pi, pi)^D, the union over every mu in [0, 2 pi)^D, with
+                                2 cell_grid cells per dimension -- valid for any measurement, so the *_batched calls
+                                (one mu per run, mu_batch_dev) can use it */
 } pfb_lik_params;
 
 /* What the weighting calls (pfb_loglik, pfb_predict_loglik and their *_batched forms) write into `logw`:

@@ -204,22 +204,25 @@ class Engine:
     def run_pad(run_len):
         return (run_len + 2047) // 2048 * 2048
 
-    def loglik_batched(self, lik, x, n_runs, run_len, logw_pad):
+    def loglik_batched(self, lik, x, n_runs, run_len, logw_pad, scaled=False):
         ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        lik.out_format = L.WEIGHTS_SCALED if scaled else L.WEIGHTS_LOG
         L.check(self.lib.pfb_loglik_batched(C.byref(lik), _DT[x.dtype], n_runs, run_len, _ptr(x), _ptr(logw_pad),
                                             _ptr(self.stats), ws, wsb, _stream(self.device)))
         self.launches += 1
 
-    def predict_loglik_batched(self, params, lik, x_in, x_out, noise, n_runs, run_len, logw_pad):
+    def predict_loglik_batched(self, params, lik, x_in, x_out, noise, n_runs, run_len, logw_pad, scaled=False):
         ws, wsb = self._ensure_ws_batched(n_runs, run_len)
+        lik.out_format = L.WEIGHTS_SCALED if scaled else L.WEIGHTS_LOG
         L.check(self.lib.pfb_predict_loglik_batched(C.byref(params), C.byref(lik), _DT[x_in.dtype], n_runs, run_len,
                                                     _ptr(x_in), _ptr(x_out), _ptr(noise), _ptr(logw_pad),
                                                     _ptr(self.stats), ws, wsb, _stream(self.device)))
         self.launches += 1
 
-    def scan_batched(self, logw_pad, cdf_pad, n_runs, run_len, exact=True):
+    def scan_batched(self, logw_pad, cdf_pad, n_runs, run_len, exact=True, scaled=False):
+        """scaled: logw_pad holds the slice-scaled linear weights a *_batched weighting call with scaled=True left"""
         ws, wsb = self._ensure_ws_batched(n_runs, run_len)
-        mode = (L.SCAN_SEQEXACT if exact else L.SCAN_FAST) | L.SCAN_TILE_STATS_VALID
+        mode = (L.SCAN_SEQEXACT if exact else L.SCAN_FAST) | L.SCAN_TILE_STATS_VALID | (L.SCAN_SLICE_SCALED if scaled else 0)
         L.check(self.lib.pfb_scan_cdf_batched(mode, n_runs, run_len, _ptr(logw_pad), _ptr(cdf_pad), _ptr(self.stats),
                                               ws, wsb, _stream(self.device)))
         self.launches += 5 if exact else 3

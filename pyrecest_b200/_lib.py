@@ -68,7 +68,7 @@ class LikParams(C.Structure):
         ("mu", C.c_double * PFB_MAXD), ("W", C.c_double * (PFB_MAXD * PFB_MAXD)),
         ("logc", C.c_double), ("kappa", C.c_double), ("sigma", C.c_double),
         ("images_dev", C.c_void_p), ("mu_batch_dev", C.c_void_p),
-        ("out_format", C.c_int32), ("reserved", C.c_int32),
+        ("out_format", C.c_int32), ("cell_span", C.c_int32),
     ]
 
 

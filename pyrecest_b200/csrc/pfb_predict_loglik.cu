@@ -284,16 +284,18 @@ __device__ __forceinline__ double loglik_parts(const pfb_lik_params& L, const do
           const double2 a = lt[2 * k], b = lt[2 * k + 1];
           return fma(a.x, d0, fma(a.y, d1, fma(b.x, d2, b.y)));
         };
-        if (L.cell_grid > 0 && L.mu_batch_dev == nullptr) {
-          // the host has listed, per cell of the box of xs, the images that can come within e^-39 of the best one
-          // anywhere in the cell (registry.wn_cell_masks: a superset that contains the minimiser) and the image
-          // that is best at the cell's centre (no image beats it by more than e^500 anywhere in the cell)
-          const int G = L.cell_grid;
-          const double inv = (double)G * 0.15915494309189535;  // G / (2 pi)
+        if (L.cell_grid > 0 && (L.mu_batch_dev == nullptr || L.cell_span == 1)) {
+          // the host has listed, per cell, the images that can come within e^-39 of the best one anywhere in the cell
+          // (registry.wn_cell_masks: a superset that contains the minimiser) and the image that is best at the cell's
+          // centre (no image beats it by more than e^500 anywhere in the cell).  The cells cut the box of xs for one
+          // measurement (cell_span 0), or the box dev in [-3 pi, pi)^D that holds every measurement (cell_span 1:
+          // twice the cells per dimension, one table for all runs of a batched launch)
+          const int G = L.cell_span == 1 ? 2 * L.cell_grid : L.cell_grid;
+          const double inv = (double)L.cell_grid * 0.15915494309189535;  // cells per unit: cell_grid / (2 pi)
           int ci = 0, mul = 1;
 #pragma unroll
           for (int c = 0; c < D; ++c) {
-            int q = (int)(xs[c] * inv);
+            int q = (int)((L.cell_span == 1 ? dev[c] + 9.42477796076938 : xs[c]) * inv);
             q = q < 0 ? 0 : (q >= G ? G - 1 : q);
             ci += q * mul;
             mul *= G;
@@ -490,9 +492,10 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
     if (L.cell_grid > 0) {  // candidate masks of the cell grid, after the linear rows
       uint64_t* cells = reinterpret_cast<uint64_t*>(lt + 4 * K);
       const uint64_t* src = reinterpret_cast<const uint64_t*>(L.images_dev + count);
-      int nc = L.cell_grid;
-      if (D > 1) nc *= L.cell_grid;
-      if (D > 2) nc *= L.cell_grid;
+      const int G = L.cell_span == 1 ? 2 * L.cell_grid : L.cell_grid;
+      int nc = G;
+      if (D > 1) nc *= G;
+      if (D > 2) nc *= G;
       for (int k = threadIdx.x; k < nc + (nc + 7) / 8; k += blockDim.x) cells[k] = src[k];  // masks, then the reference bytes
     }
   }
@@ -611,7 +614,7 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
           sacc *= f;
           pmax *= f;
         }
-        const double p = exp_le700(a - cg) * lin;  // (a = -inf: 0)
+        const double p = (a > -INFINITY) ? exp_le700(a - cg) * lin : 0.0;  // (a = cg = -inf, a slice of zero weights so far, would be NaN)
         if (local < sg.run_pad) mine[k * 32] = p;  // (padding of a batched run: weight 0)
         sacc += p;
         pmax = (p > pmax) ? p : pmax;
@@ -803,6 +806,17 @@ extern "C" int pfb_vm_strip_thresholds(double kappa, const double* table, double
 }
 #endif
 
+static size_t lik_smem(const pfb_lik_params* L) {
+  if (L->kind != PFB_LIK_WN_MULTI) return 0;
+  size_t cells = 0;
+  if (L->cell_grid > 0) {
+    cells = 1;
+    for (int c = 0; c < L->dim; ++c) cells *= (size_t)(L->cell_span == 1 ? 2 * L->cell_grid : L->cell_grid);
+    cells = cells * 8 + ((cells + 7) / 8) * 8;  // masks + one reference byte per cell
+  }
+  return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 32 + cells;
+}
+
 static int check_lik(const pfb_lik_params* L, int dim) {
   if (!L) { set_error("likelihood params NULL"); return PFB_ERR_INVALID; }
   if (L->dim != dim) { set_error("likelihood dim %d != particle dim %d", L->dim, dim); return PFB_ERR_INVALID; }
@@ -811,7 +825,8 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
     if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
-    if ((int64_t)L->n_images * ((2 * dim + 1) * 8 + 32) + 8 > 40 * 1024) { set_error("image table too large (%d rows)", L->n_images); return PFB_ERR_INVALID; }
+    if (L->cell_span != 0 && L->cell_span != 1) { set_error("bad cell_span %d", L->cell_span); return PFB_ERR_INVALID; }
+    if ((int64_t)lik_smem(L) > 40 * 1024) { set_error("image table too large (%d rows, cell grid %d)", L->n_images, L->cell_grid); return PFB_ERR_INVALID; }
     if (L->cell_grid != 0 && (L->cell_grid < 1 || L->cell_grid > 8 || dim > 3 || L->n_images > 64)) {
       set_error("cell_grid %d: candidate masks need 1 <= G <= 8, dim <= 3 and at most 64 images", L->cell_grid);
       return PFB_ERR_INVALID;
@@ -820,16 +835,6 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   return PFB_OK;
 }
 
-static size_t lik_smem(const pfb_lik_params* L) {
-  if (L->kind != PFB_LIK_WN_MULTI) return 0;
-  size_t cells = 0;
-  if (L->cell_grid > 0) {
-    cells = 1;
-    for (int c = 0; c < L->dim; ++c) cells *= (size_t)L->cell_grid;
-    cells = cells * 8 + ((cells + 7) / 8) * 8;  // masks + one reference byte per cell
-  }
-  return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 32 + cells;
-}
 
 #define PFB_DISPATCH_MODE(mode, ...)                                                       \
   switch (mode) {                                                                          \

@@ -110,13 +110,14 @@ class BatchedParticleFilter:
             p, noise = flat._pending
             flat._pending = None
             try:
-                eng.predict_loglik_batched(p, lp, x, x, noise, self.n_runs, self.n, self._logw)
+                eng.predict_loglik_batched(p, lp, x, x, noise, self.n_runs, self.n, self._logw, scaled=True)
             except NotImplementedError:
                 eng.predict(p, x, x, noise)
-                eng.loglik_batched(lp, x, self.n_runs, self.n, self._logw)
+                eng.loglik_batched(lp, x, self.n_runs, self.n, self._logw, scaled=True)
         else:
-            eng.loglik_batched(lp, x, self.n_runs, self.n, self._logw)
-        eng.scan_batched(self._logw, self._cdf, self.n_runs, self.n, exact=self.scan_exact)
+            eng.loglik_batched(lp, x, self.n_runs, self.n, self._logw, scaled=True)
+        # (slice-scaled linear weights between the weighting kernel and the scan: one exp per particle and step)
+        eng.scan_batched(self._logw, self._cdf, self.n_runs, self.n, exact=self.scan_exact, scaled=True)
         totals = self._cdf.view(self.n_runs, self.run_pad)[:, -1]
         self.failed |= ~(totals > 0)  # all weights zero / NaN: the reference's AssertionError -> run_failed
         systematic = self.resampling == "systematic"
@@ -174,7 +175,16 @@ def _wn_params_any_mean(dist, dim, device):
     p.W[: dim * dim] = W.reshape(-1).tolist()
     p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)
     p.n_images = table.shape[0]
-    keep = torch.as_tensor(np.ascontiguousarray(table), device=device).contiguous()
+    flat = np.ascontiguousarray(table).reshape(-1)
+    # candidate grid over dev in [-3 pi, pi)^d (valid for every measurement): 2 G cells per dimension, G = 8 for
+    # d <= 2 (256 cells), 4 for d = 3 (512 cells)
+    G = R.WN_CELL_GRID if dim <= 2 else 4
+    masks = R.wn_cell_masks(None, table, G=G, any_mean=True)
+    cells = None if masks is None else R.wn_cell_table(None, table, masks, G=G, any_mean=True)
+    if cells is not None:
+        flat = np.concatenate([flat, cells.view(np.float64)])
+        p.cell_grid, p.cell_span = G, 1
+    keep = torch.as_tensor(flat, device=device).contiguous()
     p.images_dev = keep.data_ptr()
     if len(_ANY_MEAN_CACHE) > 64:
         _ANY_MEAN_CACHE.clear()

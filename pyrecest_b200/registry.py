@@ -241,60 +241,62 @@ WN_CELL_GRID = 8       # cells per dimension of the candidate grid
 WN_SCREEN_CUT = 78.0   # kScreenCut of pfb_predict_loglik.cu
 
 
-def wn_cell_masks(mu, table, G=WN_CELL_GRID):
-    """Candidate masks of the image screen.  The kernel evaluates the images k with r_k <= min_j r_j + cut,
-    r_k(dev) = 2 g_k.dev + h_k linear in dev.  Over a cell of the box dev in [-pi - mu, pi - mu) (G cells per
-    dimension, index c_0 + G c_1 + G^2 c_2) r_k is bounded by its corner values, so image k can only be evaluated
-    somewhere in the cell if min_cell r_k <= min_j max_cell r_j + cut: bit k of the cell's uint64 mask.  A superset
-    of what the full screen keeps at every point of the cell (+1 of slack for the kernel's fp32 r, cells inflated by
-    1e-6 for the rounding of the cell index), so screening only the masked images selects exactly the same images."""
-    mu = _np(mu).reshape(-1)
-    d = mu.shape[0]
+def _cell_boxes(lo, n_cells, wid, d):
+    idx = np.stack(np.meshgrid(*([np.arange(n_cells)] * d), indexing="ij"), axis=-1).reshape(-1, d)  # (cells, d)
+    flat = (idx * (n_cells ** np.arange(d))[None, :]).sum(axis=1)  # c_0 + n c_1 + n^2 c_2
+    a = lo + idx * wid - 1e-6
+    return idx, flat, a, a + wid + 2e-6
+
+
+def wn_cell_masks(mu, table, G=WN_CELL_GRID, any_mean=False):
+    """Candidate masks of the image sum.  The kernel adds the images k with t_k <= min_j t_j + 38,
+    t_k(dev) = g_k.dev + h_k / 2 linear in dev (r_k = 2 t_k below).  Over a cell r_k is bounded by its corner
+    values, so image k can only matter somewhere in the cell if min_cell r_k <= min_j max_cell r_j + cut: bit k of the
+    cell's uint64 mask.  A superset of what matters at every point of the cell (+1 of slack, cells inflated by 1e-6
+    for the rounding of the cell index) that contains the minimiser.
+    The cells cut the box dev in [-pi - mu, pi - mu) of ONE measurement into G cells per dimension (index
+    c_0 + G c_1 + G^2 c_2), or -- any_mean -- the box [-3 pi, pi)^d that holds dev for every mu in [0, 2 pi)^d into 2 G
+    cells per dimension (pfb_lik_params.cell_span = 1: one table for all runs of a batched launch)."""
+    d = table.shape[1] // 2
     K = table.shape[0]
     if d > 3 or K > 64:
         return None
     g, h = table[:, :d], table[:, d]
-    lo = -math.pi - mu
-    wid = TWO_PI / G
-    idx = np.stack(np.meshgrid(*([np.arange(G)] * d), indexing="ij"), axis=-1).reshape(-1, d)  # (cells, d), c_0 slowest
-    a = lo + idx * wid - 1e-6
-    b = a + wid + 2e-6
+    lo = np.full(d, -3.0 * math.pi) if any_mean else -math.pi - _np(mu).reshape(-1)
+    n_cells = 2 * G if any_mean else G
+    idx, flat, a, b = _cell_boxes(lo, n_cells, TWO_PI / G, d)
     ga, gb = 2.0 * g[None, :, :] * a[:, None, :], 2.0 * g[None, :, :] * b[:, None, :]
     rmin = h[None, :] + np.minimum(ga, gb).sum(axis=-1)   # (cells, K)
     rmax = h[None, :] + np.maximum(ga, gb).sum(axis=-1)
     keep = rmin <= rmax.min(axis=1, keepdims=True) + WN_SCREEN_CUT + 1.0
     bits = (keep.astype(np.uint64) << np.arange(K, dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint64)
-    flat = (idx * (G ** np.arange(d))[None, :]).sum(axis=1)  # c_0 + G c_1 + G^2 c_2
-    out = np.zeros(G ** d, dtype=np.uint64)
+    out = np.zeros(n_cells ** d, dtype=np.uint64)
     out[flat] = bits
     return out
 
 
-def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0):
+def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0, any_mean=False):
     """Device form of the candidate grid: the uint64 masks followed by one reference byte per cell (padded to 8
     bytes) -- the image that is best at the cell's centre, t_k = g_k.dev + h_k / 2 smallest.  The kernel anchors the
     image sum there: exact quadratic form of the reference image, every other candidate through exp(-(t_k - t_ref)).
     Returns None (no grid: the kernel finds the best image itself) if some candidate could beat the reference by more
     than e^limit somewhere in its cell (tiny covariances), where that exp would overflow."""
-    mu = _np(mu).reshape(-1)
-    d = mu.shape[0]
+    d = table.shape[1] // 2
     K = table.shape[0]
     g, h = table[:, :d], table[:, d]
-    lo = -math.pi - mu
+    lo = np.full(d, -3.0 * math.pi) if any_mean else -math.pi - _np(mu).reshape(-1)
+    n_cells = 2 * G if any_mean else G
     wid = TWO_PI / G
-    idx = np.stack(np.meshgrid(*([np.arange(G)] * d), indexing="ij"), axis=-1).reshape(-1, d)
-    flat = (idx * (G ** np.arange(d))[None, :]).sum(axis=1)
+    idx, flat, a, b = _cell_boxes(lo, n_cells, wid, d)
     bits = ((masks[flat][:, None] >> np.arange(K, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)  # (cells, K)
     centre = lo + (idx + 0.5) * wid
     t = centre @ g.T + 0.5 * h[None, :]
     ref = np.where(bits, t, np.inf).argmin(axis=1)                                                         # (cells,)
-    a = lo + idx * wid - 1e-6
-    b = a + wid + 2e-6
     dg = g[ref][:, None, :] - g[None, :, :]                                                                # (cells, K, d)
     gain = np.maximum(dg * a[:, None, :], dg * b[:, None, :]).sum(axis=-1) + 0.5 * (h[ref][:, None] - h[None, :])
     if np.any(np.where(bits, gain, -np.inf) > limit):
         return None
-    refs = np.zeros(((G ** d + 7) // 8) * 8, dtype=np.uint8)
+    refs = np.zeros(((n_cells ** d + 7) // 8) * 8, dtype=np.uint8)
     refs[flat] = ref.astype(np.uint8)
     return np.concatenate([masks.view(np.uint8), refs]).view(np.uint64)
 
