@@ -20,7 +20,9 @@ from __future__ import annotations
 
 import copy
 import ctypes as C_
+import datetime
 import math
+import os
 import time
 import warnings
 
@@ -239,7 +241,13 @@ def iterate_configs_and_runs(groundtruths, measurements, scenario_config, filter
         torch.cuda.synchronize(bf.device)
         t0 = time.time()
         for t in range(T):
-            bf.update_identity(scenario_config["meas_noise"], meas[:, t].reshape(n_runs, -1))
+            # perform_predict_update_cycles.py:57-65: every measurement of the time step is an update of its own
+            # (measurements (n_runs, T, d): one per step; (n_runs, T, M, d): M per step)
+            if meas.ndim == 4:
+                for m in range(meas.shape[2]):
+                    bf.update_identity(scenario_config["meas_noise"], meas[:, t, m].reshape(n_runs, -1))
+            else:
+                bf.update_identity(scenario_config["meas_noise"], meas[:, t].reshape(n_runs, -1))
             if apply[t]:
                 bf.predict_identity(scenario_config["sys_noise"])
         est = bf.get_point_estimates()
@@ -379,3 +387,84 @@ def summarize_filter_results(scenario_config, filter_configs, runtimes, groundtr
     for d, e, s, tm, fr in zip(results, err_mean, err_std, times, rates):
         d["error_mean"], d["error_std"], d["time_mean"], d["failure_rate"] = float(e), float(s), float(tm), float(fr)
     return results
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's result files (checkpoint / resume of a study): evaluate_for_variables writes one .npy
+# per study with a fixed set of keys, evaluate_for_file reads such a file back and evaluates filters on its
+# ground truths and measurements.
+# ---------------------------------------------------------------------------------------------------------------
+RESULT_KEYS = ("groundtruths", "measurements", "run_failed", "last_filter_states", "runtimes", "scenario_config",
+               "filter_configs", "evaluation_config")  # evaluate_for_variables.py:58-70
+
+
+def _to_host(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+
+
+def evaluate_for_variables(groundtruths, measurements, filter_configs, scenario_config=None, save_folder=".",
+                           plot_each_step=False, convert_to_point_estimate_during_runtime=False,
+                           extract_all_point_estimates=False, tolerate_failure=False, auto_warning_on_off=False):
+    """pyrecest/evaluation/evaluate_for_variables.py:11-82 on the batched path: expand the filter configurations, run
+    them (iterate_configs_and_runs), save `<name>_<date>.npy` with the reference's keys, return the reference's
+    8-tuple.  Differences forced by the batched representation: last_filter_states[c] is the (n_runs, n_particles, D)
+    array of configuration c's last particle sets (the reference pickles one distribution object per run), and
+    runtimes[c, r] is the batch's wall time divided by the number of runs."""
+    if scenario_config is None:
+        scenario_config = {"name": "custom"}
+    if plot_each_step:
+        raise NotImplementedError("Plotting is not implemented yet.")
+    evaluation_config = {
+        "plot_each_step": plot_each_step,
+        "convert_to_point_estimate_during_runtime": convert_to_point_estimate_during_runtime,
+        "extract_all_point_estimates": extract_all_point_estimates,
+        "tolerate_failure": tolerate_failure,
+        "auto_warning_on_off": auto_warning_on_off,
+    }
+    filter_configs = [{"name": f["name"], "parameter": p} for f in filter_configs for p in (np.atleast_1d(f["parameter"]).tolist() or [None])]
+    states, runtimes, run_failed, groundtruths, measurements = iterate_configs_and_runs(
+        groundtruths, measurements, scenario_config, filter_configs, evaluation_config)
+    last_filter_states = np.empty(len(states), dtype=object)
+    for c, bf in enumerate(states):
+        last_filter_states[c] = bf.d.cpu().numpy()
+    stamp = datetime.datetime.now().strftime("%Y-%m-%d--%H-%M-%S")
+    filename = os.path.join(save_folder, f"{scenario_config['name']}_{stamp}.npy")
+    storable = {k: v for k, v in scenario_config.items() if not hasattr(v, "pdf") and not callable(v)}
+    np.save(filename, {
+        "groundtruths": _to_host(groundtruths), "measurements": _to_host(measurements), "run_failed": run_failed,
+        "last_filter_states": last_filter_states, "runtimes": runtimes, "scenario_config": storable,
+        "filter_configs": filter_configs, "evaluation_config": evaluation_config,
+    }, allow_pickle=True)
+    evaluate_for_variables.last_file = filename
+    return (last_filter_states, runtimes, run_failed, groundtruths, measurements, scenario_config, filter_configs,
+            evaluation_config)
+
+
+def evaluate_for_file(input_file_name, filter_configs, scenario_config, save_folder=".", plot_each_step=False,
+                      convert_to_point_estimate_during_runtime=False, extract_all_point_estimates=False,
+                      tolerate_failure=False, auto_warning_on_off=False):
+    """pyrecest/evaluation/evaluate_for_file.py:13-71: ground truths and measurements come from a result file (the
+    reference's or ours: both are a pickled dict with RESULT_KEYS); scenario_config supplies the manifold, the prior
+    and the noise models, and gets the reference's defaults (name, n_timesteps, n_meas_at_individual_time_step,
+    apply_sys_noise_times)."""
+    data = np.load(input_file_name, allow_pickle=True).item()
+    if "name" not in scenario_config:
+        scenario_config["name"] = os.path.splitext(os.path.basename(input_file_name))[0]
+    gts, meas = np.asarray(data["groundtruths"]), data["measurements"]
+    if "n_timesteps" in scenario_config:
+        assert scenario_config["n_timesteps"] == gts.shape[1], \
+            "n_timesteps in scenario_config does not match the number of measurements in the file"
+    else:
+        scenario_config["n_timesteps"] = gts.shape[1]
+    meas = np.asarray(meas)
+    if meas.dtype == object:  # the reference stores one array per (run, step): (d,) or (M, d)
+        meas = np.array([[np.asarray(m, dtype=np.float64) for m in row] for row in meas])
+    n_meas = np.full(meas.shape[1], meas.shape[2] if meas.ndim == 4 else 1, dtype=int)
+    scenario_config.setdefault("n_meas_at_individual_time_step", n_meas)
+    scenario_config.setdefault("apply_sys_noise_times",
+                               np.concatenate([np.ones(scenario_config["n_timesteps"] - 1, dtype=bool), [False]]))
+    return evaluate_for_variables(gts, meas, filter_configs, scenario_config, save_folder=save_folder,
+                                  plot_each_step=plot_each_step,
+                                  convert_to_point_estimate_during_runtime=convert_to_point_estimate_during_runtime,
+                                  extract_all_point_estimates=extract_all_point_estimates,
+                                  tolerate_failure=tolerate_failure, auto_warning_on_off=auto_warning_on_off)

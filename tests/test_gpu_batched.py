@@ -172,3 +172,53 @@ def test_device_scenario_generation_statistics():
     rows = E.summarize_filter_results(small, [{"name": "pf", "parameter": 500}, {"name": "pf", "parameter": 2000}], times,
                                       gts, failed, E.iterate_configs_and_runs.last_estimates)
     assert all(0 < r["error_mean"] < 0.5 for r in rows)
+
+
+def test_result_file_schema_and_reload(tmp_path):
+    """evaluate_for_variables writes the reference's .npy result file (evaluate_for_variables.py:51-70: the same eight
+    keys) and evaluate_for_file reads it back and re-runs the filters on its ground truths and measurements
+    (evaluate_for_file.py:31-71); two measurements per time step are two updates
+    (perform_predict_update_cycles.py:57-65)."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import GaussianDistribution
+    from pyrecest_b200 import evaluation as E
+
+    rng = np.random.default_rng(8)
+    n_runs, T = 12, 6
+
+    def scenario():
+        return {"name": "r2walk", "manifold": "Euclidean", "n_timesteps": T,
+                "initial_prior": GaussianDistribution(np.zeros(2), 0.5 * np.eye(2)),
+                "meas_noise": GaussianDistribution(np.zeros(2), 0.5 * np.eye(2)),
+                "sys_noise": GaussianDistribution(np.zeros(2), 0.5 * np.eye(2))}
+
+    gt = np.cumsum(rng.standard_normal((n_runs, T, 2)) * np.sqrt(0.5), axis=1)
+    meas2 = gt[:, :, None, :] + rng.standard_normal((n_runs, T, 2, 2)) * np.sqrt(0.5)   # two measurements per step
+    prandom.seed(5)
+    out = E.evaluate_for_variables(gt, meas2, [{"name": "pf", "parameter": [400, 1500]}], scenario(), save_folder=str(tmp_path),
+                                   tolerate_failure=True)
+    assert len(out) == 8
+    est2 = E.iterate_configs_and_runs.last_estimates.copy()
+    data = np.load(E.evaluate_for_variables.last_file, allow_pickle=True).item()
+    assert tuple(data.keys()) == E.RESULT_KEYS
+    assert data["groundtruths"].shape == (n_runs, T, 2) and data["measurements"].shape == (n_runs, T, 2, 2)
+    assert data["runtimes"].shape == (2, n_runs) and data["run_failed"].shape == (2, n_runs) and not data["run_failed"].any()
+    assert data["last_filter_states"][1].shape == (n_runs, 1500, 2)
+    assert data["filter_configs"] == [{"name": "pf", "parameter": 400}, {"name": "pf", "parameter": 1500}]
+    assert data["scenario_config"]["name"] == "r2walk" and "initial_prior" not in data["scenario_config"]
+    # reload: the same study from the file alone (scenario_config supplies only the models), same seed -> same estimates
+    prandom.seed(5)
+    sc = scenario()
+    del sc["n_timesteps"], sc["name"]
+    again = E.evaluate_for_file(E.evaluate_for_variables.last_file, [{"name": "pf", "parameter": [400, 1500]}], sc,
+                                save_folder=str(tmp_path), tolerate_failure=True)
+    assert sc["n_timesteps"] == T and list(sc["n_meas_at_individual_time_step"]) == [2] * T
+    assert list(sc["apply_sys_noise_times"]) == [True] * (T - 1) + [False]
+    np.testing.assert_array_equal(E.iterate_configs_and_runs.last_estimates, est2)
+    np.testing.assert_array_equal(again[0][1], out[0][1])
+    # two measurements per step pull the estimate closer to the truth than one
+    prandom.seed(5)
+    E.iterate_configs_and_runs(gt, meas2[:, :, 0, :], scenario(), [{"name": "pf", "parameter": [1500]}], {"tolerate_failure": True})
+    err1 = np.linalg.norm(E.iterate_configs_and_runs.last_estimates[0] - gt[:, -1, :], axis=1).mean()
+    err2 = np.linalg.norm(est2[1] - gt[:, -1, :], axis=1).mean()
+    assert err2 < err1 * 1.05, (err1, err2)
