@@ -211,9 +211,19 @@ def cpu_step_fn(name, n, seed=0):
 
 def run_cpu(name, n, steps, warmup):
     step = cpu_step_fn(name, n)
-    for _ in range(warmup):
-        step()
-    total = sum(step() for _ in range(steps))
+    try:  # the particle ranges are split over our own threads: numpy's BLAS / OpenMP pools stay single-threaded
+        from threadpoolctl import threadpool_limits  # (nested pools over-subscribe the cores: 32-core boxes ran slower)
+
+        limit = threadpool_limits(limits=1)
+    except Exception:
+        limit = None
+    try:
+        for _ in range(warmup):
+            step()
+        total = sum(step() for _ in range(steps))
+    finally:
+        if limit is not None:
+            limit.restore_original_limits()
     return n * steps / total, total / steps
 
 
