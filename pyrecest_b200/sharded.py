@@ -9,11 +9,14 @@ Shard g owns the contiguous global particle range [g n_loc, (g+1) n_loc).  Per s
   local CDF          sequential-exact scan of exp(logw - M)  (pfb_scan_cdf), shard total T_g
   shard offsets      all_gather of the G totals; O_{g+1} = fl(O_g + T_g) summed in rank order on every
                      rank (identical bits everywhere); global CDF v_i = fl(fl(O_g + c_i) / O_G)
-  resampling         systematic comb u_j = (j + u0)/N over the GLOBAL CDF: the offspring that fall into
-                     shard g are the contiguous range [B_g, B_{g+1}), B_g = #{j : u_j < fl(O_g/O_G)};
-                     shard g produces exactly those (pfb_resample_sharded) and an all_to_all_v moves each
-                     piece to the rank that owns those output slots.  Data volume: every particle crosses
-                     NVLink at most once; with evenly weighted shards most pieces stay on their rank.
+  resampling         systematic comb u_j = (j + u0)/N over the GLOBAL CDF; output slot j lives on rank j // n_loc.
+                     Pull form (default, pfb_resample_sharded_pull): every rank produces exactly its own n_loc
+                     slots and reads the sources they come from wherever they live -- CDF shards and particle
+                     buffers are torch symmetric memory, remote ones are read over NVLink inside the kernel, all
+                     stores are local; the work per rank does not depend on where the weight sits.  Push form
+                     (pull = False, pfb_resample_sharded_dev): the owner of a source stores its offspring into the
+                     peers' buffers.  Without symmetric memory (gloo / CPU tests): host-made plan, pieces
+                     [B_g, B_{g+1}) produced by shard g (pfb_resample_sharded) and one all_to_all_v.
   estimate           local sums + all_reduce(SUM)
 
 This is exact global systematic resampling -- identical to a single filter holding all N particles, up to the
