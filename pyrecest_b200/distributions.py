@@ -323,10 +323,13 @@ class VonMisesFisherDistribution(_RegistryDistribution):
 
     def sample(self, n):
         """scipy vonmises_fisher(mu, kappa).rvs(n) on S^2 (:59-81), from (u, z1, z2) triples."""
-        if self.input_dim != 3:
-            raise NotImplementedError("device VMF sampling is implemented on S^2")
         dev = _default_device()
         n = int(n)
+        if self.input_dim != 3:  # other dimensions: Wood's rejection sampler over all draws at once (cart_prod.vmf_rows)
+            from .cart_prod import vmf_rows
+
+            modes = torch.as_tensor(self.mu, dtype=torch.float64, device=dev).expand(n, self.input_dim).contiguous()
+            return vmf_rows(modes, self.kappa)
         t = prandom.source().vmf_triples(n, dev)
         modes = torch.as_tensor(self.mu, device=dev).expand(n, 3).contiguous()
         out = torch.empty_like(modes)
@@ -887,3 +890,12 @@ class SE3DiracDistribution(LinHypersphereCartProdDiracDistribution):
     def from_distribution(distribution, n_particles):
         assert isinstance(n_particles, int) and n_particles > 0, "n_particles must be a positive integer"
         return SE3DiracDistribution(distribution.sample(n_particles))
+
+
+def __getattr__(name):
+    """the Watson / hemisphere Cartesian-product classes live in cart_prod.py (which imports this module)"""
+    if name in ("WatsonDistribution", "HyperhemisphericalWatsonDistribution", "HyperhemisphereCartProdDiracDistribution"):
+        from . import cart_prod
+
+        return getattr(cart_prod, name)
+    raise AttributeError(name)

@@ -630,3 +630,12 @@ class WrappedNormalFilter:
     def get_point_estimate(self):
         """abstract_circular_filter / abstract_filter: the mean direction of the state."""
         return float(np.asarray(self._filter_state.mu).reshape(-1)[0])
+
+
+def __getattr__(name):
+    """HyperhemisphereCartProdParticleFilter lives in cart_prod.py"""
+    if name == "HyperhemisphereCartProdParticleFilter":
+        from .cart_prod import HyperhemisphereCartProdParticleFilter
+
+        return HyperhemisphereCartProdParticleFilter
+    raise AttributeError(name)

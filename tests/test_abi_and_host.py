@@ -263,3 +263,18 @@ def test_derived_draw_sources_differ_per_shard_and_are_reproducible():
     seeds = {a.derive(r).seed for r in range(8)} | {a.seed}
     assert len(seeds) == 9
     assert a.derive(2) is a.derive(2)  # one child per rank: its call counter keeps advancing
+
+
+def test_watson_normalising_constant_against_the_reference():
+    """cart_prod.WatsonDistribution.norm_const (host math: scipy 1F1) equals the reference's (mpmath,
+    watson_distribution.py:44-55), values recorded from a run of the reference: S^2, S^3 and the circle, bipolar and girdle"""
+    from pyrecest_b200.cart_prod import WatsonDistribution
+
+    for mu, kappa, want in [(np.array([0.0, 0.0, 1.0]), 2.0, 0.03365575103329092),
+                            (np.array([0.6, 0.0, 0.0, 0.8]), 7.5, 0.0008898317028250381),
+                            (np.array([0.0, 1.0]), -1.5, 0.29409677016225244)]:
+        w = WatsonDistribution(mu, kappa)
+        assert w.dim == mu.shape[0] - 1 and w.input_dim == mu.shape[0]
+        np.testing.assert_allclose(w.norm_const, want, rtol=1e-12)
+    with pytest.raises(AssertionError):
+        WatsonDistribution(np.array([0.0, 2.0]), 1.0)

@@ -559,3 +559,122 @@ def test_wrapped_normal_filter_particle_update_against_reference_run(golden, tag
     f.predict_identity(WrappedNormalDistribution(np.array(6.0), np.array(0.3)))
     assert float(f.filter_state.mu) == pytest.approx((g[f"{tag}_out"][0] + 6.0) % (2 * np.pi), rel=1e-12)
     assert float(np.asarray(f.filter_state.sigma).reshape(-1)[0]) == pytest.approx(math.hypot(g[f"{tag}_out"][1], 0.3), rel=1e-12)
+
+
+def test_hemisphere_cart_prod_filter_like_the_reference_tests():
+    """pyrecest/tests/filters/test_hyperhemisphere_cart_prod_particle_filter.py: init / set_state / predict / update on
+    two S^3 hemispheres (8-component records), with the reference's own parameters; the likelihood of test_update
+    (abs(sum(x))) is passed as values, a Python callable is rejected."""
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import VonMisesFisherDistribution
+    from pyrecest_b200.filters import HyperhemisphereCartProdParticleFilter, IdentityTransition
+
+    prandom.seed(2)
+    n = 1000
+    pf = HyperhemisphereCartProdParticleFilter(n, 3, 2)
+    assert pf.filter_state.d.shape == (n, 8)
+    pf.filter_state = VonMisesFisherDistribution(np.array([0.0, 0.0, 0.0, 1.0]), 1.0)
+    d = host(pf.filter_state.d)
+    assert d.shape == (n, 8) and np.all(d[:, 3] >= 0) and np.all(d[:, 7] >= 0)
+    np.testing.assert_allclose(np.linalg.norm(d[:, :4], axis=1), 1.0, atol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(d[:, 4:], axis=1), 1.0, atol=1e-12)
+    pf.predict_nonlinear_each_part(IdentityTransition(), VonMisesFisherDistribution(np.array([0.0, 0.0, 0.0, 1.0]), 1.0))
+    d = host(pf.filter_state.d)
+    np.testing.assert_allclose(np.linalg.norm(d[:, 4:], axis=1), 1.0, atol=1e-12)
+    pf.update_nonlinear_using_likelihood(np.abs(d.sum(axis=1)))
+    assert pf.filter_state.d.shape == (n, 8)
+    np.testing.assert_allclose(host(pf.filter_state.w), 1.0 / n)
+    with pytest.raises(NotImplementedError):
+        pf.update_nonlinear_using_likelihood(lambda x: np.abs(x.sum(axis=1)))
+    with pytest.raises(NotImplementedError):
+        pf.predict_nonlinear_each_part(lambda x: x, None)
+
+
+def test_hemisphere_cart_prod_filter_tracks_with_watson_and_vmf_noise():
+    """two S^2 hemispheres, Watson system noise (hemispherical) on the device, per-part von Mises-Fisher likelihoods:
+    the mean axes move to the measured axes; injected uniforms give the oracle's resampling indices."""
+    from oracle import pf_oracle as O
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import HyperhemisphericalWatsonDistribution, VonMisesFisherDistribution
+    from pyrecest_b200.filters import HyperhemisphereCartProdParticleFilter, IdentityTransition
+
+    prandom.seed(4)
+    n = 20_000
+    pf = HyperhemisphereCartProdParticleFilter(n, 2, 2)
+    pf.filter_state = VonMisesFisherDistribution(np.array([0.0, 0.0, 1.0]), 2.0)
+    z1 = np.array([0.6, 0.0, 0.8])
+    z2 = np.array([0.0, -0.6, 0.8])
+    for _ in range(6):
+        pf.predict_nonlinear_each_part(IdentityTransition(), HyperhemisphericalWatsonDistribution(np.array([0.0, 0.0, 1.0]), 60.0))
+        pf.update_nonlinear_using_likelihood((VonMisesFisherDistribution(z1, 40.0), VonMisesFisherDistribution(z2, 40.0)))
+    est = host(pf.get_point_estimate())
+    assert est.shape == (6,)
+    assert abs(est[:3] @ z1) > 0.99 and abs(est[3:] @ z2) > 0.99, est
+    # resampling indices with injected uniforms == the oracle's (weights from the caller's likelihood values)
+    d = host(pf.filter_state.d)
+    lik = np.exp(3.0 * d[:, 2]) * (1.0 + d[:, 5] ** 2)
+    u = np.random.default_rng(0).random(n)
+    with prandom.inject(uniforms=u):
+        pf.update_nonlinear_using_likelihood(lik)
+    idx = O.multinomial_indices(O.reweigh(O.uniform_w(n), lik), u)
+    assert np.array_equal(host(pf.filter_state.d), d[idx])
+
+
+@pytest.mark.parametrize("q,kappa", [(3, 8.0), (4, 2.5), (4, -6.0), (6, 15.0)])
+def test_watson_sampler_moments(q, kappa):
+    """cart_prod.watson_rows (angular-central-Gaussian rejection): E[(mu . x)^2] equals d/dkappa log 1F1(1/2; q/2; kappa)
+    = 1F1(3/2; q/2 + 1; kappa) / (q 1F1(1/2; q/2; kappa)), and the draws are symmetric about the axis."""
+    from scipy.special import hyp1f1
+
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.cart_prod import watson_rows
+
+    prandom.seed(q)
+    n = 400_000
+    rng = np.random.default_rng(q)
+    mu = rng.standard_normal(q)
+    mu /= np.linalg.norm(mu)
+    modes = torch.as_tensor(mu, device="cuda:0").expand(n, q).contiguous()
+    x = host(watson_rows(modes, kappa))
+    np.testing.assert_allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-12)
+    t = x @ mu
+    want = hyp1f1(1.5, 0.5 * q + 1.0, kappa) / (q * hyp1f1(0.5, 0.5 * q, kappa))
+    assert abs((t * t).mean() - want) < 5.0 * (t * t).std() / math.sqrt(n)
+    assert abs(t.mean()) < 5.0 / math.sqrt(n)
+    perp = x - np.outer(t, mu)
+    assert np.abs(perp.mean(axis=0)).max() < 5.0 / math.sqrt(n)
+
+
+@pytest.mark.parametrize("q,kappa", [(2, 3.0), (4, 1.0), (4, 25.0), (5, 6.0)])
+def test_vmf_rejection_sampler_moments(q, kappa):
+    """cart_prod.vmf_rows (Wood's sampler, S^d with d != 2): mean resultant length A_q(kappa) = I_{q/2}(kappa) / I_{q/2-1}(kappa)
+    along the mode, nothing across it; the pdf of the samples' own distribution integrates consistently (VMF.sample)."""
+    from scipy.special import ive
+
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.cart_prod import vmf_rows
+
+    prandom.seed(10 + q)
+    n = 400_000
+    rng = np.random.default_rng(q)
+    mu = rng.standard_normal(q)
+    mu /= np.linalg.norm(mu)
+    modes = torch.as_tensor(mu, device="cuda:0").expand(n, q).contiguous()
+    x = host(vmf_rows(modes, kappa))
+    np.testing.assert_allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-12)
+    t = x @ mu
+    want = ive(0.5 * q, kappa) / ive(0.5 * q - 1.0, kappa)
+    assert abs(t.mean() - want) < 5.0 * t.std() / math.sqrt(n)
+    perp = x - np.outer(t, mu)
+    assert np.abs(perp.mean(axis=0)).max() < 5.0 / math.sqrt(n)
+
+
+def test_watson_pdf_against_the_reference():
+    """pdf of WatsonDistribution / HyperhemisphericalWatsonDistribution at the mode and across it (values from a run of the
+    reference, watson_distribution.py:70-84, hyperhemispherical_watson_distribution.py:21-22)"""
+    from pyrecest_b200.distributions import HyperhemisphericalWatsonDistribution, WatsonDistribution
+
+    mu = np.array([0.6, 0.0, 0.0, 0.8])
+    xs = np.array([mu, np.roll(mu, 1)])
+    np.testing.assert_allclose(host(WatsonDistribution(mu, 7.5).pdf(xs)), [1.608853460435332, 0.005009204238815092], rtol=1e-12)
+    np.testing.assert_allclose(host(HyperhemisphericalWatsonDistribution(mu, 7.5).pdf(xs)), [3.217706920870664, 0.010018408477630183], rtol=1e-12)
