@@ -48,9 +48,10 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(D, E):
-    """B = 8 (4D + E + 5) per particle-step, split per kernel."""
-    return {"predict_loglik": 8 * (2 * D + E + 1), "scan": 16, "resample": 8 * (2 * D + 2)}
+def algorithmic_bytes(D, E, sb=8):
+    """B = 8 (4D + E + 5) per particle-step, split per kernel (sb: bytes per stored particle / noise
+    component: 4 with --storage f32; weights, CDF and uniforms stay fp64)."""
+    return {"predict_loglik": sb * (2 * D + E) + 8, "scan": 16, "resample": sb * 2 * D + 16}
 
 
 def random_access_roofline(kernel, resampling, n, D, ms, padded=False):
@@ -306,7 +307,8 @@ def run_gpu(args):
     # ---- public-API filter (used for e2e and to build the initial particle set)
     cls = {"torus": Fl.HypertoroidalParticleFilter, "sphere": Fl.HypersphericalParticleFilter,
            "euclid": Fl.EuclideanParticleFilter}[manifold]
-    pf = cls(n, D if manifold != "sphere" else D - 1)
+    sdt = torch.float32 if args.storage == "f32" else torch.float64
+    pf = cls(n, D if manifold != "sphere" else D - 1, dtype=sdt)
     pf.resampling = args.resampling  # 'multinomial' (the reference's scheme, default) or 'systematic'
     pf.filter_state = prior
 
@@ -321,11 +323,11 @@ def run_gpu(args):
     noise_ring, u_ring = [], []
     for _ in range(nbuf):
         if name == "t3":
-            noise_ring.append(src.vonmises((n, 3), torch.as_tensor(P["kappa_noise"]), dev))
+            noise_ring.append(src.vonmises((n, 3), torch.as_tensor(P["kappa_noise"]), dev, sdt))
         elif name == "s2":
-            noise_ring.append(src.vmf_triples(n, dev))
+            noise_ring.append(src.vmf_triples(n, dev, sdt))
         else:
-            noise_ring.append(src.normals((n, D), dev))
+            noise_ring.append(src.normals((n, D), dev, sdt))
         u_ring.append(src.uniforms((n,), dev))
     with prandom.null():  # parameter block for array-fed draws (rng_kind = 0): the value leg reads the ring
         pp, _ = pf._predict_params(trans, noise_dist, pf._default_shift)
@@ -428,7 +430,7 @@ def run_gpu(args):
         sharded = sharded_block(args, world, rank, dev, args.steps, args.warmup, n=args.sharded_particles or None)
     if rank == 0:
         peak, peak_src = peaks()
-        ab = algorithmic_bytes(D, E)
+        ab = algorithmic_bytes(D, E, 4 if args.storage == "f32" else 8)
         names = ["predict_loglik", "scan", "resample"]
         k = int(np.argmax(kt))
         achieved = ab[names[k]] * n / (kt[k] * 1e-3) / 1e9
@@ -441,6 +443,7 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "resampling": args.resampling,
+                       "storage": args.storage + (" (particles and noise draws stored in fp32, arithmetic fp64)" if args.storage == "f32" else ""),
                        "scan": "sequential-exact" if exact else "fast", "likelihood_images": int(lp.n_images) if name == "t3" else None,
                        "l2_policy": f"inputs larger than L2: ring of {nbuf} pre-generated noise/uniform buffers "
                                     f"({n * 8 * (E + 1) / 1e6:.0f} MB each) + {n * 8 * D / 1e6:.0f} MB state",
@@ -840,6 +843,8 @@ def main():
                     "(PFB_WEIGHTS_LOG) instead of the slice-scaled linear weights")
     ap.add_argument("--runs", type=int, default=1250, help="t2mc: independent runs per GPU")
     ap.add_argument("--resampling", default="multinomial_sorted", choices=["multinomial", "multinomial_sorted", "systematic"])
+    ap.add_argument("--storage", default="f64", choices=["f64", "f32"], help="storage type of particles and noise draws (north_star's "
+                    "stated fp32 option; the arithmetic is fp64 either way and the line's dtype says f64)")
     args = ap.parse_args()
     # stdout carries ONE JSON line: libraries that print to file descriptor 1 from native code (NCCL's version banner at
     # communicator init) are sent to stderr; the line itself is written to the saved descriptor
