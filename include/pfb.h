@@ -123,7 +123,7 @@ typedef struct {
   int32_t kind;
   int32_t dim;               /* stored components D */
   int32_t n_images;          /* WN_MULTI: rows of images_dev */
-  int32_t cell_grid;         /* WN_MULTI, D <= 3, n_images <= 64, single measurement: G > 0 says that images_dev is
+  int32_t cell_grid;         /* WN_MULTI, D <= 3, n_images <= 64, G <= 16: G > 0 says that images_dev is
                                 followed by G^D uint64 candidate masks, one per cell of the box dev in
                                 [-pi - mu, pi - mu)^D cut into G cells per dimension (index c_0 + G c_1 + G^2 c_2):
                                 bit k set iff image k can pass the screen somewhere in the cell.  0: screen all. */
@@ -136,10 +136,11 @@ typedef struct {
   const double* mu_batch_dev; /* *_batched only: DEVICE (n_runs, D) likelihood centres, one measurement per run
                                  (NULL: `mu` for every run) */
   int32_t out_format;        /* pfb_weight_format of the `logw` output of the weighting calls */
-  int32_t cell_span;         /* 0: the cell grid covers the box of ONE measurement (above).  1: it covers
-                                dev = wrap(x) - mu in [-3 pi, pi)^D, the union over every mu in [0, 2 pi)^D, with
-                                2 cell_grid cells per dimension -- valid for any measurement, so the *_batched calls
-                                (one mu per run, mu_batch_dev) can use it */
+  int32_t cell_span;         /* bit 0: the cell grid covers dev = wrap(x) - mu in [-3 pi, pi)^D, the union over every mu in
+                                [0, 2 pi)^D, with 2 cell_grid cells per dimension -- valid for any measurement, so the
+                                *_batched calls (one mu per run, mu_batch_dev) can use it; clear: the box of ONE
+                                measurement (above).  bit 1: the masks are uint32 (n_images <= 32), followed by the
+                                reference bytes -- a 16^3 grid then fits the shared memory of a CTA */
 } pfb_lik_params;
 
 /* What the weighting calls (pfb_loglik, pfb_predict_loglik and their *_batched forms) write into `logw`:

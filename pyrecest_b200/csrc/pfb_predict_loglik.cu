@@ -284,27 +284,34 @@ __device__ __forceinline__ double loglik_parts(const pfb_lik_params& L, const do
           const double2 a = lt[2 * k], b = lt[2 * k + 1];
           return fma(a.x, d0, fma(a.y, d1, fma(b.x, d2, b.y)));
         };
-        if (L.cell_grid > 0 && (L.mu_batch_dev == nullptr || L.cell_span == 1)) {
+        if (L.cell_grid > 0 && (L.mu_batch_dev == nullptr || (L.cell_span & 1))) {
           // the host has listed, per cell, the images that can come within e^-39 of the best one anywhere in the cell
           // (registry.wn_cell_masks: a superset that contains the minimiser) and the image that is best at the cell's
           // centre (no image beats it by more than e^500 anywhere in the cell).  The cells cut the box of xs for one
           // measurement (cell_span 0), or the box dev in [-3 pi, pi)^D that holds every measurement (cell_span 1:
           // twice the cells per dimension, one table for all runs of a batched launch)
-          const int G = L.cell_span == 1 ? 2 * L.cell_grid : L.cell_grid;
+          const int G = (L.cell_span & 1) ? 2 * L.cell_grid : L.cell_grid;
           const double inv = (double)L.cell_grid * 0.15915494309189535;  // cells per unit: cell_grid / (2 pi)
           int ci = 0, mul = 1;
 #pragma unroll
           for (int c = 0; c < D; ++c) {
-            int q = (int)((L.cell_span == 1 ? dev[c] + 9.42477796076938 : xs[c]) * inv);
+            int q = (int)(((L.cell_span & 1) ? dev[c] + 9.42477796076938 : xs[c]) * inv);
             q = q < 0 ? 0 : (q >= G ? G - 1 : q);
             ci += q * mul;
             mul *= G;
           }
-          const uint2* cells = reinterpret_cast<const uint2*>(lt + 2 * K);
-          const uint2 cand = cells[ci];
-          mlo = cand.x;
-          mhi = cand.y;
-          kref = reinterpret_cast<const unsigned char*>(cells + mul)[ci];
+          if (L.cell_span & 2) {  // at most 32 images: 32-bit masks (a 16^3 grid fits the shared memory of a CTA)
+            const uint32_t* cells = reinterpret_cast<const uint32_t*>(lt + 2 * K);
+            mlo = cells[ci];
+            mhi = 0u;
+            kref = reinterpret_cast<const unsigned char*>(cells + mul)[ci];
+          } else {
+            const uint2* cells = reinterpret_cast<const uint2*>(lt + 2 * K);
+            const uint2 cand = cells[ci];
+            mlo = cand.x;
+            mhi = cand.y;
+            kref = reinterpret_cast<const unsigned char*>(cells + mul)[ci];
+          }
         } else {
           mlo = K >= 32 ? 0xFFFFFFFFu : ((1u << K) - 1u);
           mhi = K > 32 ? (K >= 64 ? 0xFFFFFFFFu : ((1u << (K - 32)) - 1u)) : 0u;
@@ -492,11 +499,12 @@ __device__ __forceinline__ const double* stage_images(const pfb_lik_params& L, d
     if (L.cell_grid > 0) {  // candidate masks of the cell grid, after the linear rows
       uint64_t* cells = reinterpret_cast<uint64_t*>(lt + 4 * K);
       const uint64_t* src = reinterpret_cast<const uint64_t*>(L.images_dev + count);
-      const int G = L.cell_span == 1 ? 2 * L.cell_grid : L.cell_grid;
+      const int G = (L.cell_span & 1) ? 2 * L.cell_grid : L.cell_grid;
       int nc = G;
       if (D > 1) nc *= G;
       if (D > 2) nc *= G;
-      for (int k = threadIdx.x; k < nc + (nc + 7) / 8; k += blockDim.x) cells[k] = src[k];  // masks, then the reference bytes
+      const int words = (L.cell_span & 2) ? (nc * 5 + 7) / 8 : nc + (nc + 7) / 8;  // masks (4 or 8 bytes), then the reference bytes
+      for (int k = threadIdx.x; k < words; k += blockDim.x) cells[k] = src[k];
     }
   }
   __syncthreads();
@@ -811,8 +819,8 @@ static size_t lik_smem(const pfb_lik_params* L) {
   size_t cells = 0;
   if (L->cell_grid > 0) {
     cells = 1;
-    for (int c = 0; c < L->dim; ++c) cells *= (size_t)(L->cell_span == 1 ? 2 * L->cell_grid : L->cell_grid);
-    cells = cells * 8 + ((cells + 7) / 8) * 8;  // masks + one reference byte per cell
+    for (int c = 0; c < L->dim; ++c) cells *= (size_t)((L->cell_span & 1) ? 2 * L->cell_grid : L->cell_grid);
+    cells = (L->cell_span & 2) ? ((cells * 5 + 7) / 8) * 8 : cells * 8 + ((cells + 7) / 8) * 8;  // masks + one reference byte per cell
   }
   return (size_t)L->n_images * (2 * L->dim + 1) * 8 + 8 + (size_t)L->n_images * 32 + cells;
 }
@@ -825,10 +833,10 @@ static int check_lik(const pfb_lik_params* L, int dim) {
   if ((L->kind == PFB_LIK_WN_1D || L->kind == PFB_LIK_VM) && dim != 1) { set_error("likelihood kind %d is circular (dim 1), got %d", L->kind, dim); return PFB_ERR_INVALID; }
   if (L->kind == PFB_LIK_WN_MULTI) {
     if (L->n_images < 1 || !L->images_dev) { set_error("wn_multi needs an image table"); return PFB_ERR_INVALID; }
-    if (L->cell_span != 0 && L->cell_span != 1) { set_error("bad cell_span %d", L->cell_span); return PFB_ERR_INVALID; }
+    if (L->cell_span < 0 || L->cell_span > 3 || ((L->cell_span & 2) && L->n_images > 32)) { set_error("bad cell_span %d (bit 1, 32-bit masks, needs at most 32 images)", L->cell_span); return PFB_ERR_INVALID; }
     if ((int64_t)lik_smem(L) > 40 * 1024) { set_error("image table too large (%d rows, cell grid %d)", L->n_images, L->cell_grid); return PFB_ERR_INVALID; }
-    if (L->cell_grid != 0 && (L->cell_grid < 1 || L->cell_grid > 8 || dim > 3 || L->n_images > 64)) {
-      set_error("cell_grid %d: candidate masks need 1 <= G <= 8, dim <= 3 and at most 64 images", L->cell_grid);
+    if (L->cell_grid != 0 && (L->cell_grid < 1 || L->cell_grid > 16 || dim > 3 || L->n_images > 64)) {
+      set_error("cell_grid %d: candidate masks need 1 <= G <= 16, dim <= 3 and at most 64 images", L->cell_grid);
       return PFB_ERR_INVALID;
     }
   }

@@ -226,18 +226,23 @@ def wn_image_table_cached(mu, P, device_put=None):
     hit = _IMAGE_TABLE_CACHE.get(key)
     if hit is None:
         table, n_img = wn_image_table(mu, P)
-        cells = wn_cell_masks(mu, table)
+        # at most 32 images: 32-bit masks and a 16-per-dimension grid (4096 cells of 5 bytes for T^3: fewer candidates
+        # per cell, 3.0 -> 2.4 on average and 5.6 -> 3.6 for the slowest lane of a warp); else 8 per dimension
+        narrow = n_img <= 32
+        G = WN_CELL_GRID_FINE if narrow else WN_CELL_GRID
+        cells = wn_cell_masks(mu, table, G=G)
         if cells is not None:
-            cells = wn_cell_table(mu, table, cells)
+            cells = wn_cell_table(mu, table, cells, G=G, narrow=narrow)
         flat = table.reshape(-1) if cells is None else np.concatenate([table.reshape(-1), cells.view(np.float64)])
         dev = device_put(flat) if device_put is not None else None
         if len(_IMAGE_TABLE_CACHE) > 256:
             _IMAGE_TABLE_CACHE.clear()
-        hit = _IMAGE_TABLE_CACHE[key] = (table, n_img, dev, 0 if cells is None else WN_CELL_GRID)
+        hit = _IMAGE_TABLE_CACHE[key] = (table, n_img, dev, 0 if cells is None else G, 2 if (cells is not None and narrow) else 0)
     return hit
 
 
 WN_CELL_GRID = 8       # cells per dimension of the candidate grid
+WN_CELL_GRID_FINE = 16 # ... when the masks are 32-bit (at most 32 images)
 WN_SCREEN_CUT = 78.0   # kScreenCut of pfb_predict_loglik.cu
 
 
@@ -275,7 +280,7 @@ def wn_cell_masks(mu, table, G=WN_CELL_GRID, any_mean=False):
     return out
 
 
-def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0, any_mean=False):
+def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0, any_mean=False, narrow=False):
     """Device form of the candidate grid: the uint64 masks followed by one reference byte per cell (padded to 8
     bytes) -- the image that is best at the cell's centre, t_k = g_k.dev + h_k / 2 smallest.  The kernel anchors the
     image sum there: exact quadratic form of the reference image, every other candidate through exp(-(t_k - t_ref)).
@@ -296,7 +301,14 @@ def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0, any_mean=False)
     gain = np.maximum(dg * a[:, None, :], dg * b[:, None, :]).sum(axis=-1) + 0.5 * (h[ref][:, None] - h[None, :])
     if np.any(np.where(bits, gain, -np.inf) > limit):
         return None
-    refs = np.zeros(((n_cells ** d + 7) // 8) * 8, dtype=np.uint8)
+    nc = n_cells ** d
+    if narrow:  # uint32 masks, then the reference bytes, padded to 8 bytes in all
+        assert K <= 32
+        out = np.zeros(((nc * 5 + 7) // 8) * 8, dtype=np.uint8)
+        out[: nc * 4] = masks.astype(np.uint32).view(np.uint8)
+        out[nc * 4 + flat] = ref.astype(np.uint8)
+        return out.view(np.uint64)
+    refs = np.zeros(((nc + 7) // 8) * 8, dtype=np.uint8)
     refs[flat] = ref.astype(np.uint8)
     return np.concatenate([masks.view(np.uint8), refs]).view(np.uint64)
 
@@ -372,9 +384,10 @@ def lik_params(dist, dim, images_to_device=None):
             raise AssertionError("likelihood dimension does not match the filter state")
         C = np.atleast_2d(_np(dist.C))
         W, logdet = gaussian_whitening(C)
-        table, n_img, dev_table, cell_grid = wn_image_table_cached(mu, W @ W.T, images_to_device)
+        table, n_img, dev_table, cell_grid, cell_flags = wn_image_table_cached(mu, W @ W.T, images_to_device)
         p.kind = L.LIK_WN_MULTI
         p.cell_grid = cell_grid if dev_table is not None else 0
+        p.cell_span = cell_flags if dev_table is not None else 0
         p.mu[:dim] = mu.tolist()
         p.W[: dim * dim] = W.reshape(-1).tolist()
         p.logc = -0.5 * (dim * math.log(TWO_PI) + logdet)

@@ -198,31 +198,63 @@ def test_vm_strip_sampler_restatement_is_von_mises():
         assert stats.kstest(x[:, c], stats.vonmises(kap[c]).cdf).pvalue > 1e-4
 
 
+@pytest.mark.parametrize("any_mean", [False, True])
+@pytest.mark.parametrize("G", [8, 16])
 @pytest.mark.parametrize("d", [1, 2, 3])
-def test_wn_cell_masks_cover_the_full_screen(d):
-    """registry.wn_cell_masks: at every point of the dev box, the images the kernel's full screen would evaluate
-    (r_k <= min r + cut) are inside the candidate mask of the point's cell, and so is the minimiser"""
+def test_wn_cell_masks_cover_the_full_screen(d, G, any_mean):
+    """registry.wn_cell_masks / wn_cell_table: at every point of the dev box, the images that can matter
+    (r_k <= min r + cut) are inside the candidate mask of the point's cell, and so is the minimiser; the cell's
+    reference image is one of its candidates.  Both grids (8 and 16 per 2 pi) and both boxes: one measurement, and the
+    measurement-independent box dev in [-3 pi, pi)^d of the batched calls (2 G cells per dimension)."""
     from pyrecest_b200 import registry as R
 
+    if any_mean and G == 16 and d == 3:
+        pytest.skip("32^3 cells: not a configuration the host builds")
     rng = np.random.default_rng(d)
     A = rng.normal(size=(d, d))
     C = A @ A.T / d + 0.2 * np.eye(d)
     mu = rng.random(d) * 2 * np.pi
     W, _ = R.gaussian_whitening(C)
-    table, K = R.wn_image_table(mu, W @ W.T)
-    masks = R.wn_cell_masks(mu, table)
-    G = R.WN_CELL_GRID
-    assert masks.shape == (G**d,) and masks.dtype == np.uint64
+    if any_mean:  # the united table of evaluation._wn_params_any_mean
+        rows = {}
+        for corner in np.array(np.meshgrid(*[[0.0, 2 * np.pi]] * d)).T.reshape(-1, d):
+            t, _ = R.wn_image_table(corner, W @ W.T)
+            for row in t:
+                rows[tuple(np.round(row[d + 1:] / (2 * np.pi)).astype(int))] = row
+        table = np.array([rows[k] for k in sorted(rows, key=lambda kk: rows[kk][d])])
+        K = table.shape[0]
+    else:
+        table, K = R.wn_image_table(mu, W @ W.T)
+    masks = R.wn_cell_masks(mu, table, G=G, any_mean=any_mean)
+    if masks is None:
+        assert K > 64
+        return
+    n_cells = 2 * G if any_mean else G
+    assert masks.shape == (n_cells**d,) and masks.dtype == np.uint64
     g, h = table[:, :d], table[:, d]
     y = rng.random((20_000, d)) * 2 * np.pi - np.pi  # wrapped particle coordinate
-    dev = y - mu
+    mus = rng.random((20_000, d)) * 2 * np.pi if any_mean else mu
+    dev = y - mus
     r = 2.0 * dev @ g.T + h
     need = r <= r.min(axis=1, keepdims=True) + R.WN_SCREEN_CUT
-    q = np.clip(((dev + (np.pi + mu)) * (G / (2 * np.pi))).astype(int), 0, G - 1)
-    cell = (q * (G ** np.arange(d))).sum(axis=1)
+    lo = -3 * np.pi if any_mean else -(np.pi + mu)
+    q = np.clip(((dev - lo) * (G / (2 * np.pi))).astype(int), 0, n_cells - 1)
+    cell = (q * (n_cells ** np.arange(d))).sum(axis=1)
     have = ((masks[cell][:, None] >> np.arange(K, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
     assert np.all(have[need])
     assert have.sum(axis=1).mean() < K  # and it prunes
+    for narrow in ([False, True] if K <= 32 else [False]):
+        tab = R.wn_cell_table(mu, table, masks, G=G, any_mean=any_mean, narrow=narrow)
+        assert tab is not None
+        raw = tab.view(np.uint8)
+        nc = n_cells**d
+        refs = raw[nc * 4: nc * 5] if narrow else raw[nc * 8: nc * 9]
+        m2 = raw[: nc * 4].view(np.uint32).astype(np.uint64) if narrow else raw[: nc * 8].view(np.uint64)
+        assert np.array_equal(m2, masks)
+        assert np.all((masks >> refs.astype(np.uint64)) & np.uint64(1))  # the reference image is a candidate of its cell
+        # and it is the best image at the cell's centre among the candidates
+        t_ref = 0.5 * r[np.arange(r.shape[0]), refs[cell]]
+        assert np.all(t_ref - 0.5 * r.min(axis=1) <= 500.0)
 
 
 def test_graft_entry_build_runs():

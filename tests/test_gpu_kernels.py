@@ -647,9 +647,10 @@ def test_wn_cell_masks_do_not_change_the_likelihood(eng, golden):
         out = []
         for grid in (None, 0):
             lp, keep = R.lik_params(_dist("HypertoroidalWrappedNormalDistribution", mu=mu, C=Cc), D, images_to_device=dev)
-            assert lp.cell_grid == (R.WN_CELL_GRID if lp.n_images <= 64 else 0)  # (masks are uint64)
+            assert lp.cell_grid == (R.WN_CELL_GRID_FINE if lp.n_images <= 32 else (R.WN_CELL_GRID if lp.n_images <= 64 else 0))
+            assert lp.cell_span == (2 if lp.n_images <= 32 else 0)  # (32-bit masks on the fine grid, else uint64)
             if grid is not None:
-                lp.cell_grid = grid
+                lp.cell_grid, lp.cell_span = grid, 0
             logw = torch.empty(x.shape[0], dtype=torch.float64, device="cuda:0")
             eng.loglik(lp, x, logw)
             out.append(host(logw))
