@@ -677,7 +677,7 @@ __device__ __forceinline__ void weight_tiles(Seg sg, double* logw, double* stats
 }
 
 template <typename T, int D, int KIND, bool SCALED>
-__global__ void __launch_bounds__(kThreads, KIND == PFB_LIK_WN_MULTI ? 5 : 4) loglik_kernel(pfb_lik_params L, Seg sg,
+__global__ void __launch_bounds__(kThreads, 4) loglik_kernel(pfb_lik_params L, Seg sg,
                                                           const T* __restrict__ x,
                                                           const double* __restrict__ w_prev,
                                                           double* logw, double* stats,
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, KIND == PFB_LIK_WN_MULTI ? 5 : 4) lo
 }
 
 template <typename T, int D, int MODE, int KIND, bool RNG, bool SCALED, bool PLAIN>
-__global__ void __launch_bounds__(kThreads, (RNG || KIND != PFB_LIK_WN_MULTI) ? 4 : 5) predict_loglik_kernel(pfb_predict_params p,
+__global__ void __launch_bounds__(kThreads, 4) predict_loglik_kernel(pfb_predict_params p,
                                                                   pfb_lik_params L, Seg sg,
                                                                   const T* x_in, T* x_out,
                                                                   const T* __restrict__ noise,
