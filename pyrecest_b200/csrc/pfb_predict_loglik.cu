@@ -287,7 +287,7 @@ __device__ __forceinline__ double loglik_parts(const pfb_lik_params& L, const do
         if (L.cell_grid > 0 && (L.mu_batch_dev == nullptr || (L.cell_span & 1))) {
           // the host has listed, per cell, the images that can come within e^-39 of the best one anywhere in the cell
           // (registry.wn_cell_masks: a superset that contains the minimiser) and the image that is best at the cell's
-          // centre (no image beats it by more than e^500 anywhere in the cell).  The cells cut the box of xs for one
+          // centre (no image beats it by more than e^60 anywhere in the cell).  The cells cut the box of xs for one
           // measurement (cell_span 0), or the box dev in [-3 pi, pi)^D that holds every measurement (cell_span 1:
           // twice the cells per dimension, one table for all runs of a batched launch)
           const int G = (L.cell_span & 1) ? 2 * L.cell_grid : L.cell_grid;

@@ -280,12 +280,13 @@ def wn_cell_masks(mu, table, G=WN_CELL_GRID, any_mean=False):
     return out
 
 
-def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=500.0, any_mean=False, narrow=False):
+def wn_cell_table(mu, table, masks, G=WN_CELL_GRID, limit=60.0, any_mean=False, narrow=False):
     """Device form of the candidate grid: the uint64 masks followed by one reference byte per cell (padded to 8
     bytes) -- the image that is best at the cell's centre, t_k = g_k.dev + h_k / 2 smallest.  The kernel anchors the
     image sum there: exact quadratic form of the reference image, every other candidate through exp(-(t_k - t_ref)).
     Returns None (no grid: the kernel finds the best image itself) if some candidate could beat the reference by more
-    than e^limit somewhere in its cell (tiny covariances), where that exp would overflow."""
+    than e^limit somewhere in its cell (tiny covariances): the image sum `lin` then stays below K e^limit, so that the
+    slice-scaled weight exp(a - c) * lin of the weighting kernel (a - c <= 600 by its rescaling rule) cannot overflow."""
     d = table.shape[1] // 2
     K = table.shape[0]
     g, h = table[:, :d], table[:, d]

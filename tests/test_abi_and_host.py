@@ -244,7 +244,7 @@ def test_wn_cell_masks_cover_the_full_screen(d, G, any_mean):
     assert np.all(have[need])
     assert have.sum(axis=1).mean() < K  # and it prunes
     for narrow in ([False, True] if K <= 32 else [False]):
-        tab = R.wn_cell_table(mu, table, masks, G=G, any_mean=any_mean, narrow=narrow)
+        tab = R.wn_cell_table(mu, table, masks, G=G, any_mean=any_mean, narrow=narrow, limit=500.0)
         assert tab is not None
         raw = tab.view(np.uint8)
         nc = n_cells**d
