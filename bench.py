@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of the fused predict + update + resample + estimate step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload t3|s2|r2|r4] [--particles P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload t3|s2|r2|r4|r4s|t2mc] [--particles P]
+                  [--resampling multinomial_sorted|multinomial|systematic] [--storage f64|f32]
   python bench.py --impl reference ...      # the CPU restatement of the reference (oracle/) on host cores
 
 Workload at N=1 (BASELINE.json configs[1]): HypertoroidalParticleFilter on T^3, 1e8 particles, von Mises
 system noise (kappa = 10 per dim), wrapped-normal likelihood (cov 0.5 C, z = [1, 2, 3], m = 3, i.e. the
-reference's 343-image sum), multinomial resampling of N of N, mean-direction estimate.  fp64.
+reference's 343-image sum), exact multinomial resampling of N of N (offspring in CDF order; --resampling multinomial is
+the reference's order), mean-direction estimate.  fp64.
 N > 1 (torchrun): every rank runs an independent filter of the same size (independent Monte-Carlo runs shard
-with no communication -- north_star), "scaling": "weak".
+with no communication -- north_star), "scaling": "weak"; the line's `sharded` block then reports configs[4]: ONE R^4
+filter sharded over all ranks (1.25e8 particles per GPU, global systematic resampling over NVLink).
 
 value : steps timed with CUDA events, noise draws + uniforms already resident in HBM (a ring of
         pre-generated buffers larger than L2), 3 kernel launches per step through the C ABI.
@@ -436,8 +439,9 @@ def run_gpu(args):
         achieved = ab[names[k]] * n / (kt[k] * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(name, n, args.resampling, exact, names[k])
         step_gbs = sum(ab.values()) * n / (ms_step * 1e-3) / 1e9
-        cpu_n = args.cpu_particles
-        cpu_val, cpu_s = run_cpu(name, cpu_n, 2, 1) if not args.no_cpu else (None, None)
+        cpu_n = min(args.cpu_particles, n)  # (a filter smaller than the CPU sample, configs[0]: the CPU arm at the same N)
+        cpu_steps = 2 if cpu_n >= 100_000 else 50
+        cpu_val, cpu_s = run_cpu(name, cpu_n, cpu_steps, 1) if not args.no_cpu else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -463,7 +467,7 @@ def run_gpu(args):
             "cpu_baseline": None if args.no_cpu else {
                 "value": cpu_val, "unit": "particle-steps/s", "cores": cpu_threads(), "kind": "port",
                 "sample": f"oracle/pf_oracle.py (vectorised numpy restatement, predict + likelihood split over {cpu_threads()} host threads) "
-                          f"on {cpu_n} particles x 2 steps of the same workload, {cpu_s:.2f} s/step"},
+                          f"on {cpu_n} particles x {cpu_steps} steps of the same workload, {cpu_s:.4f} s/step"},
         }
         if sharded is not None:
             line["sharded"] = sharded
@@ -707,7 +711,8 @@ def run_mc(args):
 
 def run_sharded(args):
     """configs[4]: one EuclideanParticleFilter over all ranks (pyrecest_b200.sharded), in-kernel Philox noise,
-    global systematic resampling over NCCL (all_reduce max, all_gather totals, all_to_all_v offspring)."""
+    global systematic resampling (all_reduce max, all_gather totals, pull-form resampling kernel reading peer memory
+    over NVLink, all_reduce of the estimate sums)."""
     import torch
     import torch.distributed as dist
 
@@ -788,7 +793,7 @@ def run_sharded(args):
             "config": {"workload": f"{name}: {desc}", "particles_per_gpu": n, "particles_total": n * world,
                        "resampling": "systematic (global)", "scan": "sequential-exact per shard",
                        "l2_policy": f"state {n * 8 * D / 1e6:.0f} MB per GPU, far larger than L2",
-                       "parallelism": f"particles sharded over {world} GPU(s); all_reduce(max) + all_gather(totals) per step, offspring stored into the owner rank's buffer by the scatter kernel (peer stores over NVLink), all_reduce(sum) of the estimate"},
+                       "parallelism": f"particles sharded over {world} GPU(s); all_reduce(max) + all_gather(totals) per step, every rank produces its own output slots and reads remote sources from the peers' buffers (NVLink loads) inside the resampling kernel, all_reduce(sum) of the estimate"},
             "e2e": {"value": world * n / (float(e2e_ms) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(e2e_ms),
                     "h2d_bytes_per_step": int(8 * D), "d2h_bytes_per_step": int(8 * D + 8 * world),
                     "path": "public API: ShardedParticleFilter.predict_nonlinear + update + get_point_estimate"},
