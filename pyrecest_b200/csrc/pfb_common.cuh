@@ -159,13 +159,66 @@ __device__ __forceinline__ uint4 rng_block(const RngKey& k, uint64_t index, uint
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return (double)((((uint64_t)a << 32) | b) >> 11) * 1.1102230246251565e-16;
 }
+// ---- log and sincospi for the Box-Muller transform ------------------------------------------------------------
+// The library versions cost ~60 and ~70 instructions here (every fp64 literal is materialised with two moves next to
+// the FMA that uses it); the kernels that draw their own normals (R^d filters, wrapped-normal noise, the batched and
+// the sharded filter) are issue-bound on exactly that.  Same accuracy class (< 2 ulp), coefficients in constant memory.
+//
+// fast_log(x), 2^-1022 <= x <= 1 (normal numbers): x = m 2^e, m in [1, 2); j = round((m - 1) 128), table entry
+// (A_j, L_j) with m A_j = 1 + r, |r| <= 2^-8, log x = (e + [j >= 64]) ln 2 + L_j + log1p(r).  Entries 0 and 128 are
+// exact (A = 1 resp. 1/2, L = 0), so log(1) = 0 and values just below 1 lose nothing to cancellation.
+__device__ const double2 kLogTab[129] = {
+#include "pfb_log_table.inc"
+};
+static __constant__ double kLogCoef[10] = {
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,  // ln 2: high part (32 significant bits), low part
+    // log1p(r) / r on |r| <= 2^-8 (Chebyshev interpolant, degree 7, error 3e-19 of 2^-8)
+    -0.3446376251677561, 0.14308502155395733, -0.1666603624887342, 0.19999999345180994, -0.2500000000492417,
+    0.33333333333338416, -0.49999999999999994, 1.0};
+__device__ __forceinline__ double fast_log(double x) {
+  const long long bits = __double_as_longlong(x);
+  const int hi = (int)(bits >> 32);
+  const int j = (((hi >> 12) & 0xff) + 1) >> 1;                 // round((m - 1) 128): top 8 mantissa bits, rounded
+  const int e = ((hi >> 20) & 0x7ff) - 1023 + (j >> 6 ? 1 : 0);  // (j >= 64 also covers j == 128)
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double2 t = __ldg(&kLogTab[j]);
+  const double r = fma(m, t.x, -1.0);
+  double q = kLogCoef[2];
+#pragma unroll
+  for (int k = 3; k < 10; ++k) q = fma(q, r, kLogCoef[k]);
+  const double ed = (double)e;
+  return fma(ed, kLogCoef[0], t.y + fma(r, q, ed * kLogCoef[1]));
+}
+// sin(pi t), cos(pi t) for 0 <= t < 2: t = k / 2 + r, |r| <= 1/4; sin(pi r) / r and cos(pi r) as polynomials in r^2
+// (Chebyshev interpolants, absolute error 3e-17), then the quadrant.
+static __constant__ double kTrigCoef[17] = {
+    -3.0361360815105725e-05, 0.0004681824775472955, -0.007370594536623111, 0.08214589369866764, -0.5992645294795359,
+    2.5501640398790455, -5.1677127800499765, 3.141592653589793,                                          // sin(pi r) / r
+    -1.960666668533104e-05, -8.73282354687988e-05, 0.0019264845203986242, -0.025806646050006207, 0.23533062036880426,
+    -1.3352627686441232, 4.058712126414695, -4.934802200544673, 1.0};                                     // cos(pi r)
+__device__ __forceinline__ void fast_sincospi_02(double t, double* sn, double* cs) {
+  const double kd = rint(t + t);        // 0 .. 4
+  const int k = (int)kd;
+  const double r = fma(kd, -0.5, t);    // exact
+  const double w = r * r;
+  double ps = kTrigCoef[0], pc = kTrigCoef[8];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) ps = fma(ps, w, kTrigCoef[i]);
+#pragma unroll
+  for (int i = 9; i < 17; ++i) pc = fma(pc, w, kTrigCoef[i]);
+  const double s = ps * r, c = pc;
+  // angle = k pi / 2 + pi r:  k odd swaps sine and cosine; signs by quadrant
+  const double s1 = (k & 1) ? c : s, c1 = (k & 1) ? s : c;
+  *sn = (k & 2) ? -s1 : s1;
+  *cs = ((k + 1) & 2) ? -c1 : c1;
+}
 // two independent standard normals from one Philox block (Box-Muller; u1 in (0, 1])
 __device__ __forceinline__ void normal_pair(const uint4& r, double* z0, double* z1) {
   const double u1 = 1.0 - u53(r.x, r.y);
   const double u2 = u53(r.z, r.w);
-  const double rad = sqrt(-2.0 * log(u1));
+  const double rad = sqrt(-2.0 * fast_log(u1));
   double sn, cs;
-  sincospi(2.0 * u2, &sn, &cs);
+  fast_sincospi_02(2.0 * u2, &sn, &cs);
   *z0 = rad * cs;
   *z1 = rad * sn;
 }
