@@ -227,3 +227,33 @@ def test_fused_euclid_step_matches_oracle_at_scale():
     rep = _index_parity_report("r4_fused_10000000", got, ref, u, row_tol=1e-12)
     np.testing.assert_allclose(est, got.mean(axis=0), rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(est, ref["est"], atol=(rep["differing"] + 1) * 20.0 / n)
+
+
+def test_fused_sphere_step_matches_oracle_at_scale():
+    """S^2, von Mises-Fisher noise and likelihood (configs[2]'s model), 10^7 particles through the public API against the
+    oracle on identical injected (u, z1, z2) triples and uniforms."""
+    from oracle import pf_oracle as O
+    from pyrecest_b200 import random as prandom
+    from pyrecest_b200.distributions import VonMisesFisherDistribution as VMF
+    from pyrecest_b200.filters import HypersphericalParticleFilter
+
+    n = 10_000_000
+    rng = np.random.default_rng(77)
+    d0 = rng.standard_normal((n, 3))
+    d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+    trip = np.column_stack([rng.random(n), rng.standard_normal((n, 2))])
+    u = rng.random(n)
+    z = np.array([1.0, 1.0, 1.0]) / math.sqrt(3)
+    pf = HypersphericalParticleFilter(n, 2, device=DEV)
+    pf.filter_state.d = d0
+    with prandom.inject(vmf_triples=trip, uniforms=u):
+        pf.predict_identity(VMF(np.array([0.0, 0.0, 1.0]), 50.0))
+        pf.update_nonlinear_using_likelihood(VMF(z, 10.0))
+        est = pf.get_point_estimate().cpu().numpy()
+    got = pf.filter_state.d.cpu().numpy()
+    ref = O.step("sphere", d0, trip, "vmf", {"mu": z, "kappa": 10.0}, u, kappa_noise=50.0)
+    # (the sampler's sqrt / log / divisions round differently: rows agree to 1e-13 instead of bit for bit)
+    rep = _index_parity_report("s2_fused_10000000", got, ref, u, row_tol=1e-12)
+    m = got.mean(axis=0)
+    np.testing.assert_allclose(est, m / np.linalg.norm(m), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(est, ref["est"], atol=(rep["differing"] + 1) * 10.0 / n)
