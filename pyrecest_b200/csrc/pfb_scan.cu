@@ -636,30 +636,72 @@ __device__ __forceinline__ double hard_tile_walk(const double (&p)[kItems], int 
     const double u = ulp_value(ue);
     bool ok;
     const long long S0 = int_of(cur, e, &ok);
-    PMap f; f.e = 0; f.o = 0;
-#pragma unroll
-    for (int k = 0; k < kItems; ++k)
-      if (tb + k >= pos && tb + k < cnt) f = pmap_then(f, pmap_of(p[k], ue));
-    PMap tot;
-    const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
-    long long S = pmap_apply(g, S0);
     int mine = 0x7fffffff;
-    long long S_before = 0;
+    long long S_before = 0, S_end;
+    // Floating-point form of the increments (as in scan_maps_kernel) when the binade is not at the bottom of the range
+    // and no remaining addend is a tie: the pass is then a plain int64 scan -- a third of the cost of the parity-map
+    // form.  Increments are clamped at 2^54 (any value >= 2^53 only ever means "this crosses into the next binade",
+    // and nothing before the first crossing is clamped), so that the block-wide sums cannot overflow.
+    constexpr long long kClamp = 0x0040000000000000LL;
+    bool tie = false;
+    long long incs[kItems];
+    const bool fast = ue >= kFastUlpMin;
+    if (fast) {
+      const double inv_ulp = ulp_value(-ue);
 #pragma unroll
-    for (int k = 0; k < kItems; ++k) {
-      if (tb + k >= pos && tb + k < cnt) {
-        const long long Sp = S;
-        S = pmap_apply(pmap_of(p[k], ue), S);
-        if (S >= 0x0020000000000000LL) {
-          if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
-        } else {
-          c[k] = (double)S * u;
+      for (int k = 0; k < kItems; ++k) {
+        incs[k] = 0;
+        if (tb + k >= pos && tb + k < cnt) {
+          const double kk = p[k] * inv_ulp;
+          incs[k] = (kk < 1.8014398509481984e16) ? inc_of_fast(p[k], inv_ulp, &tie) : kClamp;  // (2^54)
         }
       }
     }
+    if (fast && !__syncthreads_or(tie ? 1 : 0)) {
+      long long tsum = 0;
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) { tsum += incs[k]; tsum = tsum < kClamp ? tsum : kClamp; }
+      long long tot;
+      long long S = S0 + block_excl_scan_ll(tsum, s_ll, &tot);
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        if (tb + k >= pos && tb + k < cnt) {
+          const long long Sp = S;
+          S += incs[k];
+          if (S >= 0x0020000000000000LL) {
+            if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
+            S = kClamp;  // (stays a crossing for the rest of the thread's elements, without overflow)
+          } else {
+            c[k] = (double)S * u;
+          }
+        }
+      }
+      S_end = S0 + tot;
+    } else {
+      PMap f; f.e = 0; f.o = 0;
+#pragma unroll
+      for (int k = 0; k < kItems; ++k)
+        if (tb + k >= pos && tb + k < cnt) f = pmap_then(f, pmap_of(p[k], ue));
+      PMap tot;
+      const PMap g = block_excl_scan_pmap(f, s_ll, &tot);
+      long long S = pmap_apply(g, S0);
+#pragma unroll
+      for (int k = 0; k < kItems; ++k) {
+        if (tb + k >= pos && tb + k < cnt) {
+          const long long Sp = S;
+          S = pmap_apply(pmap_of(p[k], ue), S);
+          if (S >= 0x0020000000000000LL) {
+            if (mine == 0x7fffffff) { mine = tb + k; S_before = Sp; }
+          } else {
+            c[k] = (double)S * u;
+          }
+        }
+      }
+      S_end = pmap_apply(tot, S0);
+    }
     const int first = block_min_int(mine, s_int);
     if (first >= cnt) {  // no crossing left: the tile ends inside this binade
-      cur = (double)pmap_apply(tot, S0) * u;
+      cur = (double)S_end * u;
       break;
     }
     if (first == mine) {
