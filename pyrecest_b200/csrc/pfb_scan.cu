@@ -474,6 +474,81 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(TileState ts, int64_t
   }
 }
 
+// The same prefix for long inputs, three small launches instead of one CTA walking all tiles (88 us of an otherwise
+// idle GPU at 49 k tiles): chunk maxima of the tile exponents (scaled input only) -> prefix inside every chunk of 1024
+// tiles + chunk totals -> carries.  `part`: 2 * nchunks doubles of the workspace's reduction partials.
+__global__ void __launch_bounds__(1024) tile_prefix_max_kernel(TileState ts, int64_t ntiles, double* __restrict__ part) {
+  __shared__ double s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  double m = warp_max(t < ntiles ? ts.tmax[t] : -INFINITY);
+  if (lane == 0) s_warp[warp] = m;
+  __syncthreads();
+  m = warp_max(s_warp[lane]);
+  if (threadIdx.x == 0) part[blockIdx.x] = m;
+}
+__global__ void __launch_bounds__(1024) tile_prefix_local_kernel(TileState ts, int64_t ntiles,
+                                                                 const double* __restrict__ max_ptr, int scaled, int nchunks,
+                                                                 double* __restrict__ part) {
+  __shared__ double s_warp[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double M = max_ptr ? *max_ptr : 0.0;
+  if (scaled) {  // the common exponent E = largest tile exponent = largest chunk maximum
+    double m = -INFINITY;
+    for (int c = threadIdx.x; c < nchunks; c += 1024) m = fmax(m, part[c]);
+    m = warp_max(m);
+    if (lane == 0) s_warp[warp] = m;
+    __syncthreads();
+    M = warp_max(s_warp[lane]);
+    __syncthreads();
+  }
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  double v = 0.0;
+  if (t < ntiles) {
+    const double tm = ts.tmax[t];
+    const double sc = scaled ? ((tm == -INFINITY) ? 0.0 : pow2_of(tm - M)) : (max_ptr ? ((tm == -INFINITY) ? 0.0 : exp(tm - M)) : 1.0);
+    v = ts.tsum[t] * sc;
+  }
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const double w = s_warp[lane];
+    double wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double x = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += x;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  if (t < ntiles) {
+    ts.aprefix[t] = s_warp[warp] + (inc - v);  // (inside the chunk; the carry is added by the next launch)
+    ts.tsum[t] = v;
+    ts.tmax[t] = M;
+  }
+  if (threadIdx.x == 0) part[nchunks + blockIdx.x] = s_warp[32];
+}
+__global__ void __launch_bounds__(1024) tile_prefix_carry_kernel(TileState ts, int64_t ntiles, int nchunks,
+                                                                 const double* __restrict__ part) {
+  __shared__ double s_carry;
+  if (threadIdx.x == 0) {  // chunk totals added in chunk order (<= 1024 of them)
+    double carry = 0.0;
+    for (int c = 0; c < (int)blockIdx.x; ++c) carry += part[nchunks + c];
+    s_carry = carry;
+  }
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (t < ntiles && blockIdx.x > 0) ts.aprefix[t] = s_carry + ts.aprefix[t];
+}
+
 // ---- the scan proper: three kernels, no inter-CTA waiting ---------------------------------------------
 //   scan_maps_kernel   every tile, in parallel: classify (safe binade e / hard) from the approximate prefix and,
 //                      for safe tiles, reduce the tile to its composed parity map
@@ -944,7 +1019,14 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, int in_kind, dou
     PFB_LAUNCH_OK("tile_stats_kernel");
   }
   // 2. approximate prefix of the tile sums (one CTA; one warp per run when batched)
-  if (n_runs == 1) {
+  if (n_runs == 1 && ntiles > 8192) {
+    const int nchunks = (int)((ntiles + 1023) / 1024);  // (<= 2^20 tiles for 2^31 particles: 1024 chunks)
+    double* part = W.partials;
+    if (scaled) tile_prefix_max_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, part);
+    tile_prefix_local_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr, scaled ? 1 : 0, nchunks, part);
+    tile_prefix_carry_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, nchunks, part);
+    PFB_LAUNCH_OK("tile_prefix_local_kernel");
+  } else if (n_runs == 1) {
     tile_prefix_kernel<<<1, 1024, 0, st>>>(ts, ntiles, from_log ? stats + PFB_STAT_MAX : nullptr, scaled ? 1 : 0);
     PFB_LAUNCH_OK("tile_prefix_kernel");
   } else {
