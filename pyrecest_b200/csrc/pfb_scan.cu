@@ -901,6 +901,163 @@ __global__ void __launch_bounds__(kThreads) scan_chain_kernel(int64_t n, const d
   }
 }
 
+// ---- the chain of long inputs, with the stretches taken out of the serial part ---------------------------------------
+// scan_chain_kernel spends ~6 us per stretch of safe tiles (probe, composition pass, write-back pass) on top of every
+// hard tile's own walk.  None of that depends on the running value: the increment of a tie-free safe tile is the plain
+// integer aggE (aggE == aggO), so the sum of the increments since the last hard tile is a segmented prefix over all
+// tiles, made by two parallel launches ahead of the chain (tiles with a tie count as hard: hard_tile_walk handles any
+// tile).  The serial kernel then only walks the hard tiles in order (the stretch before each is ONE addition), and a
+// last parallel launch turns (value after the preceding hard tile, increments since) into every safe tile's start.
+//   columns reused after scan_maps (exact mode reads neither again):  tsum -> rel[t]  int64 increments since the last
+//   break before t;  aggO -> pb[t]  tile index of that break;  aprefix -> the list of breaks in order.
+struct SegVal {
+  long long s;   // sum of aggE since the last break (saturating)
+  long long lb;  // tile index of the last break, -1: none yet
+  long long c;   // number of breaks
+};
+__device__ __forceinline__ SegVal seg_then(SegVal a, SegVal b) {  // a first, then b
+  SegVal r;
+  r.s = b.lb >= 0 ? b.s : sat(a.s + b.s);
+  r.lb = b.lb >= 0 ? b.lb : a.lb;
+  r.c = a.c + b.c;
+  return r;
+}
+__device__ __forceinline__ SegVal seg_shfl_up(SegVal v, int o) {
+  SegVal t;
+  t.s = __shfl_up_sync(0xffffffffu, v.s, o);
+  t.lb = __shfl_up_sync(0xffffffffu, v.lb, o);
+  t.c = __shfl_up_sync(0xffffffffu, v.c, o);
+  return t;
+}
+// prefix inside chunks of 1024 tiles; part[3 b ..] = the chunk's total
+__global__ void __launch_bounds__(1024) scan_seg_local_kernel(TileState ts, int64_t ntiles, long long* __restrict__ part) {
+  __shared__ long long s_w[3 * 33];
+  long long* cls = reinterpret_cast<long long*>(ts.flagB);
+  long long* rel = reinterpret_cast<long long*>(ts.tsum);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  SegVal v{0, -1, 0};
+  if (t < ntiles) {
+    const long long c = cls[t];
+    const bool brk = c == kHardTile || cls_has_tie(c);
+    if (brk && c != kHardTile) cls[t] = kHardTile;  // a tile with a tie is walked by the chain like a hard one
+    if (brk) { v.s = 0; v.lb = t; v.c = 1; } else { v.s = sat(ts.aggE[t]); }
+  }
+  SegVal inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const SegVal x = seg_shfl_up(inc, o);
+    if (lane >= o) inc = seg_then(x, inc);
+  }
+  if (lane == 31) { s_w[3 * warp] = inc.s; s_w[3 * warp + 1] = inc.lb; s_w[3 * warp + 2] = inc.c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive prefix over the 32 warp totals, in order
+    SegVal run{0, -1, 0};
+    for (int w = 0; w < 32; ++w) {
+      const SegVal cur{s_w[3 * w], s_w[3 * w + 1], s_w[3 * w + 2]};
+      s_w[3 * w] = run.s; s_w[3 * w + 1] = run.lb; s_w[3 * w + 2] = run.c;
+      run = seg_then(run, cur);
+    }
+    part[3 * blockIdx.x] = run.s; part[3 * blockIdx.x + 1] = run.lb; part[3 * blockIdx.x + 2] = run.c;
+  }
+  __syncthreads();
+  SegVal exc = seg_shfl_up(inc, 1);
+  if (lane == 0) exc = SegVal{0, -1, 0};
+  const SegVal wp{s_w[3 * warp], s_w[3 * warp + 1], s_w[3 * warp + 2]};
+  exc = seg_then(wp, exc);
+  if (t < ntiles) {
+    rel[t] = exc.s;
+    ts.aggO[t] = exc.lb;                                  // (-1: no break before t inside this chunk)
+    ts.aggE[t] = v.c ? -(exc.c + 1) : ts.aggE[t];          // a break remembers its rank inside the chunk (negative: never a sum)
+  }
+}
+// carries across the chunks; the ordered list of breaks; part[3 nchunks] <- number of breaks
+__global__ void __launch_bounds__(1024) scan_seg_carry_kernel(TileState ts, int64_t ntiles, int nchunks,
+                                                              long long* __restrict__ part) {
+  __shared__ long long s_c[3];
+  long long* cls = reinterpret_cast<long long*>(ts.flagB);
+  long long* rel = reinterpret_cast<long long*>(ts.tsum);
+  long long* blist = reinterpret_cast<long long*>(ts.aprefix);
+  if (threadIdx.x == 0) {
+    SegVal run{0, -1, 0};
+    for (int c = 0; c < (int)blockIdx.x; ++c) run = seg_then(run, SegVal{part[3 * c], part[3 * c + 1], part[3 * c + 2]});
+    s_c[0] = run.s; s_c[1] = run.lb; s_c[2] = run.c;
+    if (blockIdx.x == (unsigned)nchunks - 1) {
+      const SegVal all = seg_then(run, SegVal{part[3 * blockIdx.x], part[3 * blockIdx.x + 1], part[3 * blockIdx.x + 2]});
+      part[3 * nchunks] = all.c;
+      part[3 * nchunks + 1] = all.s;   // increments after the last break
+    }
+  }
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (t >= ntiles) return;
+  if (ts.aggO[t] < 0) {  // no break before t inside the chunk: the carry's
+    rel[t] = sat(s_c[0] + rel[t]);
+    ts.aggO[t] = s_c[1];
+  }
+  if (cls[t] == kHardTile) blist[s_c[2] + (-ts.aggE[t] - 1)] = t;
+}
+// safe tiles: start value = (value after the preceding break, in ulps of the tile's binade) + increments since
+__global__ void __launch_bounds__(1024) scan_seg_apply_kernel(TileState ts, int64_t ntiles, unsigned int* err) {
+  const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
+  const long long* rel = reinterpret_cast<const long long*>(ts.tsum);
+  const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (t >= ntiles) return;
+  const long long c = cls[t];
+  if (c == kHardTile) return;
+  const int e = (int)c;
+  const long long pb = ts.aggO[t];
+  bool ok = pb >= 0;
+  const long long S0 = ok ? int_of(ts.inclB[pb], e, &ok) : 0;
+  const long long S = S0 + rel[t];
+  if (!ok) atomicOr(err, 4u);                              // the tile's binade is not the running value's
+  if (S >= 0x0020000000000000LL) atomicOr(err, 2u);        // a safe stretch left its binade: bound violated
+  ts.inclB[t] = (double)S * ulp_value(e - 52);
+}
+// the serial part: the breaks in order; inclB[b] <- the exact value AFTER tile b
+template <int IN>
+__global__ void __launch_bounds__(kThreads) scan_chain_seg_kernel(int64_t n, const double* __restrict__ in,
+                                                                  double* __restrict__ cdf, double* stats, TileState ts,
+                                                                  int64_t ntiles, const long long* __restrict__ part,
+                                                                  int nchunks, unsigned int* err,
+                                                                  const double* __restrict__ wpart) {
+  __shared__ long long s_ll[72];
+  __shared__ int s_int[40];
+  __shared__ double s_cur;
+  const long long* cls = reinterpret_cast<const long long*>(ts.flagB);
+  const long long* rel = reinterpret_cast<const long long*>(ts.tsum);
+  const long long* blist = reinterpret_cast<const long long*>(ts.aprefix);
+  const long long nb = part[3 * nchunks];
+  double cur = 0.0;
+  long long prev = -1;
+  for (long long k = 0; k < nb; ++k) {
+    const long long b = blist[k];
+    if (b > prev + 1) {  // the stretch of safe tiles before this break: one addition
+      const int e = (int)cls[prev + 1];
+      bool ok;
+      const long long S0 = int_of(cur, e, &ok);
+      const long long Send = S0 + rel[b];
+      if (threadIdx.x == 0) {
+        if (!ok) atomicOr(err, 1u);
+        if (Send >= 0x0020000000000000LL) atomicOr(err, 2u);
+      }
+      cur = (double)Send * ulp_value(e - 52);
+    }
+    double p[kItems], c[kItems];
+    load_tile<IN>(in, n, b, IN != kInW ? ts.tmax[b] : 0.0, p, wpart);
+    const int64_t left = n - b * kScanTile;
+    const int cnt = (int)(left < kScanTile ? left : kScanTile);
+    cur = hard_tile_walk(p, cnt, cur, c, s_ll, s_int, &s_cur, b == 0);
+    store_tile(cdf, n, b, c);
+    if (threadIdx.x == 0) {
+      ts.inclB[b] = cur;
+      if (b * kScanTile + cnt == n) stats[PFB_STAT_TOTAL] = cur;
+    }
+    prev = b;
+    __syncthreads();
+  }
+}
+
 template <bool EXACT, int IN>
 __global__ void __launch_bounds__(kThreads) scan_final_kernel(int64_t n, const double* __restrict__ in,
                                                               double* __restrict__ cdf, double* stats, TileState ts,
@@ -1041,9 +1198,21 @@ static int scan_impl(int32_t mode, int64_t n, const double* in, int in_kind, dou
   const double* wp = W.wpart;
   if (mode == PFB_SCAN_SEQEXACT) {
     const int rg = (int)(n_runs < (int64_t)sm_count() * 8 ? n_runs : (int64_t)sm_count() * 8);
+    // long single inputs: the stretches of safe tiles leave the serial chain (scan_seg_* above)
+    static const int64_t seg_min = getenv("PFB_SCAN_SEG_MIN") ? atoll(getenv("PFB_SCAN_SEG_MIN")) : 8192;
+    const bool seg = n_runs == 1 && ntiles > seg_min;
+    const int nchunks = (int)((ntiles + 1023) / 1024);
+    long long* spart = reinterpret_cast<long long*>(W.partials);
 #define PFB_SCAN_EXACT(IN)                                                                            \
     scan_maps_kernel<IN><<<tg, kThreads, 0, st>>>(n, in, ts, ntiles, tpr, margin, wp);                \
-    scan_chain_kernel<IN><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err, wp);      \
+    if (seg) {                                                                                        \
+      scan_seg_local_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, spart);                             \
+      scan_seg_carry_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, nchunks, spart);                    \
+      scan_chain_seg_kernel<IN><<<1, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, spart, nchunks, err, wp); \
+      scan_seg_apply_kernel<<<nchunks, 1024, 0, st>>>(ts, ntiles, err);                               \
+    } else {                                                                                          \
+      scan_chain_kernel<IN><<<rg, kThreads, 0, st>>>(n, in, cdf, stats, ts, n_runs, tpr, err, wp);    \
+    }                                                                                                 \
     scan_final_kernel<true, IN><<<tg, kThreads, 0, st>>>(n, in, cdf, stats, ts, ntiles, wp);
     if (scaled) { PFB_SCAN_EXACT(kInScaled) } else if (from_log) { PFB_SCAN_EXACT(kInLog) } else { PFB_SCAN_EXACT(kInW) }
 #undef PFB_SCAN_EXACT
