@@ -107,7 +107,11 @@ class Engine:
             self._tile_stats_key = None if logw is None else (logw.data_ptr(), n, st.data_ptr(), False)
         L.check(self.lib.pfb_scan_cdf(mode, n, _ptr(w), _ptr(logw), _ptr(cdf), _ptr(st), ws, wsb,
                                       _stream(self.device)))
-        self.launches += (4 if exact else 2) + 1  # tile_combine | tile_stats, tile_prefix, maps + chain + final | final
+        # tile_combine | tile_stats; tile_prefix (2 launches for long inputs, +1 for the exponent maximum of scaled
+        # weights); exact: maps + chain + final, long inputs also the 3 segment launches around the chain; fast: final
+        long_input = (n + 2047) // 2048 > 8192
+        scaled = bool(mode & L.SCAN_SLICE_SCALED)
+        self.launches += 1 + ((2 + (1 if scaled else 0)) if long_input else 1) + ((3 + (3 if long_input else 0)) if exact else 1)
 
     def resample(self, cdf, u, x_in, x_out, n_out, dim, systematic=False, idx_out=None, est_kind=L.EST_NONE,
                  est_out=None, x_in_stride=0):
@@ -149,7 +153,7 @@ class Engine:
         L.check(self.lib.pfb_resample_msort(dt, dim, n, n_out, _ptr(cdf), seed, offset, _ptr(x_in), x_in_stride,
                                             _ptr(x_out), _ptr(idx_out), est_kind, _ptr(est_out), ws, wsb,
                                             _stream(self.device)))
-        self.launches += 4  # count tree, record build + fill, resample
+        self.launches += 3  # count tree, source ranges of the coarse bins, resample
 
     def msort_uniforms(self, out, seed, offset):
         ws, wsb = self._ensure_ws(0)
